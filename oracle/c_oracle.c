@@ -1,0 +1,247 @@
+/* C restatement of MLMC_RSCAM's per-level coupled sampler.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library, and only as the checker or the timed CPU baseline.  The product
+ * (libmlmcb.so, CUDA) never links or calls it.
+ *
+ * Parity status: PINNED through oracle/np_oracle.py, which is bit-identical to the unmodified
+ * reference for a given np.random.seed (tests/test_oracle_vs_reference.py) and to the golden
+ * fixtures in tests/golden/ generated from the reference.  This file is checked against
+ * np_oracle on replayed draws (bit-exact for GBM: IEEE double, same operation order, built
+ * with -ffp-contract=off; <= 4 ulp for Merton because libm exp() and numpy's exp may differ
+ * in the last bit).
+ *
+ * Citations ":NNN" are line numbers of /root/reference/MLMC_RSCAM.py.  Expression order is
+ * the reference's left-to-right Python evaluation order, kept on purpose.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+
+typedef struct {
+    double X0, K, T, r, sig, drift;          /* Option :796-813, GBM_Option :1330-1347      */
+    double lam, jumpmean, jumpstd;           /* Merton_Option :1273-1296                    */
+    double beta;                             /* Lookback offset constant :1443 / :1691      */
+    double disc;                             /* np.exp(-r*T) as evaluated by the caller :80 */
+    double J_bar;                            /* np.exp(jumpmean+0.5*jumpstd**2)-1 :1291     */
+} orc_params;
+
+enum { ORC_GBM = 0, ORC_MERTON = 1 };
+enum { ORC_EURO = 0, ORC_ASIAN = 1, ORC_LOOKBACK = 2, ORC_DIGITAL = 3 };
+
+static int64_t ipow(int M, int l) { int64_t n = 1; for (int i = 0; i < l; ++i) n *= M; return n; }
+
+/* GBM_Option.sde :1363  mu*X*dt + sig*X*dW */
+static inline double gbm_inc(double mu, double sig, double X, double dt, double dW) {
+    return mu * X * dt + sig * X * dW;
+}
+/* Merton_Option.sde :1314-1315 */
+static inline double mjd_inc(double c, double sig, double X, double dt, double dW, double dJ) {
+    double dx = c * X * dt + sig * X * dW;
+    return dx + (dx + X) * dJ;
+}
+
+/* EA_payoff :79-85, Lookback_payoff :105-111, Digital_payoff :131-135 */
+static inline double payoff_of(const orc_params *p, int payoff, double X, double Mn, double look_c) {
+    switch (payoff) {
+    case ORC_EURO:
+    case ORC_ASIAN: { double v = X - p->K; v = v > 0 ? v : 0; return p->disc * v; }
+    case ORC_LOOKBACK: return p->disc * (X - Mn * look_c);
+    default: return p->disc * p->K * (X > p->K ? 1.0 : 0.0);
+    }
+}
+
+/* A normal source: either a replayed array with a stride, or an internal generator. */
+typedef struct { uint64_t s[4]; int have; double spare; } orc_rng;
+static inline uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+static uint64_t splitmix(uint64_t *x) {
+    uint64_t z = (*x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static void rng_seed(orc_rng *g, uint64_t seed, uint64_t stream) {
+    uint64_t x = seed * 0xD1342543DE82EF95ull + stream;
+    for (int i = 0; i < 4; ++i) g->s[i] = splitmix(&x);
+    g->have = 0;
+}
+static inline uint64_t rng_next(orc_rng *g) {   /* xoshiro256++ */
+    uint64_t *s = g->s, r = rotl(s[0] + s[3], 23) + s[0], t = s[1] << 17;
+    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45);
+    return r;
+}
+static inline double rng_u01(orc_rng *g) { return ((rng_next(g) >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+static inline double rng_normal(orc_rng *g) {   /* Box-Muller, both branches used */
+    if (g->have) { g->have = 0; return g->spare; }
+    double u1 = rng_u01(g), u2 = rng_u01(g);
+    double r = sqrt(-2.0 * log(u1)), a = 6.283185307179586476925 * u2;
+    g->spare = r * sin(a); g->have = 1;
+    return r * cos(a);
+}
+
+/* ---- one coupled GBM path: diffusion_path :320-349, _avg :351-386, _min :388-426 -------- */
+static void gbm_one(const orc_params *p, int payoff, int l, int M, int64_t nsteps,
+                    const double *Z, int64_t zstride, orc_rng *g, double *Pf, double *Pc) {
+    const double T = p->T, X0 = p->X0, mu = p->r + p->drift, sig = p->sig;
+    const double dt = T / (double)nsteps, sqrt_dt = sqrt(dt);
+    double Xf = X0, Xc = X0, dWc = 0.0;
+    double Af = 0.5 * dt * Xf, Ac = 0.5 * M * dt * Xc;             /* :369-370 */
+    double Mf = X0, Mc = X0;                                       /* :411-412 */
+    for (int64_t j = 1; j <= nsteps; ++j) {
+        double z = Z ? Z[(j - 1) * zstride] : rng_normal(g);
+        double dWf = z * sqrt_dt;                                  /* :343 */
+        dWc = dWc + dWf;                                           /* :344 */
+        Xf += gbm_inc(mu, sig, Xf, dt, dWf);                       /* :345 */
+        if (payoff == ORC_ASIAN) Af += Xf * dt;                    /* :377 */
+        if (payoff == ORC_LOOKBACK) Mf = Xf < Mf ? Xf : Mf;        /* :420 */
+        if (j % M == 0) {
+            Xc += gbm_inc(mu, sig, Xc, M * dt, dWc);               /* :347 */
+            if (payoff == ORC_ASIAN) Ac += Xc * M * dt;            /* :380 */
+            if (payoff == ORC_LOOKBACK) Mc = Xc < Mc ? Xc : Mc;    /* :423 */
+            dWc = 0.0;                                             /* :348 */
+        }
+    }
+    double vf = Xf, vc = Xc;
+    if (payoff == ORC_ASIAN) {
+        Af -= 0.5 * Xf * dt;                                       /* :383 */
+        Ac -= 0.5 * Xc * M * dt;                                   /* :384 */
+        vf = Af / T; vc = Ac / T;                                  /* :386 */
+    }
+    double cf = 1 - p->beta * sig * sqrt(dt), cc = 1 - p->beta * sig * sqrt(M * dt);   /* :105 :110 */
+    *Pf = payoff_of(p, payoff, vf, Mf, cf);
+    *Pc = (l == 0) ? vc : payoff_of(p, payoff, vc, Mc, cc);        /* l==0: raw coarse output :82 */
+}
+
+/* ---- one coupled Merton path: JD_path :428-492, _avg :494-571, _min :573-651 ------------ */
+typedef struct { const double *zW, *zQ, *E; int64_t iw, iq, ie; orc_rng *g; double scale; } jd_src;
+static inline double src_w(jd_src *s) { return s->zW ? s->zW[s->iw++] : rng_normal(s->g); }
+static inline double src_q(jd_src *s) { return s->zQ ? s->zQ[s->iq++] : rng_normal(s->g); }
+static inline double src_e(jd_src *s) { return s->E ? s->E[s->ie++] : -log(rng_u01(s->g)) * s->scale; }
+
+static void mjd_one(const orc_params *p, int payoff, int l, int M, int64_t nsteps, jd_src *s,
+                    double *Pf, double *Pc) {
+    const double T = p->T, X0 = p->X0, sig = p->sig, c = p->r - p->lam * p->J_bar;
+    double dWc = 0, tau = 0, tf = 0, tc = 0, dtc = 0, Sf = X0, Sc = X0;
+    double avg_f = 0, avg_c = 0, mf = X0, mc = X0;
+    tau += src_e(s);                                               /* :454 */
+    for (int64_t j = 1; j <= nsteps; ++j) {
+        double tn = (double)j * T / (double)nsteps;                /* :456 */
+        while (tau < tn) {                                         /* :457 */
+            double dt = tau - tf;
+            dtc += dt;
+            double dWf = src_w(s) * sqrt(dt);                      /* :460 */
+            dWc += dWf;
+            double dJ = exp(p->jumpmean + p->jumpstd * src_q(s)) - 1;      /* :462 */
+            if (payoff == ORC_ASIAN) {                             /* :532-540 */
+                avg_f += 0.5 * dt * Sf;  Sf += mjd_inc(c, sig, Sf, dt, dWf, 0.0);
+                avg_f += 0.5 * dt * Sf;  Sf += Sf * dJ;
+                avg_c += 0.5 * dtc * Sc; Sc += mjd_inc(c, sig, Sc, dtc, dWc, 0.0);
+                avg_c += 0.5 * dtc * Sc; Sc += Sc * dJ;
+            } else {                                               /* :465-468 */
+                Sf += mjd_inc(c, sig, Sf, dt, dWf, dJ);
+                Sc += mjd_inc(c, sig, Sc, dtc, dWc, dJ);
+                if (payoff == ORC_LOOKBACK) { mf = Sf < mf ? Sf : mf; mc = Sc < mc ? Sc : mc; }  /* :621-622 */
+            }
+            dWc = 0; dtc = 0; tf = tau; tc = tau;                  /* :470-473 */
+            tau += src_e(s);                                       /* :474 */
+        }
+        double dt = tn - tf;                                       /* :477 */
+        dtc += dt;
+        double dWf = src_w(s) * sqrt(dt);                          /* :479 */
+        dWc += dWf;
+        if (payoff == ORC_ASIAN) {                                 /* :554-556 */
+            avg_f += 0.5 * dt * Sf; Sf += mjd_inc(c, sig, Sf, dt, dWf, 0.0); avg_f += 0.5 * dt * Sf;
+        } else {
+            Sf += mjd_inc(c, sig, Sf, dt, dWf, 0.0);               /* :481 */
+        }
+        tf = tn;
+        if (payoff == ORC_LOOKBACK) mf = Sf < mf ? Sf : mf;        /* :637 */
+        if (j % M == 0) {
+            if (payoff == ORC_ASIAN) {                             /* :560-562 */
+                avg_c += 0.5 * dtc * Sc; Sc += mjd_inc(c, sig, Sc, dtc, dWc, 0.0); avg_c += 0.5 * dtc * Sc;
+            } else {
+                Sc += mjd_inc(c, sig, Sc, dtc, dWc, 0.0);          /* :484 */
+                if (payoff == ORC_LOOKBACK) mc = Sc < mc ? Sc : mc;        /* :640 */
+            }
+            tc = tn; dtc = 0; dWc = 0;
+        }
+    }
+    (void)tc;
+    double vf = Sf, vc = Sc;
+    if (payoff == ORC_ASIAN) { vf = avg_f / T; vc = avg_c / T; }   /* :571 */
+    double dtg = T / (double)nsteps;                               /* Lookback_payoff :102 */
+    double cf = 1 - p->beta * sig * sqrt(dtg), cc = 1 - p->beta * sig * sqrt(M * dtg);
+    *Pf = payoff_of(p, payoff, vf, mf, cf);
+    *Pc = (l == 0) ? vc : payoff_of(p, payoff, vc, mc, cc);
+}
+
+/* ---- replay entry points ---------------------------------------------------------------- */
+int orc_gbm_replay(const orc_params *p, int payoff, int l, int M, int64_t n,
+                   const double *Z /* [M**l][n], step-major as np.random.randn(N_loop) per step */,
+                   double *Pf, double *Pc) {
+    int64_t nsteps = ipow(M, l);
+    for (int64_t i = 0; i < n; ++i) gbm_one(p, payoff, l, M, nsteps, Z + i, n, NULL, Pf + i, Pc + i);
+    return 0;
+}
+
+int orc_merton_replay(const orc_params *p, int payoff, int l, int M, int64_t n,
+                      const double *zW, const int64_t *offW, const double *zQ, const int64_t *offQ,
+                      const double *E, const int64_t *offE, double *Pf, double *Pc) {
+    int64_t nsteps = ipow(M, l);
+    for (int64_t i = 0; i < n; ++i) {
+        jd_src s = { zW, zQ, E, offW[i], offQ[i], offE[i], NULL, 1.0 / p->lam };
+        mjd_one(p, payoff, l, M, nsteps, &s, Pf + i, Pc + i);
+    }
+    return 0;
+}
+
+/* ---- Option.looper :919-957 with an internal generator (xoshiro256++ / Box-Muller) ------ *
+ * Statistical twin of the reference level function for sample counts the Python loops cannot
+ * reach, and the multi-threaded "C port" CPU baseline (pthreads; this image's gcc has no
+ * libgomp).  out7 row order :955; l==0 row :949.  Thread t takes a contiguous slice of path
+ * ids and the partial rows are added in thread order, so the result is deterministic.      */
+typedef struct {
+    const orc_params *p; int model, payoff, l, M; int64_t nsteps, lo, hi; uint64_t seed; double a[7];
+} orc_job;
+
+static void *orc_worker(void *arg) {
+    orc_job *jb = (orc_job *)arg;
+    double *a = jb->a;
+    for (int k = 0; k < 7; ++k) a[k] = 0;
+    for (int64_t i = jb->lo; i < jb->hi; ++i) {
+        orc_rng g; rng_seed(&g, jb->seed, (uint64_t)i + ((uint64_t)jb->l << 48));
+        double Pf, Pc;
+        if (jb->model == ORC_GBM) gbm_one(jb->p, jb->payoff, jb->l, jb->M, jb->nsteps, NULL, 0, &g, &Pf, &Pc);
+        else {
+            jd_src s = { NULL, NULL, NULL, 0, 0, 0, &g, 1.0 / jb->p->lam };
+            mjd_one(jb->p, jb->payoff, jb->l, jb->M, jb->nsteps, &s, &Pf, &Pc);
+        }
+        if (jb->l == 0) { a[0] += Pf; a[1] += Pf * Pf; a[2] += Pf; a[3] += Pf * Pf; }
+        else {
+            double d = Pf - Pc;
+            a[0] += d; a[1] += d * d; a[2] += Pf; a[3] += Pf * Pf; a[4] += Pc; a[5] += Pc * Pc; a[6] += Pc * Pf;
+        }
+    }
+    return NULL;
+}
+
+int orc_level_sums(const orc_params *p, int model, int payoff, int l, int M, int64_t n,
+                   uint64_t seed, int nthreads, double *out7) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    orc_job jobs[256]; pthread_t th[256];
+    int64_t nsteps = ipow(M, l);
+    for (int t = 0; t < nthreads; ++t) {
+        orc_job jb = { p, model, payoff, l, M, nsteps, n * t / nthreads, n * (t + 1) / nthreads, seed, {0} };
+        jobs[t] = jb;
+    }
+    for (int t = 1; t < nthreads; ++t) pthread_create(&th[t], NULL, orc_worker, &jobs[t]);
+    orc_worker(&jobs[0]);
+    for (int t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
+    for (int k = 0; k < 7; ++k) { double v = 0; for (int t = 0; t < nthreads; ++t) v += jobs[t].a[k]; out7[k] = v; }
+    return 0;
+}
+
+int orc_max_threads(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }
