@@ -1,0 +1,122 @@
+/* mlmcb.h - C ABI of libmlmcb.so, the B200 (sm_100a) per-level coupled sampler.
+ *
+ * Drop-in boundary for ONE path of mckeownish/Multilevel_MC_SDEs (MLMC_RSCAM.py): the level
+ * function `Option.looper(Nl,l,M,anti,Npl)` (:919-957) with everything below it
+ * (`payoff` :62-136, `(diffusion|JD)_path(_avg|_min)` :320-651, `sde` :1298-1315 / :1349-1363,
+ * numpy RNG).  The reference has no FFI of its own (pure Python); these entry points are what
+ * a ctypes binding on the reference side would call - see INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; `d_` = device pointer (valid on `device`),
+ * `h_` = host pointer; every function returns 0 on success or a negative MLMCB_E* code and
+ * never throws; mlmcb_last_error() gives the text for the calling thread.  All launches are
+ * asynchronous on `cuda_stream` (a cudaStream_t / CUstream, NULL = default stream) unless the
+ * name ends in `_host`, which synchronises that stream before returning.
+ * There is NO CPU fallback: without a CUDA device every compute call fails with MLMCB_ECUDA.
+ */
+#ifndef MLMCB_H
+#define MLMCB_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Parameter struct = the attributes the reference classes carry
+ * (Option.__init__ :796-813, GBM_Option.__init__ :1330-1347, Merton_Option.__init__ :1273-1296,
+ *  Lookback beta :1443/:1691).  `disc` and `J_bar` are the two derived constants the reference
+ * evaluates with numpy (np.exp(-r*T) :80, np.exp(jumpmean+0.5*jumpstd**2)-1 :1291); a caller
+ * that wants replay results bit-identical to numpy passes numpy's values, anyone else calls
+ * mlmcb_params_fill_derived(). */
+typedef struct mlmcb_params {
+    double X0, K, T, r, sig, drift;
+    double lam, jumpmean, jumpstd;
+    double beta;
+    double disc;
+    double J_bar;
+} mlmcb_params;
+
+enum { MLMCB_GBM = 0, MLMCB_MERTON = 1 };                                   /* model   */
+enum { MLMCB_EURO = 0, MLMCB_ASIAN = 1, MLMCB_LOOKBACK = 2, MLMCB_DIGITAL = 3 };  /* payoff */
+
+/* flags for the Philox-mode level function */
+enum {
+    MLMCB_SAMPLER_F32BM = 0,   /* default: 32-bit uniforms, fp32 Box-Muller, promoted to fp64      */
+    MLMCB_SAMPLER_F64BM = 1,   /* canonical: 53-bit uniforms, fp64 Box-Muller (log/sqrt/sincospi)  */
+    MLMCB_SAMPLER_MASK  = 0xF,
+    MLMCB_FP32_PATHS    = 0x10 /* opt-in: path arithmetic in fp32 (sums stay fp64)                 */
+};
+/* arithmetic policy for replay */
+enum {
+    MLMCB_ARITH_FAST  = 0,     /* production arithmetic (FMA form), the one Philox mode uses       */
+    MLMCB_ARITH_EXACT = 1      /* reference expression order, no contraction: bit-exact vs numpy   */
+};
+
+enum { MLMCB_OK = 0, MLMCB_EINVAL = -1, MLMCB_ECUDA = -2, MLMCB_ENOTIMPL = -3 };
+
+/* ---- the level function (replaces Option.looper :919-957, anti=False) --------------------
+ * Simulates coupled paths with global ids [path_offset, path_offset+n_paths) at level l
+ * (M**l fine steps, M**(l-1) coarse) and writes the seven sums in the reference's row order
+ * (:955)  [sum dP, sum dP^2, sum Pf, sum Pf^2, sum Pc, sum Pc^2, sum Pf*Pc];  at l==0
+ * [sum Pf, sum Pf^2, sum Pf, sum Pf^2, 0, 0, 0] (:949).  Randomness is Philox4x32-10 addressed
+ * by (seed, l, global path id, draw index): disjoint id ranges give independent samples, the
+ * same id range gives the same samples on any GPU count.  d_Pf / d_Pc (each n_paths doubles)
+ * are optional per-path outputs = what Option.payoff (:62-136) returns; pass NULL to skip.
+ * The result is deterministic for a given (arguments, GPU model).                           */
+int mlmcb_level_sums(const mlmcb_params* p, int model, int payoff, int l, int M,
+                     uint64_t n_paths, uint64_t seed, uint64_t path_offset, int flags,
+                     int device, void* cuda_stream,
+                     double* d_out7, double* d_Pf, double* d_Pc);
+
+/* Same, result delivered to HOST memory (h_out7[7]); launch + 56-byte D2H + stream sync.
+ * This is the call `Option.looper` makes. */
+int mlmcb_level_sums_host(const mlmcb_params* p, int model, int payoff, int l, int M,
+                          uint64_t n_paths, uint64_t seed, uint64_t path_offset, int flags,
+                          int device, void* cuda_stream, double* h_out7);
+
+/* One sweep of Option.mlmc's inner `for l in range(L+1)` (:994-997): n_levels independent
+ * level calls issued concurrently (internal side streams), one D2H of h_out[n_levels][7].
+ * levels[i] is the level index, n_paths[i] may be 0 (row left zero).                        */
+int mlmcb_level_sweep_host(const mlmcb_params* p, int model, int payoff, int M, int n_levels,
+                           const int* levels, const uint64_t* n_paths, const uint64_t* path_offsets,
+                           uint64_t seed, int flags, int device, void* cuda_stream, double* h_out);
+
+/* ---- replay mode (parity check (a) of the north star) ------------------------------------
+ * Feeds the reference's own draws.  GBM: d_Z[step*n_paths + path] is the np.random.randn(N_loop)
+ * vector of step `step+1` (:343).  Merton: three ragged per-path streams in CSR layout, in the
+ * order the reference consumes them (:454-479): d_zW dW normals, d_zQ jump-size normals,
+ * d_E inter-arrival times (already scaled by 1/lam); d_off* have n_paths+1 entries.
+ * Outputs per path (Pf,Pc) as Option.payoff returns them (at l==0 Pc = raw coarse path value,
+ * :82) and, if d_out7 != NULL, the seven sums.                                               */
+int mlmcb_replay_gbm(const mlmcb_params* p, int payoff, int l, int M, uint64_t n_paths,
+                     const double* d_Z, int arith, int device, void* cuda_stream,
+                     double* d_Pf, double* d_Pc, double* d_out7);
+int mlmcb_replay_merton(const mlmcb_params* p, int payoff, int l, int M, uint64_t n_paths,
+                        const double* d_zW, const int64_t* d_offW,
+                        const double* d_zQ, const int64_t* d_offQ,
+                        const double* d_E, const int64_t* d_offE,
+                        int arith, int device, void* cuda_stream,
+                        double* d_Pf, double* d_Pc, double* d_out7);
+
+/* ---- test / measurement hooks ------------------------------------------------------------ */
+/* The standard normals the Philox-mode kernels use for grid steps: d_out[step*n_paths+path],
+ * step < n_steps, for global path ids path_offset.. at level l.  For distribution tests.    */
+int mlmcb_sampler_probe(int sampler, uint64_t seed, int l, uint64_t path_offset, uint64_t n_paths,
+                        uint64_t n_steps, int device, void* cuda_stream, double* d_out);
+/* Host-side Philox4x32-10 (same code the kernels use), for known-answer tests; no GPU needed. */
+void mlmcb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* Pipe micro-benchmarks used for the roofline denominators.  which: 0 DFMA, 1 DADD, 2 FFMA,
+ * 3 IMAD.WIDE (mul.wide.u32+add), 4 LOP3, 5 MUFU.LG2, 6 I2F.U32, 7 F2F.F64.F32, 8 MUFU.SIN.
+ * Returns warp-level instructions per second per GPU in *inst_per_s and the elapsed ms.      */
+int mlmcb_pipe_probe(int which, int device, double* inst_per_s, float* ms);
+/* Steps/sec the kernel's launch geometry: threads per block and resident blocks used.       */
+int mlmcb_launch_geometry(int model, int payoff, int M, int flags, int device,
+                          int* threads_per_block, int* max_blocks);
+
+void mlmcb_params_fill_derived(mlmcb_params* p);   /* disc = exp(-r*T), J_bar = exp(m+s^2/2)-1 */
+const char* mlmcb_last_error(void);
+int mlmcb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLMCB_H */

@@ -1,0 +1,507 @@
+// mlmcb_api.cu - C ABI (include/mlmcb.h) over the kernels in mlmcb_kernels.cuh.
+// Host side only: argument checking, the per-launch constant block (evaluated in the same
+// order numpy evaluates the reference's expressions), kernel selection, launch geometry,
+// stream-ordered workspace, and the pipe micro-benchmarks.  No torch types, no CPU fallback.
+#include "../../include/mlmcb.h"
+#include "mlmcb_kernels.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+using namespace mlmcb;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(MLMCB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+struct DeviceInfo { int sms = 0; bool pool_ready = false; };
+DeviceInfo g_dev[64];
+
+int device_info(int dev, DeviceInfo** out) {
+    if (dev < 0 || dev >= 64) return fail(MLMCB_EINVAL, "device %d out of range", dev);
+    DeviceInfo& d = g_dev[dev];
+    if (!d.sms) {
+        int sms = 0;
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        cudaMemPool_t pool;
+        CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long keep = ~0ull;   // keep freed workspace blocks cached in the pool
+        CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        d.sms = sms;
+    }
+    *out = &d;
+    return 0;
+}
+
+int ipow_checked(int M, int l, ull* out) {
+    ull n = 1;
+    for (int i = 0; i < l; ++i) {
+        if (n > (1ull << 40) / (ull)M) return fail(MLMCB_EINVAL, "M**l = %d**%d exceeds 2^40 fine steps", M, l);
+        n *= (ull)M;
+    }
+    *out = n;
+    return 0;
+}
+
+// The per-launch constants.  Each reference-order scalar is one IEEE double operation per
+// Python operator, in Python's evaluation order (citations: /root/reference/MLMC_RSCAM.py).
+int make_consts(const mlmcb_params* p, int model, int payoff, int l, int M, ull n_paths, ull seed,
+                ull path_offset, LevelConsts* C) {
+    if (!p) return fail(MLMCB_EINVAL, "params is NULL");
+    if (model != MLMCB_GBM && model != MLMCB_MERTON) return fail(MLMCB_EINVAL, "unknown model %d", model);
+    if (payoff < 0 || payoff > 3) return fail(MLMCB_EINVAL, "unknown payoff %d", payoff);
+    if (l < 0 || l > 255) return fail(MLMCB_EINVAL, "level %d out of range", l);
+    if (M < 2) return fail(MLMCB_EINVAL, "coarseness factor M=%d must be >= 2", M);
+    if (path_offset + n_paths >= (1ull << 48)) return fail(MLMCB_EINVAL, "path ids must stay below 2^48");
+    if (!(p->T > 0) || !(p->sig >= 0) || !(p->X0 > 0)) return fail(MLMCB_EINVAL, "need T>0, sig>=0, X0>0");
+    if (model == MLMCB_MERTON && !(p->lam >= 0)) return fail(MLMCB_EINVAL, "need lam>=0");
+    memset(C, 0, sizeof *C);
+    ull nsteps;
+    if (int rc = ipow_checked(M, l, &nsteps)) return rc;
+    C->n_paths = n_paths; C->path_offset = path_offset; C->nsteps = nsteps;
+    C->M = M; C->l = l; C->payoff = payoff; C->is_l0 = (l == 0);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { C->k0[r] = k0; C->k1[r] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
+    C->ctr3_tag = (uint32_t)l << 16;
+    const double disc = p->disc > 0 ? p->disc : exp(-p->r * p->T);                   // :80
+    C->X0 = p->X0; C->K = p->K; C->T = p->T; C->sig = p->sig;
+    C->Md = (double)M;
+    C->dt = p->T / (double)nsteps;                                                   // :334
+    C->sqrt_dt = sqrt(C->dt);                                                        // :335
+    C->Mdt = C->Md * C->dt;                                                          // M*dt :347
+    if (model == MLMCB_GBM) {
+        C->mu = p->r + p->drift;                                                     // :1347
+    } else {
+        const double J_bar = (p->J_bar == p->J_bar && p->J_bar != 0.0) ? p->J_bar
+                             : exp(p->jumpmean + 0.5 * p->jumpstd * p->jumpstd) - 1; // :1291
+        C->mu = p->r - p->lam * J_bar;                                               // :1314
+        C->lam = p->lam; C->inv_lam = 1.0 / p->lam; C->jm = p->jumpmean; C->js = p->jumpstd;
+    }
+    C->disc = disc;
+    C->discK = disc * p->K;                                                          // :131
+    C->look_cf = 1 - p->beta * p->sig * sqrt(C->dt);                                 // :105
+    C->look_cc = 1 - p->beta * p->sig * sqrt(C->Md * C->dt);                         // :110
+    C->a_f = C->mu * C->dt; C->b_f = C->sig * C->sqrt_dt; C->a_c = C->mu * C->Mdt;
+    C->avg_wf = C->dt / C->T; C->avg_wc = C->Mdt / C->T;
+    return 0;
+}
+
+int fn_of(int payoff) { return payoff == MLMCB_ASIAN ? FN_AVG : payoff == MLMCB_LOOKBACK ? FN_MIN : FN_FINAL; }
+int mt_of(int M) { return M == 2 ? 2 : M == 4 ? 4 : 0; }
+
+typedef void (*LevelKernel)(const LevelConsts, double*, unsigned*, double*, double*, double*);
+
+template <typename R, int MODEL, int FN, int SAMP>
+LevelKernel pick_mt(int mt) {
+    switch (mt) {
+    case 2: return level_kernel<R, MODEL, FN, 2, SAMP>;
+    case 4: return level_kernel<R, MODEL, FN, 4, SAMP>;
+    default: return level_kernel<R, MODEL, FN, 0, SAMP>;
+    }
+}
+template <typename R, int MODEL, int SAMP>
+LevelKernel pick_fn(int fn, int mt) {
+    switch (fn) {
+    case FN_AVG: return pick_mt<R, MODEL, FN_AVG, SAMP>(mt);
+    case FN_MIN: return pick_mt<R, MODEL, FN_MIN, SAMP>(mt);
+    default: return pick_mt<R, MODEL, FN_FINAL, SAMP>(mt);
+    }
+}
+template <typename R, int SAMP>
+LevelKernel pick_model(int model, int fn, int mt) {
+    return model == MLMCB_GBM ? pick_fn<R, 0, SAMP>(fn, mt) : pick_fn<R, 1, SAMP>(fn, mt);
+}
+LevelKernel pick_kernel(int model, int payoff, int M, int flags) {
+    const int fn = fn_of(payoff), mt = mt_of(M), samp = flags & MLMCB_SAMPLER_MASK;
+    if (flags & MLMCB_FP32_PATHS)
+        return samp == MLMCB_SAMPLER_F64BM ? pick_model<float, SAMP_F64BM>(model, fn, mt)
+                                           : pick_model<float, SAMP_F32BM>(model, fn, mt);
+    return samp == MLMCB_SAMPLER_F64BM ? pick_model<double, SAMP_F64BM>(model, fn, mt)
+                                       : pick_model<double, SAMP_F32BM>(model, fn, mt);
+}
+
+// Launch geometry: a grid-stride loop over paths.  The grid never exceeds the number of
+// co-resident blocks (148 SMs x occupancy), and is shrunk so every thread gets the same
+// number of paths (no ragged tail wave).
+template <typename K>
+int geometry(K kernel, int dev, ull n_paths, int* grid, int* max_blocks_out) {
+    DeviceInfo* d;
+    if (int rc = device_info(dev, &d)) return rc;
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    const ull max_threads = (ull)d->sms * per_sm * kThreads;
+    const ull per_thread = (n_paths + max_threads - 1) / max_threads;
+    const ull threads = per_thread ? (n_paths + per_thread - 1) / per_thread : 1;
+    ull g = (threads + kThreads - 1) / kThreads;
+    if (g < 1) g = 1;
+    *grid = (int)g;
+    if (max_blocks_out) *max_blocks_out = d->sms * per_sm;
+    return 0;
+}
+
+struct Workspace {
+    double* partials = nullptr;
+    unsigned* ticket = nullptr;
+    void* base = nullptr;
+};
+
+int ws_alloc(int grid, cudaStream_t st, Workspace* w) {
+    const size_t bytes = (size_t)grid * 8 * sizeof(double) + 256;
+    CU(cudaMallocAsync(&w->base, bytes, st));
+    w->ticket = (unsigned*)w->base;
+    w->partials = (double*)((char*)w->base + 256);
+    CU(cudaMemsetAsync(w->ticket, 0, sizeof(unsigned), st));
+    return 0;
+}
+int ws_free(Workspace* w, cudaStream_t st) {
+    CU(cudaFreeAsync(w->base, st));
+    return 0;
+}
+
+int check_flags(int flags) {
+    const int samp = flags & MLMCB_SAMPLER_MASK;
+    if (samp != MLMCB_SAMPLER_F32BM && samp != MLMCB_SAMPLER_F64BM) return fail(MLMCB_EINVAL, "unknown sampler %d", samp);
+    if (flags & ~(MLMCB_SAMPLER_MASK | MLMCB_FP32_PATHS)) return fail(MLMCB_EINVAL, "unknown flag bits 0x%x", flags);
+    return 0;
+}
+
+int level_sums_impl(const mlmcb_params* p, int model, int payoff, int l, int M, ull n_paths, ull seed,
+                    ull path_offset, int flags, int device, cudaStream_t st, double* d_out7, double* d_Pf,
+                    double* d_Pc) {
+    if (!d_out7) return fail(MLMCB_EINVAL, "d_out7 is NULL");
+    if (int rc = check_flags(flags)) return rc;
+    LevelConsts C;
+    if (int rc = make_consts(p, model, payoff, l, M, n_paths, seed, path_offset, &C)) return rc;
+    if (n_paths == 0) { CU(cudaMemsetAsync(d_out7, 0, 7 * sizeof(double), st)); return 0; }
+    LevelKernel k = pick_kernel(model, payoff, M, flags);
+    int grid = 1;
+    if (int rc = geometry(k, device, n_paths, &grid, nullptr)) return rc;
+    Workspace w;
+    if (int rc = ws_alloc(grid, st, &w)) return rc;
+    k<<<grid, kThreads, 0, st>>>(C, w.partials, w.ticket, d_out7, d_Pf, d_Pc);
+    CU(cudaGetLastError());
+    return ws_free(&w, st);
+}
+
+// pinned staging + side streams for the _host entry points (per device, created lazily)
+struct HostSide {
+    double* pinned = nullptr;      // [kMaxSweep][8]
+    double* dev = nullptr;         // same shape on the device
+    cudaStream_t side[8] = {};
+    cudaEvent_t fork = nullptr, join[8] = {};
+    bool ready = false;
+};
+constexpr int kMaxSweep = 64;
+HostSide g_host[64];
+
+int host_side(int dev, HostSide** out) {
+    HostSide& h = g_host[dev];
+    if (!h.ready) {
+        CU(cudaHostAlloc((void**)&h.pinned, kMaxSweep * 8 * sizeof(double), cudaHostAllocDefault));
+        CU(cudaMalloc((void**)&h.dev, kMaxSweep * 8 * sizeof(double)));
+        CU(cudaEventCreateWithFlags(&h.fork, cudaEventDisableTiming));
+        for (int i = 0; i < 8; ++i) {
+            CU(cudaStreamCreateWithFlags(&h.side[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&h.join[i], cudaEventDisableTiming));
+        }
+        h.ready = true;
+    }
+    *out = &h;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mlmcb_last_error(void) { return g_err; }
+int mlmcb_version(void) { return 100; }
+
+void mlmcb_params_fill_derived(mlmcb_params* p) {
+    if (!p) return;
+    p->disc = exp(-p->r * p->T);
+    p->J_bar = exp(p->jumpmean + 0.5 * p->jumpstd * p->jumpstd) - 1;
+}
+
+void mlmcb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    U4 c = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) { c = philox_round(c, k0, k1); k0 += PHILOX_W0; k1 += PHILOX_W1; }
+    out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w;
+}
+
+int mlmcb_level_sums(const mlmcb_params* p, int model, int payoff, int l, int M, uint64_t n_paths,
+                     uint64_t seed, uint64_t path_offset, int flags, int device, void* cuda_stream,
+                     double* d_out7, double* d_Pf, double* d_Pc) {
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    return level_sums_impl(p, model, payoff, l, M, n_paths, seed, path_offset, flags, device,
+                           (cudaStream_t)cuda_stream, d_out7, d_Pf, d_Pc);
+}
+
+int mlmcb_level_sums_host(const mlmcb_params* p, int model, int payoff, int l, int M, uint64_t n_paths,
+                          uint64_t seed, uint64_t path_offset, int flags, int device, void* cuda_stream,
+                          double* h_out7) {
+    if (!h_out7) return fail(MLMCB_EINVAL, "h_out7 is NULL");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    HostSide* h;
+    if (int rc = host_side(device, &h)) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (int rc = level_sums_impl(p, model, payoff, l, M, n_paths, seed, path_offset, flags, device, st, h->dev,
+                                 nullptr, nullptr))
+        return rc;
+    CU(cudaMemcpyAsync(h->pinned, h->dev, 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(h_out7, h->pinned, 7 * sizeof(double));
+    return 0;
+}
+
+int mlmcb_level_sweep_host(const mlmcb_params* p, int model, int payoff, int M, int n_levels,
+                           const int* levels, const uint64_t* n_paths, const uint64_t* path_offsets,
+                           uint64_t seed, int flags, int device, void* cuda_stream, double* h_out) {
+    if (!levels || !n_paths || !path_offsets || !h_out) return fail(MLMCB_EINVAL, "NULL array argument");
+    if (n_levels < 0 || n_levels > kMaxSweep) return fail(MLMCB_EINVAL, "n_levels=%d out of range (max %d)", n_levels, kMaxSweep);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    HostSide* h;
+    if (int rc = host_side(device, &h)) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    // fork: side streams wait for whatever precedes on the caller's stream
+    CU(cudaEventRecord(h->fork, st));
+    CU(cudaMemsetAsync(h->dev, 0, (size_t)n_levels * 8 * sizeof(double), st));
+    CU(cudaEventRecord(h->fork, st));
+    bool used[8] = {};
+    // deepest level first: it is the longest-running launch of the sweep
+    for (int i = n_levels - 1, slot = 0; i >= 0; --i) {
+        if (n_paths[i] == 0) continue;
+        cudaStream_t s = h->side[slot & 7];
+        if (!used[slot & 7]) { CU(cudaStreamWaitEvent(s, h->fork, 0)); used[slot & 7] = true; }
+        if (int rc = level_sums_impl(p, model, payoff, levels[i], M, n_paths[i], seed, path_offsets[i], flags,
+                                     device, s, h->dev + (size_t)i * 8, nullptr, nullptr))
+            return rc;
+        ++slot;
+    }
+    for (int s = 0; s < 8; ++s) {
+        if (!used[s]) continue;
+        CU(cudaEventRecord(h->join[s], h->side[s]));
+        CU(cudaStreamWaitEvent(st, h->join[s], 0));
+    }
+    CU(cudaMemcpyAsync(h->pinned, h->dev, (size_t)n_levels * 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < n_levels; ++i) memcpy(h_out + (size_t)i * 7, h->pinned + (size_t)i * 8, 7 * sizeof(double));
+    return 0;
+}
+
+int mlmcb_replay_gbm(const mlmcb_params* p, int payoff, int l, int M, uint64_t n_paths, const double* d_Z,
+                     int arith, int device, void* cuda_stream, double* d_Pf, double* d_Pc, double* d_out7) {
+    if (!d_Z || !d_Pf || !d_Pc) return fail(MLMCB_EINVAL, "NULL device pointer");
+    if (arith != MLMCB_ARITH_FAST && arith != MLMCB_ARITH_EXACT) return fail(MLMCB_EINVAL, "unknown arith %d", arith);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    LevelConsts C;
+    if (int rc = make_consts(p, MLMCB_GBM, payoff, l, M, n_paths, 0, 0, &C)) return rc;
+    if (n_paths == 0) return 0;
+    typedef void (*K)(const LevelConsts, const double*, double*, unsigned*, double*, double*, double*);
+    static const K table[3][2] = {
+        {replay_gbm_kernel<FN_FINAL, AR_FAST>, replay_gbm_kernel<FN_FINAL, AR_EXACT>},
+        {replay_gbm_kernel<FN_AVG, AR_FAST>, replay_gbm_kernel<FN_AVG, AR_EXACT>},
+        {replay_gbm_kernel<FN_MIN, AR_FAST>, replay_gbm_kernel<FN_MIN, AR_EXACT>}};
+    K k = table[fn_of(payoff)][arith];
+    int grid = (int)((n_paths + kThreads - 1) / kThreads);
+    if (grid > 65535) grid = 65535;
+    Workspace w;
+    if (int rc = ws_alloc(grid + 1, st, &w)) return rc;
+    double* out = d_out7 ? d_out7 : w.partials;   // sums are always formed; row 0 is scratch if unwanted
+    k<<<grid, kThreads, 0, st>>>(C, d_Z, w.partials + 8, w.ticket, out, d_Pf, d_Pc);
+    CU(cudaGetLastError());
+    return ws_free(&w, st);
+}
+
+int mlmcb_replay_merton(const mlmcb_params* p, int payoff, int l, int M, uint64_t n_paths,
+                        const double* d_zW, const int64_t* d_offW, const double* d_zQ, const int64_t* d_offQ,
+                        const double* d_E, const int64_t* d_offE, int arith, int device, void* cuda_stream,
+                        double* d_Pf, double* d_Pc, double* d_out7) {
+    if (!d_zW || !d_offW || !d_zQ || !d_offQ || !d_E || !d_offE || !d_Pf || !d_Pc)
+        return fail(MLMCB_EINVAL, "NULL device pointer");
+    if (arith != MLMCB_ARITH_FAST && arith != MLMCB_ARITH_EXACT) return fail(MLMCB_EINVAL, "unknown arith %d", arith);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    LevelConsts C;
+    if (int rc = make_consts(p, MLMCB_MERTON, payoff, l, M, n_paths, 0, 0, &C)) return rc;
+    if (n_paths == 0) return 0;
+    typedef void (*K)(const LevelConsts, const double*, const long long*, const double*, const long long*,
+                      const double*, const long long*, double*, unsigned*, double*, double*, double*);
+    static const K table[3][2] = {
+        {replay_mjd_kernel<FN_FINAL, AR_FAST>, replay_mjd_kernel<FN_FINAL, AR_EXACT>},
+        {replay_mjd_kernel<FN_AVG, AR_FAST>, replay_mjd_kernel<FN_AVG, AR_EXACT>},
+        {replay_mjd_kernel<FN_MIN, AR_FAST>, replay_mjd_kernel<FN_MIN, AR_EXACT>}};
+    K k = table[fn_of(payoff)][arith];
+    int grid = (int)((n_paths + kThreads - 1) / kThreads);
+    if (grid > 65535) grid = 65535;
+    Workspace w;
+    if (int rc = ws_alloc(grid + 1, st, &w)) return rc;
+    double* out = d_out7 ? d_out7 : w.partials;
+    k<<<grid, kThreads, 0, st>>>(C, d_zW, (const long long*)d_offW, d_zQ, (const long long*)d_offQ, d_E,
+                                 (const long long*)d_offE, w.partials + 8, w.ticket, out, d_Pf, d_Pc);
+    CU(cudaGetLastError());
+    return ws_free(&w, st);
+}
+
+int mlmcb_sampler_probe(int sampler, uint64_t seed, int l, uint64_t path_offset, uint64_t n_paths,
+                        uint64_t n_steps, int device, void* cuda_stream, double* d_out) {
+    if (!d_out) return fail(MLMCB_EINVAL, "d_out is NULL");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    mlmcb_params p;
+    memset(&p, 0, sizeof p);
+    p.X0 = 1; p.K = 1; p.T = 1; p.sig = 1;
+    LevelConsts C;
+    if (int rc = make_consts(&p, MLMCB_GBM, MLMCB_EURO, 0, 2, n_paths, seed, path_offset, &C)) return rc;
+    C.ctr3_tag = (uint32_t)l << 16;
+    if (n_paths == 0 || n_steps == 0) return 0;
+    const int grid = (int)((n_paths + kThreads - 1) / kThreads);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (sampler == MLMCB_SAMPLER_F32BM) sampler_probe_kernel<SAMP_F32BM><<<grid, kThreads, 0, st>>>(C, n_steps, d_out);
+    else if (sampler == MLMCB_SAMPLER_F64BM) sampler_probe_kernel<SAMP_F64BM><<<grid, kThreads, 0, st>>>(C, n_steps, d_out);
+    else return fail(MLMCB_EINVAL, "unknown sampler %d", sampler);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mlmcb_launch_geometry(int model, int payoff, int M, int flags, int device, int* threads_per_block,
+                          int* max_blocks) {
+    if (int rc = check_flags(flags)) return rc;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    int grid = 0, mb = 0;
+    if (int rc = geometry(pick_kernel(model, payoff, M, flags), device, ~0ull >> 16, &grid, &mb)) return rc;
+    if (threads_per_block) *threads_per_block = kThreads;
+    if (max_blocks) *max_blocks = mb;
+    return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Pipe micro-benchmarks: 8 independent dependent-chains per thread of one instruction kind.
+// They give the roofline denominators MEASURED_PEAKS.json lacks (FP64 FMA issue rate) and the
+// per-pipe rates the kernel's instruction mix is budgeted against.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kProbeIters = 2048, kProbeChains = 8, kProbeUnroll = 4;
+
+template <int WHICH>
+__global__ void __launch_bounds__(256) pipe_probe_kernel(float seed, unsigned* sink) {
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+    double d[kProbeChains];
+    float f[kProbeChains];
+    unsigned u[kProbeChains];
+    unsigned long long w[kProbeChains];
+#pragma unroll
+    for (int c = 0; c < kProbeChains; ++c) {
+        d[c] = 1.0 + 1e-9 * (tid + c); f[c] = 1.0f + seed * (tid + c); u[c] = tid * 2654435761u + c; w[c] = u[c];
+    }
+    const double da = 1.0000000001, db = 1e-12;
+    const float fa = 1.0000001f, fb = seed;
+    for (int it = 0; it < kProbeIters; ++it) {
+#pragma unroll
+        for (int r = 0; r < kProbeUnroll; ++r) {
+#pragma unroll
+            for (int c = 0; c < kProbeChains; ++c) {
+                if (WHICH == 0) d[c] = fma(d[c], da, db);
+                else if (WHICH == 1) d[c] = d[c] + db;
+                else if (WHICH == 2) f[c] = fmaf(f[c], fa, fb);
+                else if (WHICH == 3) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"((unsigned)w[c]), "r"(0xD2511F53u));
+                else if (WHICH == 4) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[c]) : "r"(tid), "r"(0x9E3779B9u + it));
+                else if (WHICH == 5) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(f[c]));
+                else if (WHICH == 6) asm volatile("cvt.rn.f32.u32 %0, %1;" : "=f"(f[c]) : "r"(__float_as_uint(f[c])));
+                else if (WHICH == 7) asm volatile("{ .reg .f64 t; cvt.f64.f32 t, %0; cvt.rn.f32.f64 %0, t; }" : "+f"(f[c]));
+                else if (WHICH == 8) asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(f[c]));
+            }
+        }
+    }
+    unsigned acc = 0;
+#pragma unroll
+    for (int c = 0; c < kProbeChains; ++c) acc ^= (unsigned)d[c] ^ __float_as_uint(f[c]) ^ u[c] ^ (unsigned)w[c];
+    if (acc == 0x12345u) sink[0] = acc;
+}
+
+typedef void (*ProbeKernel)(float, unsigned*);
+ProbeKernel probe_of(int which) {
+    switch (which) {
+    case 0: return pipe_probe_kernel<0>;
+    case 1: return pipe_probe_kernel<1>;
+    case 2: return pipe_probe_kernel<2>;
+    case 3: return pipe_probe_kernel<3>;
+    case 4: return pipe_probe_kernel<4>;
+    case 5: return pipe_probe_kernel<5>;
+    case 6: return pipe_probe_kernel<6>;
+    case 7: return pipe_probe_kernel<7>;
+    case 8: return pipe_probe_kernel<8>;
+    default: return nullptr;
+    }
+}
+
+}  // namespace
+
+extern "C" int mlmcb_pipe_probe(int which, int device, double* inst_per_s, float* ms_out) {
+    ProbeKernel k = probe_of(which);
+    if (!k) return fail(MLMCB_EINVAL, "unknown probe %d", which);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    DeviceInfo* d;
+    if (int rc = device_info(device, &d)) return rc;
+    unsigned* sink;
+    CU(cudaMalloc((void**)&sink, 4));
+    const int grid = d->sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    k<<<grid, threads>>>(1e-7f, sink);   // warm-up
+    CU(cudaEventRecord(e0));
+    k<<<grid, threads>>>(1e-7f, sink);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    CU(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    // F2F probe issues two conversions per chain step
+    const double per_step = which == 7 ? 2.0 : 1.0;
+    const double warp_insts = (double)grid * (threads / 32) * kProbeIters * kProbeUnroll * kProbeChains * per_step;
+    if (inst_per_s) *inst_per_s = warp_insts / (ms * 1e-3);
+    if (ms_out) *ms_out = ms;
+    return 0;
+}

@@ -1,0 +1,660 @@
+// mlmcb_kernels.cuh - device code of the B200 per-level coupled sampler (sm_100a).
+//
+// One thread simulates one coupled fine/coarse Euler-Maruyama path at a time, entirely in
+// registers: Philox4x32-10 counter-based draws -> normals -> fine step every draw, coarse
+// step every M draws with the summed Brownian increment -> path functional (final / trapezoid
+// average / running minimum) -> payoff -> the seven looper sums, reduced warp-shuffle ->
+// shared memory -> one row per block -> last-arriving block folds the rows in a fixed order.
+// No path is ever written to HBM.
+//
+// What each piece restates (line numbers = /root/reference/MLMC_RSCAM.py):
+//   gbm_*      diffusion_path :320-349, diffusion_path_avg :351-386, diffusion_path_min :388-426
+//              with GBM_Option.sde :1363
+//   JD<...>    JD_path :428-492, JD_path_avg :494-571, JD_path_min :573-651 (jump-ADAPTED EM)
+//              with Merton_Option.sde :1314-1315
+//   payoff_*   EA_payoff :62-86, Lookback_payoff :89-112, Digital_payoff :114-136
+//   seven sums Option.looper :946-955
+//
+// Two arithmetic policies share the control flow:
+//   AR_FAST   production form  X <- fma(X, fma(b,z,a), X)   (3 + 2/M FP64 issue slots / step)
+//   AR_EXACT  the reference's left-to-right expression order with explicitly rounded
+//             __dmul_rn/__dadd_rn (never contracted) - replay mode, bit-exact vs numpy for GBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mlmcb {
+
+typedef unsigned long long ull;
+
+enum { FN_FINAL = 0, FN_AVG = 1, FN_MIN = 2 };
+enum { AR_FAST = 0, AR_EXACT = 1 };
+enum { SAMP_F32BM = 0, SAMP_F64BM = 1 };
+enum { PAY_EURO = 0, PAY_ASIAN = 1, PAY_LOOKBACK = 2, PAY_DIGITAL = 3 };
+
+constexpr int kThreads = 128;
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+
+// Everything a launch needs, computed once on the host (mlmcb_api.cu: make_consts) and passed
+// by value as a __grid_constant__ kernel parameter (constant bank -> uniform operands).
+struct LevelConsts {
+    ull n_paths, path_offset, nsteps;
+    int M, l, payoff, is_l0;
+    uint32_t k0[10], k1[10];        // Philox round keys (key schedule hoisted to the host)
+    uint32_t ctr3_tag;              // level << 16 ; ORed onto the high half of the path id
+    // reference-order scalars (AR_EXACT) - each evaluated on the host exactly as numpy does
+    double X0, K, T, mu, sig, dt, sqrt_dt, Mdt, Md;
+    double disc, discK, look_cf, look_cc;
+    // AR_FAST per-step coefficients:  t = a + b*z ;  X += X*t
+    double a_f, b_f, a_c;
+    double avg_wf, avg_wc;          // dt/T and M*dt/T
+    // Merton
+    double lam, inv_lam, jm, js;
+};
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  Round keys come precomputed; one round is two
+// 32x32->64 multiplies (IMAD.WIDE.U32) and two three-input XORs (LOP3).
+// ------------------------------------------------------------------------------------------
+struct U4 { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ U4 philox_round(U4 c, uint32_t k0, uint32_t k1) {
+    ull p0 = (ull)PHILOX_M0 * c.x, p1 = (ull)PHILOX_M1 * c.z;
+    U4 r;
+    r.x = (uint32_t)(p1 >> 32) ^ c.y ^ k0;
+    r.y = (uint32_t)p1;
+    r.z = (uint32_t)(p0 >> 32) ^ c.w ^ k1;
+    r.w = (uint32_t)p0;
+    return r;
+}
+
+__device__ __forceinline__ U4 philox10(const LevelConsts& C, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    U4 c = {c0, c1, c2, c3};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) c = philox_round(c, C.k0[r], C.k1[r]);
+    return c;
+}
+
+// Counter layout (128 bit):  c0,c1 = draw-block index (60 bit) | stream kind (4 bit, top of c1)
+//                            c2,c3 = global path id (48 bit) | level (8 bit) | 0
+// key = 64-bit seed.  Distinct (seed, level, path id, kind, block) -> distinct counter, so
+// repeated looper calls (advancing path_offset), levels, ranks and the Merton jump stream never
+// reuse a draw.
+enum { STREAM_GRID = 0, STREAM_JUMP = 1 };
+
+__device__ __forceinline__ U4 philox_at(const LevelConsts& C, ull pid, uint32_t kind, ull blk) {
+    return philox10(C, (uint32_t)blk, (uint32_t)(blk >> 32) | (kind << 28),
+                    (uint32_t)pid, ((uint32_t)(pid >> 32) & 0xFFFFu) | C.ctr3_tag);
+}
+
+// ------------------------------------------------------------------------------------------
+// Normal samplers.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// fp32 Box-Muller from two 32-bit words: u in (0,1] for the radius (tail reaches 6.6 sigma),
+// a 32-bit angle.  MUFU.LG2 + MUFU.SQRT for the radius, polynomial sin/cos of pi*x.
+__device__ __forceinline__ void bm_pair_f32(uint32_t ru, uint32_t ra, float& z0, float& z1) {
+    float u = fmaf(__uint2float_rn(ru), 0x1p-32f, 0x1p-33f);
+    float rad = sqrt_approx(__log2f(u) * -1.3862943611198906f);     // sqrt(-2 ln u)
+    float x = __int2float_rn((int)ra) * 0x1p-31f;                   // angle / pi in [-1,1)
+    float sn, cs;
+    sincospif(x, &sn, &cs);
+    z0 = rad * cs;
+    z1 = rad * sn;
+}
+
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {   // (0,1), 53 random bits
+    ull v = ((ull)hi << 21) | (ull)(lo >> 11);
+    return ((double)v + 0.5) * 0x1p-53;
+}
+
+__device__ __forceinline__ void bm_pair_f64(uint32_t a, uint32_t b, uint32_t c, uint32_t d, double& z0, double& z1) {
+    double rad = sqrt(-2.0 * log(u53(a, b)));
+    double sn, cs;
+    sincospi(2.0 * u53(c, d), &sn, &cs);
+    z0 = rad * cs;
+    z1 = rad * sn;
+}
+
+template <typename R> __device__ __forceinline__ R fma_(R a, R b, R c);
+template <> __device__ __forceinline__ double fma_<double>(double a, double b, double c) { return fma(a, b, c); }
+template <> __device__ __forceinline__ float fma_<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <typename R> __device__ __forceinline__ R min_(R a, R b);
+template <> __device__ __forceinline__ double min_<double>(double a, double b) { return fmin(a, b); }
+template <> __device__ __forceinline__ float min_<float>(float a, float b) { return fminf(a, b); }
+
+// Four grid-step normals for (path, block b) = steps 4b+1 .. 4b+4.
+template <typename R, int SAMP>
+struct PhiloxSource {
+    const LevelConsts& C;
+    ull pid;
+    __device__ __forceinline__ void load4(ull b, R z[4]) const {
+        if (SAMP == SAMP_F32BM) {
+            U4 r = philox_at(C, pid, STREAM_GRID, b);
+            float f0, f1, f2, f3;
+            bm_pair_f32(r.x, r.y, f0, f1);
+            bm_pair_f32(r.z, r.w, f2, f3);
+            z[0] = (R)f0; z[1] = (R)f1; z[2] = (R)f2; z[3] = (R)f3;
+        } else {
+            U4 r = philox_at(C, pid, STREAM_GRID, 2 * b), s = philox_at(C, pid, STREAM_GRID, 2 * b + 1);
+            double d0, d1, d2, d3;
+            bm_pair_f64(r.x, r.y, r.z, r.w, d0, d1);
+            bm_pair_f64(s.x, s.y, s.z, s.w, d2, d3);
+            z[0] = (R)d0; z[1] = (R)d1; z[2] = (R)d2; z[3] = (R)d3;
+        }
+    }
+};
+
+// Replayed normals, step-major Z[step*n + path] (MLMC_RSCAM.py:343 call order).
+struct ReplaySource {
+    const double* Z;
+    ull n, i, nsteps;
+    __device__ __forceinline__ void load4(ull b, double z[4]) const {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ull s = 4 * b + k;
+            z[k] = s < nsteps ? Z[s * n + i] : 0.0;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Payoffs and the seven sums.
+// ------------------------------------------------------------------------------------------
+// vf/vc: terminal value or average; gf/gc: running minima (lookback only).
+__device__ __forceinline__ double payoff_fine(const LevelConsts& C, double v, double g) {
+    switch (C.payoff) {
+    case PAY_EURO:
+    case PAY_ASIAN: return __dmul_rn(C.disc, fmax(0.0, __dsub_rn(v, C.K)));                 // :79-80
+    case PAY_LOOKBACK: return __dmul_rn(C.disc, __dsub_rn(v, __dmul_rn(g, C.look_cf)));      // :105-106
+    default: return v > C.K ? C.discK : 0.0;                                                 // :131
+    }
+}
+__device__ __forceinline__ double payoff_coarse(const LevelConsts& C, double v, double g) {
+    switch (C.payoff) {
+    case PAY_EURO:
+    case PAY_ASIAN: return __dmul_rn(C.disc, fmax(0.0, __dsub_rn(v, C.K)));                 // :84-85
+    case PAY_LOOKBACK: return __dmul_rn(C.disc, __dsub_rn(v, __dmul_rn(g, C.look_cc)));      // :110-111
+    default: return v > C.K ? C.discK : 0.0;                                                 // :135
+    }
+}
+
+struct Sums7 {
+    double s[7];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) s[k] = 0.0;
+    }
+    // Option.looper :946-955 ; l==0 row :949
+    __device__ __forceinline__ void add(double Pf, double Pc, int is_l0) {
+        if (is_l0) {
+            s[0] += Pf; s[1] = fma(Pf, Pf, s[1]); s[2] += Pf; s[3] = fma(Pf, Pf, s[3]);
+        } else {
+            double d = Pf - Pc;
+            s[0] += d; s[1] = fma(d, d, s[1]);
+            s[2] += Pf; s[3] = fma(Pf, Pf, s[3]);
+            s[4] += Pc; s[5] = fma(Pc, Pc, s[5]);
+            s[6] = fma(Pc, Pf, s[6]);
+        }
+    }
+};
+
+// Block-level fold + deterministic cross-block finish.  `partials` has gridDim.x rows of 8
+// doubles; `ticket` is zero at launch.  The last block to arrive sums the rows in index order.
+// block_fold returns, in thread k < 7, the block total of sum k (other threads: 0).
+__device__ __forceinline__ double block_fold(const Sums7& a, double* sm /* [kThreads/32][8] */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        double v = a.s[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sm[w * 8 + k] = v;
+    }
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x < 7)
+        for (int j = 0; j < (int)(blockDim.x >> 5); ++j) r += sm[j * 8 + threadIdx.x];
+    return r;
+}
+
+__device__ __forceinline__ void grid_finish(const Sums7& a, double* partials, unsigned* ticket, double* out7) {
+    __shared__ double sm[(kThreads / 32) * 8];
+    __shared__ unsigned last;
+    const double mine = block_fold(a, sm);
+    if (threadIdx.x < 7) partials[(size_t)blockIdx.x * 8 + threadIdx.x] = mine;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    Sums7 t;
+    t.clear();
+    for (unsigned r = threadIdx.x; r < gridDim.x; r += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t.s[k] += __ldcg(&partials[(size_t)r * 8 + k]);
+    }
+    const double tot = block_fold(t, sm);
+    if (threadIdx.x < 7) out7[threadIdx.x] = tot;
+}
+
+// ------------------------------------------------------------------------------------------
+// GBM coupled path, production arithmetic.  Source supplies normals four steps at a time.
+// MT = 2 or 4: coarse refinement factor known at compile time (coarse steps fall on fixed
+// positions of a 4-step block); MT = 0: any M, a counter decides.
+// Returns the path outputs the reference path function returns: terminal values (FN_FINAL),
+// averages (FN_AVG) or terminal values + minima (FN_MIN).
+// ------------------------------------------------------------------------------------------
+template <typename R, int FN, int MT, typename Source>
+__device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source& src,
+                                              double& vf, double& vc, double& gf, double& gc) {
+    const R af = (R)C.a_f, bf = (R)C.b_f, ac = (R)C.a_c;
+    R Xf = (R)C.X0, Xc = (R)C.X0, sz = (R)0;
+    R Ff = FN == FN_MIN ? (R)C.X0 : (R)0, Fc = Ff;
+    int cm = 0;
+    const int M = C.M;
+
+#define MLMCB_FINE(zz)                                                   \
+    {                                                                    \
+        R t_ = fma_<R>(bf, (zz), af);                                    \
+        Xf = fma_<R>(Xf, t_, Xf);                                        \
+        sz += (zz);                                                      \
+        if (FN == FN_AVG) Ff += Xf;                                      \
+        if (FN == FN_MIN) Ff = min_<R>(Ff, Xf);                          \
+    }
+#define MLMCB_COARSE()                                                   \
+    {                                                                    \
+        R t_ = fma_<R>(bf, sz, ac);                                      \
+        Xc = fma_<R>(Xc, t_, Xc);                                        \
+        sz = (R)0;                                                       \
+        if (FN == FN_AVG) Fc += Xc;                                      \
+        if (FN == FN_MIN) Fc = min_<R>(Fc, Xc);                          \
+    }
+
+    const ull nblk = C.nsteps >> 2;
+    for (ull b = 0; b < nblk; ++b) {
+        R z[4];
+        src.load4(b, z);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            MLMCB_FINE(z[k]);
+            if (MT == 4) { if (k == 3) MLMCB_COARSE(); }
+            else if (MT == 2) { if (k & 1) MLMCB_COARSE(); }
+            else { if (++cm == M) { cm = 0; MLMCB_COARSE(); } }
+        }
+    }
+    const int rem = (int)(C.nsteps & 3);
+    if (rem) {                       // l==0 (1 step), M=2,l=1 (2 steps), odd M
+        R z[4];
+        src.load4(nblk, z);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (k < rem) {
+                MLMCB_FINE(z[k]);
+                if (++cm == M) { cm = 0; MLMCB_COARSE(); }
+            }
+        }
+    }
+#undef MLMCB_FINE
+#undef MLMCB_COARSE
+
+    if (FN == FN_AVG) {              // trapezoid: dt*(X0/2 + sum_{j<=N} X_j - X_N/2)/T   :369-386
+        const double h0 = 0.5 * C.X0;
+        vf = C.avg_wf * ((double)Ff + fma(-0.5, (double)Xf, h0));
+        vc = C.avg_wc * ((double)Fc + fma(-0.5, (double)Xc, h0));
+        gf = gc = 0.0;
+    } else {
+        vf = (double)Xf; vc = (double)Xc; gf = (double)Ff; gc = (double)Fc;
+    }
+}
+
+// GBM coupled path, reference expression order (replay, bit-exact vs numpy).
+template <int FN>
+__device__ __forceinline__ void gbm_path_exact(const LevelConsts& C, const double* Z, ull n, ull i,
+                                               double& vf, double& vc, double& gf, double& gc) {
+    const double dt = C.dt, Mdt = C.Mdt, mu = C.mu, sig = C.sig, Md = C.Md;
+    double Xf = C.X0, Xc = C.X0, dWc = 0.0;
+    double Af = __dmul_rn(__dmul_rn(0.5, dt), Xf);                       // :369
+    double Ac = __dmul_rn(__dmul_rn(__dmul_rn(0.5, Md), dt), Xc);        // :370
+    double Mf = C.X0, Mc = C.X0;
+    int cm = 0;
+    for (ull j = 0; j < C.nsteps; ++j) {
+        double dWf = __dmul_rn(Z[j * n + i], C.sqrt_dt);                 // :343
+        dWc = __dadd_rn(dWc, dWf);                                       // :344
+        Xf = __dadd_rn(Xf, __dadd_rn(__dmul_rn(__dmul_rn(mu, Xf), dt), __dmul_rn(__dmul_rn(sig, Xf), dWf)));   // :345
+        if (FN == FN_AVG) Af = __dadd_rn(Af, __dmul_rn(Xf, dt));         // :377
+        if (FN == FN_MIN) Mf = fmin(Xf, Mf);                             // :420
+        if (++cm == C.M) {
+            cm = 0;
+            Xc = __dadd_rn(Xc, __dadd_rn(__dmul_rn(__dmul_rn(mu, Xc), Mdt), __dmul_rn(__dmul_rn(sig, Xc), dWc)));  // :347
+            if (FN == FN_AVG) Ac = __dadd_rn(Ac, __dmul_rn(__dmul_rn(Xc, Md), dt));   // :380
+            if (FN == FN_MIN) Mc = fmin(Xc, Mc);                         // :423
+            dWc = 0.0;
+        }
+    }
+    if (FN == FN_AVG) {
+        Af = __dsub_rn(Af, __dmul_rn(__dmul_rn(0.5, Xf), dt));           // :383
+        Ac = __dsub_rn(Ac, __dmul_rn(__dmul_rn(__dmul_rn(0.5, Xc), Md), dt));   // :384
+        vf = __ddiv_rn(Af, C.T); vc = __ddiv_rn(Ac, C.T);                // :386
+        gf = gc = 0.0;
+    } else {
+        vf = Xf; vc = Xc; gf = Mf; gc = Mc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Merton jump-adapted coupled path state (JD_path* :428-651).  Times are always double.
+// G = trapezoid integral (FN_AVG) or running minimum (FN_MIN).
+// ------------------------------------------------------------------------------------------
+template <typename R, int FN, int AR>
+struct JD {
+    R Sf, Sc, Gf, Gc, dWc;
+    double dtc, tf, tc;
+
+    __device__ __forceinline__ void init(const LevelConsts& C) {
+        Sf = Sc = (R)C.X0;
+        Gf = Gc = FN == FN_MIN ? (R)C.X0 : (R)0;
+        dWc = (R)0;
+        dtc = tf = tc = 0.0;
+    }
+
+    // diffusion part of Merton_Option.sde :1314  dx_ = c*X*dt + sig*X*dW
+    __device__ __forceinline__ R dx(const LevelConsts& C, R X, double dt, R dW) const {
+        if (AR == AR_EXACT)
+            return (R)__dadd_rn(__dmul_rn(__dmul_rn(C.mu, (double)X), dt), __dmul_rn(__dmul_rn(C.sig, (double)X), (double)dW));
+        return X * fma_<R>((R)C.sig, dW, (R)(C.mu * dt));
+    }
+    __device__ __forceinline__ R half_area(R S, double dt) const {       // 0.5*dt*S :532
+        if (AR == AR_EXACT) return (R)__dmul_rn(__dmul_rn(0.5, dt), (double)S);
+        return (R)(0.5 * dt) * S;
+    }
+    __device__ __forceinline__ static R add(R a, R b) {
+        if (AR == AR_EXACT) return (R)__dadd_rn((double)a, (double)b);
+        return a + b;
+    }
+    __device__ __forceinline__ static R mul(R a, R b) {
+        if (AR == AR_EXACT) return (R)__dmul_rn((double)a, (double)b);
+        return a * b;
+    }
+
+    // one pass of the `while tau<tn` body :458-474 (the caller advances tau afterwards)
+    __device__ __forceinline__ void jump(const LevelConsts& C, double tau, R zw, R zq) {
+        double dt = tau - tf;                                            // :458
+        dtc += dt;                                                       // :459
+        R dWf = mul(zw, (R)sqrt(dt));                                    // :460
+        dWc = add(dWc, dWf);                                             // :461
+        R dJ;
+        if (AR == AR_EXACT) dJ = (R)__dsub_rn(exp(__dadd_rn(C.jm, __dmul_rn(C.js, (double)zq))), 1.0);   // :462
+        else dJ = (R)(exp(fma(C.js, (double)zq, C.jm)) - 1.0);
+        if (FN == FN_AVG) {                                              // :532-540
+            Gf = add(Gf, half_area(Sf, dt));
+            Sf = add(Sf, dx(C, Sf, dt, dWf));
+            Gf = add(Gf, half_area(Sf, dt));
+            Sf = add(Sf, mul(Sf, dJ));
+            Gc = add(Gc, half_area(Sc, dtc));
+            Sc = add(Sc, dx(C, Sc, dtc, dWc));
+            Gc = add(Gc, half_area(Sc, dtc));
+            Sc = add(Sc, mul(Sc, dJ));
+        } else {                                                         // :465-468, sde with dJ :1315
+            R d = dx(C, Sf, dt, dWf);
+            Sf = add(Sf, add(d, mul(add(d, Sf), dJ)));
+            d = dx(C, Sc, dtc, dWc);
+            Sc = add(Sc, add(d, mul(add(d, Sc), dJ)));
+            if (FN == FN_MIN) { Gf = min_<R>(Gf, Sf); Gc = min_<R>(Gc, Sc); }   // :621-622
+        }
+        dWc = (R)0; dtc = 0.0; tf = tau; tc = tau;                       // :470-473
+    }
+
+    // the remainder step up to the grid time tn :477-482 (+ :637)
+    __device__ __forceinline__ void grid(const LevelConsts& C, double tn, R zw) {
+        double dt = tn - tf;                                             // :477
+        dtc += dt;                                                       // :478
+        R dWf = mul(zw, (R)sqrt(dt));                                    // :479
+        dWc = add(dWc, dWf);                                             // :480
+        if (FN == FN_AVG) {                                              // :554-556
+            Gf = add(Gf, half_area(Sf, dt));
+            Sf = add(Sf, dx(C, Sf, dt, dWf));
+            Gf = add(Gf, half_area(Sf, dt));
+        } else {
+            Sf = add(Sf, dx(C, Sf, dt, dWf));                            // :481
+            if (FN == FN_MIN) Gf = min_<R>(Gf, Sf);                      // :637
+        }
+        tf = tn;                                                         // :482
+    }
+
+    // coarse path catches up at a coarse grid time :483-487
+    __device__ __forceinline__ void coarse(const LevelConsts& C, double tn) {
+        if (FN == FN_AVG) {                                              // :560-562
+            Gc = add(Gc, half_area(Sc, dtc));
+            Sc = add(Sc, dx(C, Sc, dtc, dWc));
+            Gc = add(Gc, half_area(Sc, dtc));
+        } else {
+            Sc = add(Sc, dx(C, Sc, dtc, dWc));                           // :484
+            if (FN == FN_MIN) Gc = min_<R>(Gc, Sc);                      // :640
+        }
+        tc = tn; dtc = 0.0; dWc = (R)0;                                  // :485-487
+    }
+
+    __device__ __forceinline__ void outputs(const LevelConsts& C, double& vf, double& vc, double& gf, double& gc) const {
+        if (FN == FN_AVG) {
+            if (AR == AR_EXACT) { vf = __ddiv_rn((double)Gf, C.T); vc = __ddiv_rn((double)Gc, C.T); }   // :571
+            else { vf = (double)Gf / C.T; vc = (double)Gc / C.T; }
+            gf = gc = 0.0;
+        } else {
+            vf = (double)Sf; vc = (double)Sc; gf = (double)Gf; gc = (double)Gc;
+        }
+    }
+};
+
+// Jump-stream draws for jump number jk of a path: inter-arrival time, jump-size normal and the
+// Brownian normal of the adaptive step that ends at that jump.
+template <typename R, int SAMP>
+__device__ __forceinline__ void jump_draws(const LevelConsts& C, ull pid, ull jk, double& gap, R& zq, R& zw) {
+    if (SAMP == SAMP_F32BM) {
+        U4 r = philox_at(C, pid, STREAM_JUMP, jk);
+        gap = -log(u53(r.x, r.y)) * C.inv_lam;
+        float a, b;
+        bm_pair_f32(r.z, r.w, a, b);
+        zq = (R)a; zw = (R)b;
+    } else {
+        U4 r = philox_at(C, pid, STREAM_JUMP, 2 * jk), s = philox_at(C, pid, STREAM_JUMP, 2 * jk + 1);
+        gap = -log(u53(r.x, r.y)) * C.inv_lam;
+        double a, b;
+        bm_pair_f64(s.x, s.y, s.z, s.w, a, b);
+        zq = (R)a; zw = (R)b;
+    }
+}
+
+// Merton coupled path, Philox mode.  A 4-step block with no jump inside is exactly a GBM block
+// with drift c = r - lam*J_bar (fast path); a block that contains a jump takes the general
+// jump-adapted code above (rare: lam*T*4/nsteps per path).
+template <typename R, int FN, int MT, int SAMP>
+__device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid,
+                                                double& vf, double& vc, double& gf, double& gc) {
+    PhiloxSource<R, SAMP> src{C, pid};
+    JD<R, FN, AR_FAST> st;
+    st.init(C);
+    const R af = (R)C.a_f, bf = (R)C.b_f, ac = (R)C.a_c;
+    ull jk = 0;
+    double gap, tau;
+    R zq, zwj;
+    jump_draws<R, SAMP>(C, pid, jk, gap, zq, zwj);
+    tau = gap;                                                           // :454
+    int cm = 0;
+    const int M = C.M;
+    const ull nblk = (C.nsteps + 3) >> 2;
+    for (ull b = 0; b < nblk; ++b) {
+        R z[4];
+        src.load4(b, z);
+        const ull j0 = 4 * b;
+        const bool full = j0 + 4 <= C.nsteps;
+        const double t_end = (double)(j0 + 4) * C.dt;
+        if (MT != 0 && full && tau >= t_end) {
+            // ---- no jump in this block: regular steps, state is clean at both block ends
+            R Xf = st.Sf, Xc = st.Sc, sz = (R)0;
+            if (FN == FN_AVG) {
+                R acc = (R)0.5 * Xf, accc = (R)0.5 * Xc;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    R t_ = fma_<R>(bf, z[k], af);
+                    Xf = fma_<R>(Xf, t_, Xf);
+                    sz += z[k];
+                    acc += (k == 3) ? (R)0.5 * Xf : Xf;
+                    if ((MT == 4 && k == 3) || (MT == 2 && (k & 1))) {
+                        R tc_ = fma_<R>(bf, sz, ac);
+                        Xc = fma_<R>(Xc, tc_, Xc);
+                        sz = (R)0;
+                        if (MT == 4) accc = fma_<R>((R)0.5, Xc, accc);
+                        else accc += (k == 3) ? (R)0.5 * Xc : Xc;
+                    }
+                }
+                st.Gf = fma_<R>((R)C.dt, acc, st.Gf);
+                st.Gc = fma_<R>((R)C.Mdt, accc, st.Gc);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    R t_ = fma_<R>(bf, z[k], af);
+                    Xf = fma_<R>(Xf, t_, Xf);
+                    sz += z[k];
+                    if (FN == FN_MIN) st.Gf = min_<R>(st.Gf, Xf);
+                    if ((MT == 4 && k == 3) || (MT == 2 && (k & 1))) {
+                        R tc_ = fma_<R>(bf, sz, ac);
+                        Xc = fma_<R>(Xc, tc_, Xc);
+                        sz = (R)0;
+                        if (FN == FN_MIN) st.Gc = min_<R>(st.Gc, Xc);
+                    }
+                }
+            }
+            st.Sf = Xf; st.Sc = Xc;
+            st.tf = st.tc = t_end;
+        } else {
+            // ---- general jump-adapted steps
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const ull j = j0 + k + 1;
+                if (j <= C.nsteps) {
+                    const double tn = (double)j * C.dt;                  // :456
+                    while (tau < tn) {                                   // :457
+                        st.jump(C, tau, zwj, zq);
+                        ++jk;
+                        jump_draws<R, SAMP>(C, pid, jk, gap, zq, zwj);
+                        tau += gap;                                      // :474
+                    }
+                    st.grid(C, tn, z[k]);
+                    if (++cm == M) { cm = 0; st.coarse(C, tn); }         // :483
+                }
+            }
+        }
+    }
+    st.outputs(C, vf, vc, gf, gc);
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernels.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit(const LevelConsts& C, ull i, double vf, double vc, double gf, double gc,
+                                     Sums7& acc, double* Pf_out, double* Pc_out) {
+    const double Pf = payoff_fine(C, vf, gf);
+    const double Pc = C.is_l0 ? vc : payoff_coarse(C, vc, gc);          // l==0: raw coarse output :82
+    acc.add(Pf, Pc, C.is_l0);
+    if (Pf_out) Pf_out[i] = Pf;
+    if (Pc_out) Pc_out[i] = Pc;
+}
+
+template <typename R, int MODEL, int FN, int MT, int SAMP>
+__global__ void __launch_bounds__(kThreads)
+level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
+             double* out7, double* Pf_out, double* Pc_out) {
+    Sums7 acc;
+    acc.clear();
+    const ull stride = (ull)gridDim.x * blockDim.x;
+    for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
+        const ull pid = C.path_offset + i;
+        double vf, vc, gf, gc;
+        if (MODEL == 0) {
+            PhiloxSource<R, SAMP> src{C, pid};
+            gbm_path_fast<R, FN, MT>(C, src, vf, vc, gf, gc);
+        } else {
+            mjd_path_philox<R, FN, MT, SAMP>(C, pid, vf, vc, gf, gc);
+        }
+        emit(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
+    }
+    grid_finish(acc, partials, ticket, out7);
+}
+
+template <int FN, int AR>
+__global__ void __launch_bounds__(kThreads)
+replay_gbm_kernel(const __grid_constant__ LevelConsts C, const double* Z, double* partials, unsigned* ticket,
+                  double* out7, double* Pf_out, double* Pc_out) {
+    Sums7 acc;
+    acc.clear();
+    const ull stride = (ull)gridDim.x * blockDim.x;
+    for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
+        double vf, vc, gf, gc;
+        if (AR == AR_EXACT) {
+            gbm_path_exact<FN>(C, Z, C.n_paths, i, vf, vc, gf, gc);
+        } else {
+            ReplaySource src{Z, C.n_paths, i, C.nsteps};
+            gbm_path_fast<double, FN, 0>(C, src, vf, vc, gf, gc);
+        }
+        emit(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
+    }
+    grid_finish(acc, partials, ticket, out7);
+}
+
+template <int FN, int AR>
+__global__ void __launch_bounds__(kThreads)
+replay_mjd_kernel(const __grid_constant__ LevelConsts C, const double* zW, const long long* offW,
+                  const double* zQ, const long long* offQ, const double* E, const long long* offE,
+                  double* partials, unsigned* ticket, double* out7, double* Pf_out, double* Pc_out) {
+    Sums7 acc;
+    acc.clear();
+    const ull stride = (ull)gridDim.x * blockDim.x;
+    for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
+        JD<double, FN, AR> st;
+        st.init(C);
+        long long iw = offW[i], iq = offQ[i], ie = offE[i];
+        double tau = 0.0;
+        tau += E[ie++];                                                  // :454
+        int cm = 0;
+        for (ull j = 1; j <= C.nsteps; ++j) {
+            // :456  tn = j*T/Nsteps   (EXACT keeps the multiply-then-divide)
+            const double tn = AR == AR_EXACT ? __ddiv_rn(__dmul_rn((double)j, C.T), (double)C.nsteps)
+                                             : (double)j * C.dt;
+            while (tau < tn) {
+                st.jump(C, tau, zW[iw++], zQ[iq++]);
+                tau += E[ie++];                                          // :474
+            }
+            st.grid(C, tn, zW[iw++]);
+            if (++cm == C.M) { cm = 0; st.coarse(C, tn); }
+        }
+        double vf, vc, gf, gc;
+        st.outputs(C, vf, vc, gf, gc);
+        emit(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
+    }
+    grid_finish(acc, partials, ticket, out7);
+}
+
+template <int SAMP>
+__global__ void sampler_probe_kernel(const __grid_constant__ LevelConsts C, ull n_steps, double* out) {
+    const ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_paths) return;
+    PhiloxSource<double, SAMP> src{C, C.path_offset + i};
+    for (ull b = 0; 4 * b < n_steps; ++b) {
+        double z[4];
+        src.load4(b, z);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (4 * b + k < n_steps) out[(4 * b + k) * C.n_paths + i] = z[k];
+    }
+}
+
+}  // namespace mlmcb

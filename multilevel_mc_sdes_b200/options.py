@@ -1,0 +1,415 @@
+"""Host-side mirror of the reference's Option classes for the hot path (drop-in surface).
+
+Same class names, constructor kwargs, attributes and method contracts as
+/root/reference/MLMC_RSCAM.py (`:NNN` = line numbers there):
+
+    Option :777-1042, GBM_Option :1317-1363, Merton_Option :1248-1315,
+    Euro_/Asian_/Lookback_/Digital_GBM :1367-1481, *_Merton :1636-1704
+
+What differs: `looper` / `payoff` run on the GPU through libmlmcb.so (include/mlmcb.h) instead of
+numpy loops; randomness is Philox addressed by (seed, level, global path id) instead of numpy's
+global MT19937, so each Option carries a seed and a per-level path-offset counter (every looper
+call consumes fresh ids).  `mlmc` is the reference driver restated line by line
+(host code; it only decides how many samples each level gets), None-safe for alpha_0/beta_0.
+
+Extra constructor kwargs (keyword-only, all optional): seed, device, sampler ("f32bm"|"f64bm"),
+fp32 (path arithmetic in fp32, opt-in), distributed (shard each level call over the
+torch.distributed world and all-reduce the 7 sums).
+"""
+import ctypes as C
+import math
+import sys
+
+import numpy as np
+
+from . import _lib
+from ._lib import GBM, MERTON, EURO, ASIAN, LOOKBACK, DIGITAL
+
+_SAMPLERS = {"f32bm": _lib.SAMPLER_F32BM, "f64bm": _lib.SAMPLER_F64BM}
+
+
+try:  # what scipy.stats.norm.cdf evaluates (the reference's BS() uses norm.cdf, :35)
+    from scipy.special import ndtr as _norm_cdf
+except Exception:  # pragma: no cover - scipy is present in this image
+    def _norm_cdf(x):
+        return 0.5 * math.erfc(-x / math.sqrt(2.0))
+
+
+def _stream_handle(device):
+    """cudaStream_t of torch's current stream if torch is loaded, else the default stream."""
+    torch = sys.modules.get("torch")
+    if torch is not None and torch.cuda.is_available():
+        return int(torch.cuda.current_stream(device).cuda_stream)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# MLMC driver, restated from Option.mlmc :960-1042.  `sweep(requests, M)` must return, for each
+# (Nl, l) in `requests`, the 7-vector Option.looper would return; everything else is host numpy
+# exactly as in the reference (same float N, same extrapolation fix, same regressions, same
+# convergence test).
+# ------------------------------------------------------------------------------------------------
+def mlmc_driver(sweep, eps, M, N0, alpha_0, beta_0):
+    alpha = max(0, alpha_0) if alpha_0 is not None else 0       # :982 (None-safe)
+    beta = max(0, beta_0) if beta_0 is not None else 0          # :983
+    L = 2
+    V = np.zeros(L + 1)
+    N = np.zeros(L + 1)
+    dN = N0 * np.ones(L + 1)
+    sums = np.zeros((7, L + 1))
+    sqrt_h = np.sqrt(M ** (np.arange(0, L + 1)))
+
+    while np.sum(dN) > 0:                                       # :993
+        requests = [(int(dN[l]), l) for l in range(L + 1) if dN[l] > 0]      # :994-997
+        for (num, l), s in zip(requests, sweep(requests, M)):
+            sums[:, l] += s
+
+        N += dN                                                 # :999
+        Yl = np.abs(sums[0, :]) / N
+        V = np.maximum((sums[1, :] / N) - (Yl) ** 2, 0)
+
+        Yl[3:] = np.maximum(Yl[3:], Yl[2:L] * M ** (-alpha))    # :1004
+        V[3:] = np.maximum(V[3:], V[2:L] * M ** (-beta))        # :1005
+
+        if alpha_0 is None:                                     # :1007-1013
+            X = np.ones((L, 2))
+            X[:, 0] = np.arange(1, L + 1)
+            with np.errstate(divide="ignore"):
+                a = np.linalg.lstsq(X, np.log(Yl[1:]), rcond=None)[0]
+            alpha = max(0.5, -a[0] / np.log(M))
+        if beta_0 is None:                                      # :1014-1018
+            X = np.ones((L, 2))
+            X[:, 0] = np.arange(1, L + 1)
+            with np.errstate(divide="ignore"):
+                b = np.linalg.lstsq(X, np.log(V[1:]), rcond=None)[0]
+            beta = max(0.5, -b[0] / np.log(M))
+
+        sqrt_V = np.sqrt(V)
+        Nl_new = np.ceil((2 * eps ** -2) * np.sum(sqrt_V * sqrt_h) * (sqrt_V / sqrt_h))   # :1021
+        dN = np.maximum(0, Nl_new - N)
+
+        if sum(dN > 0.01 * N) == 0:                             # :1024
+            if max(Yl[-2] / (M ** alpha), Yl[-1]) > (M ** alpha - 1) * eps * np.sqrt(0.5):   # :1025
+                L += 1
+                V = np.concatenate((V, np.zeros(1)), axis=0)
+                N = np.concatenate((N, N0 * np.zeros(1)), axis=0)
+                dN = np.concatenate((dN, N0 * np.ones(1)), axis=0)
+                sqrt_h = np.concatenate((sqrt_h, [np.sqrt(M ** L)]), axis=0)
+                sums = np.concatenate((sums, np.zeros((7, 1))), axis=1)
+    return sums, N, alpha, beta
+
+
+class Option:
+    """Base class (reference Option :777-1042): holds alpha_0, beta_0, X0, K, T, r."""
+
+    _model = None
+    _payoff_kind = None
+
+    def __init__(self, alpha_0=None, beta_0=None, X0=100, K=100, T=1, r=0.05, *,
+                 seed=0, device=0, sampler="f32bm", fp32=False, distributed=False, verbose=True):
+        self.alpha_0 = alpha_0
+        self.beta_0 = beta_0
+        self.X0 = X0
+        self.r = r
+        self.K = K
+        self.T = T
+        if sampler not in _SAMPLERS:
+            raise ValueError(f"sampler must be one of {sorted(_SAMPLERS)}")
+        self.seed = int(seed)
+        self.device = int(device)
+        self.sampler = sampler
+        self.fp32 = bool(fp32)
+        self.distributed = bool(distributed)
+        self.verbose = verbose
+        self._next_path = {}          # level -> next unused global path id
+
+    # -- virtuals the reference declares (:816-915) ------------------------------------------
+    def anti_payoff(self, N_loop, l, M):
+        raise NotImplementedError("Option instance has no implemented anti_payoff method")
+
+    def path(self, N_loop, l, M):
+        raise NotImplementedError("Option instance has no implemented path method")
+
+    def anti_path(self, N_loop, l, M):
+        raise NotImplementedError("Option instance has no implemented anti_path method")
+
+    def sde(self, X, dt, t_, dW, dJ=0):
+        raise NotImplementedError("Option instance has no implemented sde method")
+
+    def BS(self):
+        raise NotImplementedError("Option instance has no implemented BS method")
+
+    def asset_plot(self, L=6, M=2):
+        raise NotImplementedError("Option instance has no implemented asset_plot method")
+
+    # -- plumbing ----------------------------------------------------------------------------
+    def _params(self):
+        p = _lib.Params()
+        p.X0 = float(self.X0)
+        p.K = float(self.K) if self.K is not None else 0.0
+        p.T = float(self.T)
+        p.r = float(self.r)
+        p.sig = float(self.sig)
+        if self._model == GBM:      # the kernel forms mu = r + drift (:1347); keep it bit-identical
+            d = getattr(self, "_drift", 0.0)
+            p.drift = float(d if self.r + d == self.mu else self.mu - self.r)
+        else:
+            p.drift = 0.0
+        p.lam = float(getattr(self, "lam", 0.0))
+        p.jumpmean = float(getattr(self, "jumpmean", 0.0))
+        p.jumpstd = float(getattr(self, "jumpstd", 0.0))
+        p.beta = float(getattr(self, "beta", 0.5826))
+        p.disc = float(np.exp(-self.r * self.T))                # numpy's value, as the reference :80
+        p.J_bar = float(getattr(self, "J_bar", 0.0))
+        return p
+
+    def _flags(self):
+        return _SAMPLERS[self.sampler] | (_lib.FP32_PATHS if self.fp32 else 0)
+
+    def _check_product(self):
+        if self._model is None or self._payoff_kind is None:
+            raise NotImplementedError("Option instance has no implemented payoff method")   # :829
+
+    def _take_ids(self, l, n):
+        start = self._next_path.get(l, 0)
+        self._next_path[l] = start + int(n)
+        return start
+
+    def _shard(self, n, start):
+        """Contiguous slice of [start, start+n) for this rank."""
+        if not self.distributed:
+            return n, start
+        import torch.distributed as dist
+        g, G = dist.get_rank(), dist.get_world_size()
+        lo, hi = (g * n) // G, ((g + 1) * n) // G
+        return hi - lo, start + lo
+
+    def _allreduce(self, rows):
+        """Sum rows (k,7) over the world: the only message of the method."""
+        if not self.distributed:
+            return rows
+        import torch
+        import torch.distributed as dist
+        backend = dist.get_backend()
+        dev = f"cuda:{self.device}" if backend == "nccl" else "cpu"
+        t = torch.as_tensor(np.ascontiguousarray(rows), dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    # -- the per-path function (reference payoff :62-136) ------------------------------------
+    def payoff(self, N_loop, l, M):
+        """(Pf, Pc) for N_loop fresh coupled paths at level l; at l==0 the second item is the raw
+        coarse path output, as in the reference (:82)."""
+        self._check_product()
+        import torch
+        n = int(N_loop)
+        start = self._take_ids(l, n)
+        dev = torch.device("cuda", self.device)
+        Pf = torch.empty(n, dtype=torch.float64, device=dev)
+        Pc = torch.empty(n, dtype=torch.float64, device=dev)
+        out7 = torch.empty(7, dtype=torch.float64, device=dev)
+        p = self._params()
+        _lib.check(_lib.load().mlmcb_level_sums(
+            C.byref(p), self._model, self._payoff_kind, int(l), int(M), n, self.seed, start, self._flags(),
+            self.device, _stream_handle(self.device), out7.data_ptr(), Pf.data_ptr(), Pc.data_ptr()))
+        return Pf.cpu().numpy(), Pc.cpu().numpy()
+
+    # -- the level function (reference looper :919-957) --------------------------------------
+    def looper(self, Nl, l, M, anti, Npl=10 ** 4):
+        """suml (7,) float64 = [sum dP, sum dP^2, sum Pf, sum Pf^2, sum Pc, sum Pc^2, sum Pc*Pf];
+        [sum Pf, sum Pf^2, sum Pf, sum Pf^2, 0,0,0] at l==0.  One kernel launch; Npl is accepted
+        for signature compatibility (the GPU needs no chunking)."""
+        if anti == True:  # noqa: E712  (reference spelling :941)
+            return self._looper_anti(Nl, l, M)
+        return self._sweep([(int(Nl), int(l))], M)[0]
+
+    def _looper_anti(self, Nl, l, M):
+        self.anti_payoff(0, l, M)        # raises NotImplementedError, as the reference does (:844)
+
+    def _sweep(self, requests, M):
+        """requests: [(Nl, l), ...] -> list of 7-vectors.  All launches of one sweep run
+        concurrently on the device; one D2H copy brings every row back."""
+        self._check_product()
+        k = len(requests)
+        if k == 0:
+            return []
+        levels = (C.c_int * k)(*[l for _, l in requests])
+        counts, offsets = [], []
+        for n, l in requests:
+            start = self._take_ids(l, n)
+            n_loc, start_loc = self._shard(n, start)
+            counts.append(n_loc)
+            offsets.append(start_loc)
+        n_arr = (C.c_uint64 * k)(*counts)
+        o_arr = (C.c_uint64 * k)(*offsets)
+        out = np.zeros((k, 7))
+        p = self._params()
+        _lib.check(_lib.load().mlmcb_level_sweep_host(
+            C.byref(p), self._model, self._payoff_kind, int(M), k, levels, n_arr, o_arr, self.seed,
+            self._flags(), self.device, _stream_handle(self.device),
+            out.ctypes.data_as(C.POINTER(C.c_double))))
+        out = self._allreduce(out)
+        return [out[i].copy() for i in range(k)]
+
+    # -- replay (parity check (a)) -----------------------------------------------------------
+    def payoff_replay(self, draws, l, M, arith="fast"):
+        """Feed the reference's own draws.  GBM: `draws` = Z (M**l, N) array, row j the
+        np.random.randn(N) of step j+1.  Merton: dict with zW/offW, zQ/offQ, E/offE (CSR, the
+        order the reference consumes them).  Returns (Pf, Pc) per path."""
+        self._check_product()
+        import torch
+        dev = torch.device("cuda", self.device)
+        ar = {"fast": _lib.ARITH_FAST, "exact": _lib.ARITH_EXACT}[arith]
+        p = self._params()
+        st = _stream_handle(self.device)
+        if self._model == GBM:
+            Z = torch.as_tensor(np.ascontiguousarray(draws, dtype=np.float64), device=dev)
+            if Z.shape[0] != int(M) ** int(l):
+                raise ValueError("Z must have M**l rows")
+            n = Z.shape[1]
+            Pf = torch.empty(n, dtype=torch.float64, device=dev)
+            Pc = torch.empty(n, dtype=torch.float64, device=dev)
+            _lib.check(_lib.load().mlmcb_replay_gbm(C.byref(p), self._payoff_kind, int(l), int(M), n, Z.data_ptr(),
+                                                    ar, self.device, st, Pf.data_ptr(), Pc.data_ptr(), None))
+        else:
+            t = {k: torch.as_tensor(np.ascontiguousarray(draws[k]), device=dev)
+                 for k in ("zW", "offW", "zQ", "offQ", "E", "offE")}
+            # empty streams still need a valid pointer
+            for k in ("zW", "zQ", "E"):
+                if t[k].numel() == 0:
+                    t[k] = torch.zeros(1, dtype=torch.float64, device=dev)
+            n = t["offW"].numel() - 1
+            Pf = torch.empty(n, dtype=torch.float64, device=dev)
+            Pc = torch.empty(n, dtype=torch.float64, device=dev)
+            _lib.check(_lib.load().mlmcb_replay_merton(
+                C.byref(p), self._payoff_kind, int(l), int(M), n, t["zW"].data_ptr(), t["offW"].data_ptr(),
+                t["zQ"].data_ptr(), t["offQ"].data_ptr(), t["E"].data_ptr(), t["offE"].data_ptr(),
+                ar, self.device, st, Pf.data_ptr(), Pc.data_ptr(), None))
+        return Pf.cpu().numpy(), Pc.cpu().numpy()
+
+    # -- MLMC driver (reference mlmc :960-1042) ----------------------------------------------
+    def mlmc(self, eps, M=2, anti=False, N0=10 ** 3, warm_start=True):
+        """Returns (sums (7,L+1) float64, N (L+1,) float64); price = sum(sums[0,:]/N)."""
+        if anti == True:  # noqa: E712
+            self.anti_payoff(0, 0, M)
+        sums, N, alpha, beta = mlmc_driver(self._sweep, eps, M, N0, self.alpha_0, self.beta_0)
+        if self.verbose:
+            print(f'Estimated alpha = {alpha}')                 # :1034
+            print(f'Estimated beta = {beta}')
+        if warm_start:                                          # :1037-1041
+            self.alpha_0 = alpha
+            self.beta_0 = beta
+            if self.verbose:
+                print(f'    Saved estimated alpha_0 = {alpha}')
+                print(f'    Saved estimated beta_0 = {beta}')
+        return sums, N
+
+    # -- numeric core of Giles_plot's fixed-level sweep (:1775-1777) -------------------------
+    def level_sweep(self, Lmax=8, Nsamples=10 ** 6, M=2):
+        """sums (7, Lmax+1) of looper(Nsamples, l, M) for l = 0..Lmax, issued as one sweep."""
+        rows = self._sweep([(int(Nsamples), l) for l in range(Lmax + 1)], M)
+        return np.stack(rows, axis=1)
+
+
+class GBM_Option(Option):
+    """dS = mu*S*dt + sig*S*dW, mu = drift + r  (reference :1317-1363)."""
+    _model = GBM
+
+    def __init__(self, drift=0, sig=0.2, **kwargs):
+        super().__init__(**kwargs)
+        self.sig = sig
+        r = self.r
+        self._drift = drift
+        self.mu = (r + drift)                                   # :1347
+
+    def sde(self, X, dt, t_, dW):
+        return self.mu * X * dt + self.sig * X * dW             # :1363
+
+
+class Merton_Option(Option):
+    """Merton jump-diffusion (reference :1248-1315)."""
+    _model = MERTON
+
+    def __init__(self, lam=1, jumpmean=0.1, jumpstd=0.2, sig=0.2, **kwargs):
+        super().__init__(**kwargs)
+        self.lam = lam
+        self.J_bar = np.exp(jumpmean + 0.5 * jumpstd ** 2) - 1   # :1291
+        self.jumpstd = jumpstd
+        self.jumpmean = jumpmean
+        self.sig = sig
+
+    def sde(self, X, dt, t_, dW, dJ=0):
+        dx_ = (self.r - self.lam * self.J_bar) * X * dt + self.sig * X * dW     # :1314
+        return dx_ + (dx_ + X) * dJ
+
+
+class Euro_GBM(GBM_Option):
+    _payoff_kind = EURO
+
+    def BS(self):                                               # :1383-1393
+        D1 = (np.log(self.X0 / self.K) + (self.r + 0.5 * self.sig ** 2) * self.T) / (self.sig * np.sqrt(self.T))
+        D2 = D1 - self.sig * np.sqrt(self.T)
+        return self.X0 * _norm_cdf(D1) - self.K * np.exp(-self.r * self.T) * _norm_cdf(D2)
+
+
+class Asian_GBM(GBM_Option):
+    _payoff_kind = ASIAN
+
+    def BS(self):                                               # Turnbull-Wakeman approximation :1411-1429
+        X0, r, T, sig, K = self.X0, self.r, self.T, self.sig, self.K
+        M1 = X0 * (np.exp(r * T) - 1) / (r * T)
+        M2 = (2 * X0 ** 2) * (np.exp((2 * r + sig ** 2) * T) / ((r + sig ** 2) * (2 * r + sig ** 2) * T ** 2)
+                              + (1 / (2 * r + sig ** 2) - np.exp(r * T) / (r + sig ** 2)) / (r * T ** 2))
+        sig_A = np.sqrt(np.log(M2 / (M1 ** 2)))
+        d1 = (np.log(M1 / K) + 0.5 * sig_A ** 2) / sig_A
+        d2 = d1 - sig_A
+        return np.exp(-r * T) * (M1 * _norm_cdf(d1) - K * _norm_cdf(d2))
+
+
+class Lookback_GBM(GBM_Option):
+    _payoff_kind = LOOKBACK
+    beta = 0.5826                                               # :1443
+
+    def BS(self):                                               # :1446-1456
+        D1 = (self.r + 0.5 * self.sig ** 2) * self.T / (self.sig * np.sqrt(self.T))
+        D2 = D1 - self.sig * np.sqrt(self.T)
+        k = 0.5 * self.sig ** 2 / self.r
+        return self.X0 * (_norm_cdf(D1) - _norm_cdf(-D1) * k
+                          - np.exp(-self.r * self.T) * (_norm_cdf(D2) - _norm_cdf(D2) * k))
+
+
+class Digital_GBM(GBM_Option):
+    _payoff_kind = DIGITAL
+
+    def BS(self):                                               # :1473-1481
+        D2 = ((np.log(self.X0 / self.K) + (self.r + 0.5 * self.sig ** 2) * self.T) / (self.sig * np.sqrt(self.T))
+              - self.sig * np.sqrt(self.T))
+        return self.K * np.exp(-self.r * self.T) * _norm_cdf(D2)
+
+
+class Euro_Merton(Merton_Option):
+    _payoff_kind = EURO
+
+    def BS(self, n=100):                                        # :1648-1664
+        k = np.arange(0, n)
+        sig_n = np.sqrt(self.sig ** 2 + (self.jumpstd ** 2) * k / self.T)
+        r_n = self.r - self.lam * self.J_bar + k * np.log((1 + self.J_bar) / self.T)
+        D1 = (np.log(self.X0 / self.K) + (r_n + 0.5 * sig_n ** 2) * self.T) / (sig_n * np.sqrt(self.T))
+        D2 = D1 - sig_n * np.sqrt(self.T)
+        bs = self.X0 * _norm_cdf(D1) - self.K * np.exp(-r_n * self.T) * _norm_cdf(D2)
+        discount = np.exp(-self.lam * (1 + self.J_bar) * self.T)
+        fact = np.array([math.factorial(int(i)) for i in k], dtype=np.float64)
+        return discount * np.sum(((self.lam * (1 + self.J_bar) * self.T) ** k / fact) * bs)
+
+
+class Asian_Merton(Merton_Option):
+    _payoff_kind = ASIAN
+
+
+class Lookback_Merton(Merton_Option):
+    _payoff_kind = LOOKBACK
+    beta = 0.5826                                               # :1691
+
+
+class Digital_Merton(Merton_Option):
+    _payoff_kind = DIGITAL

@@ -1,0 +1,36 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return {n: np.load(os.path.join(GOLDEN, n + ".npz"), allow_pickle=False)
+            for n in ("payoffs_gbm", "payoffs_merton", "looper", "mlmc_trace", "closed_forms")}
+
+
+@pytest.fixture(scope="session")
+def c_oracle():
+    from oracle import c_oracle as co
+    co.build()
+    return co
+
+
+@pytest.fixture(scope="session")
+def cuda_lib():
+    """The product library on a real device; fails (not skips) if it is not there."""
+    import torch
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    from multilevel_mc_sdes_b200 import _lib
+    return _lib.load()

@@ -1,0 +1,49 @@
+"""GPU: end-to-end Option.mlmc(eps) against the reference's closed forms (north-star check (b))."""
+import numpy as np
+import pytest
+
+import multilevel_mc_sdes_b200 as mm
+
+pytestmark = pytest.mark.gpu
+
+
+def price(sums, N):
+    return float(np.sum(sums[0, :] / N))          # README.md:29
+
+
+def test_readme_example_within_eps_of_BS(cuda_lib):
+    """BASELINE config #1: Euro_GBM(125,105,.02,.5).mlmc(0.01) vs BS() = 35.17419437739385, with
+    alpha_0 = beta_0 = None exactly as the README writes it."""
+    opt = mm.Euro_GBM(X0=125, K=105, r=0.02, sig=0.5, verbose=False)
+    sums, N = opt.mlmc(eps=0.01)
+    assert sums.shape == (7, len(N)) and N.dtype == np.float64
+    assert abs(price(sums, N) - opt.BS()) < 0.01
+    assert opt.alpha_0 is not None and opt.beta_0 is not None      # warm_start side effect (:1037)
+
+
+def test_rms_error_over_seeds_is_below_eps(cuda_lib):
+    eps, errs = 0.02, []
+    for seed in range(8):
+        opt = mm.Euro_GBM(seed=seed, verbose=False)
+        sums, N = opt.mlmc(eps=eps, M=4)
+        errs.append(price(sums, N) - opt.BS())
+    assert np.sqrt(np.mean(np.square(errs))) < eps
+
+
+@pytest.mark.parametrize("cls,kw,eps,M", [
+    (mm.Lookback_GBM, {}, 0.02, 4),
+    (mm.Digital_GBM, dict(beta_0=0.5), 0.05, 4),
+    (mm.Euro_Merton, {}, 0.03, 2),
+    (mm.Euro_GBM, dict(sampler="f64bm"), 0.02, 2),
+])
+def test_other_closed_forms(cuda_lib, cls, kw, eps, M):
+    opt = cls(verbose=False, **kw)
+    sums, N = opt.mlmc(eps=eps, M=M)
+    assert abs(price(sums, N) - opt.BS()) < 2 * eps
+
+
+def test_asian_matches_reference_limit(cuda_lib):
+    # Asian BS() is the Turnbull-Wakeman approximation (5.7828); MLMC converges to ~5.763
+    opt = mm.Asian_GBM(verbose=False)
+    sums, N = opt.mlmc(eps=0.005, M=4)
+    assert abs(price(sums, N) - 5.7626) < 0.012

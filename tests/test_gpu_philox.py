@@ -1,0 +1,168 @@
+"""GPU: Philox-mode level function through the C ABI (north-star check (b)) and its invariants."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import multilevel_mc_sdes_b200 as mm
+from multilevel_mc_sdes_b200 import _lib
+from oracle import np_oracle as O
+from tests.helpers import CLASS_CODES
+
+pytestmark = pytest.mark.gpu
+
+
+def level_sums(opt, n, l, M, offset=0, flags=None, per_path=False):
+    import torch
+    dev = torch.device("cuda", 0)
+    out = torch.zeros(7, dtype=torch.float64, device=dev)
+    Pf = torch.empty(n if per_path else 1, dtype=torch.float64, device=dev)
+    Pc = torch.empty(n if per_path else 1, dtype=torch.float64, device=dev)
+    p = opt._params()
+    _lib.check(_lib.load().mlmcb_level_sums(
+        C.byref(p), opt._model, opt._payoff_kind, l, M, n, opt.seed, offset,
+        opt._flags() if flags is None else flags, 0, 0, out.data_ptr(),
+        Pf.data_ptr() if per_path else None, Pc.data_ptr() if per_path else None))
+    torch.cuda.synchronize()
+    if per_path:
+        return out.cpu().numpy(), Pf.cpu().numpy(), Pc.cpu().numpy()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("sampler", [_lib.SAMPLER_F32BM, _lib.SAMPLER_F64BM])
+def test_sampler_is_standard_normal(cuda_lib, sampler):
+    import torch
+    from scipy import stats
+    n_paths, n_steps = 1 << 16, 64
+    out = torch.empty(n_steps * n_paths, dtype=torch.float64, device="cuda")
+    _lib.check(cuda_lib.mlmcb_sampler_probe(sampler, 12345, 3, 0, n_paths, n_steps, 0, 0, out.data_ptr()))
+    torch.cuda.synchronize()
+    z = out.cpu().numpy()
+    N = z.size                                  # 4.2e6 draws
+    assert abs(z.mean()) < 4 / np.sqrt(N)
+    assert abs(z.var() - 1) < 4 * np.sqrt(2 / N)
+    assert abs(stats.skew(z)) < 4 * np.sqrt(6 / N)
+    assert abs(stats.kurtosis(z)) < 4 * np.sqrt(24 / N)
+    assert stats.kstest(z[:1000000], "norm").pvalue > 1e-3
+    assert 4.5 < np.abs(z).max() < 7.5          # tails are populated and finite
+    # tail mass: P(|z|>3) = 2.6998e-3
+    p3 = (np.abs(z) > 3).mean()
+    assert abs(p3 - 2.6998e-3) < 4 * np.sqrt(2.6998e-3 / N)
+    # consecutive steps of a path and neighbouring paths are uncorrelated
+    zz = z.reshape(n_steps, n_paths)
+    assert abs(np.mean(zz[:-1] * zz[1:])) < 4 / np.sqrt(zz[:-1].size)
+    assert abs(np.mean(zz[:, :-1] * zz[:, 1:])) < 4 / np.sqrt(zz[:, :-1].size)
+    # a different level tag / seed / path offset gives a different stream; same arguments the same one
+    out2 = torch.empty_like(out)
+    _lib.check(cuda_lib.mlmcb_sampler_probe(sampler, 12345, 3, 0, n_paths, n_steps, 0, 0, out2.data_ptr()))
+    assert torch.equal(out, out2)
+    _lib.check(cuda_lib.mlmcb_sampler_probe(sampler, 12345, 4, 0, n_paths, n_steps, 0, 0, out2.data_ptr()))
+    assert abs(np.corrcoef(z, out2.cpu().numpy())[0, 1]) < 4 / np.sqrt(N)
+    _lib.check(cuda_lib.mlmcb_sampler_probe(sampler, 12345, 3, 1000, n_paths, n_steps, 0, 0, out2.data_ptr()))
+    z3 = out2.cpu().numpy().reshape(n_steps, n_paths)
+    assert np.array_equal(z3[:, :-1000], zz[:, 1000:])       # ids are global: offset shifts the window
+
+
+def _moments(s, n, l):
+    m_d, m_f = s[0] / n, s[2] / n
+    v_d, v_f = s[1] / n - m_d ** 2, s[3] / n - m_f ** 2
+    return m_d, v_d, m_f, v_f
+
+
+CASES = [(c, l, M) for c in sorted(CLASS_CODES) for (l, M) in ((0, 2), (1, 2), (2, 4), (3, 4), (4, 2))]
+
+
+@pytest.mark.parametrize("cname,l,M", CASES)
+def test_level_moments_match_reference_port(cuda_lib, c_oracle, cname, l, M):
+    """Means and variances of dP and Pf within 4 combined standard errors of the pinned C port of
+    the reference (own generator), both samplers; plus the 7-sum identity on the GPU result."""
+    model, pay = CLASS_CODES[cname]
+    n_gpu, n_cpu = 4_000_000, 400_000
+    ref = c_oracle.level_sums(O.Params(), model, pay, l, M, n_cpu, seed=11 + l, nthreads=8)
+    rm_d, rv_d, rm_f, rv_f = _moments(ref, n_cpu, l)
+    for sampler in ("f32bm", "f64bm"):
+        opt = getattr(mm, cname)(seed=2024, sampler=sampler)
+        s = level_sums(opt, n_gpu, l, M)
+        m_d, v_d, m_f, v_f = _moments(s, n_gpu, l)
+        se = lambda v: np.sqrt(v / n_gpu + v / n_cpu)
+        assert abs(m_d - rm_d) < 4 * se(max(v_d, rv_d)) + 1e-15, (sampler, m_d, rm_d)
+        assert abs(m_f - rm_f) < 4 * se(max(v_f, rv_f)), (sampler, m_f, rm_f)
+        # variances: s.e. of a sample variance ~ sqrt((m4 - v^2)/n); bound by a generous kurtosis of 60
+        assert abs(v_f - rv_f) < 4 * rv_f * np.sqrt(60 / n_cpu), (sampler, v_f, rv_f)
+        if l > 0 and rv_d > 0:
+            tol = 4 * rv_d * np.sqrt((3000 if pay == O.DIGITAL else 300) / n_cpu)
+            assert abs(v_d - rv_d) < tol, (sampler, v_d, rv_d)
+        if l == 0:
+            assert s[0] == s[2] and s[1] == s[3] and not s[4:].any()
+        else:
+            assert s[1] == pytest.approx(s[3] - 2 * s[6] + s[5], rel=1e-9, abs=1e-9 * s[3])
+
+
+def test_per_path_outputs_consistent_and_deterministic(cuda_lib):
+    for cname in ("Euro_GBM", "Asian_GBM", "Lookback_GBM", "Digital_GBM", "Euro_Merton", "Asian_Merton",
+                  "Lookback_Merton", "Digital_Merton"):
+        opt = getattr(mm, cname)(seed=5)
+        n = 100_003
+        s, Pf, Pc = level_sums(opt, n, 3, 4, per_path=True)
+        want = O.seven_sums(Pf, Pc, 3)
+        np.testing.assert_allclose(s, want, rtol=1e-12)
+        s2, Pf2, Pc2 = level_sums(opt, n, 3, 4, per_path=True)
+        assert np.array_equal(s, s2) and np.array_equal(Pf, Pf2) and np.array_equal(Pc, Pc2)   # run-to-run
+        # global ids: two half calls reproduce the per-path values of one call
+        _, Pfa, _ = level_sums(opt, 50_000, 3, 4, offset=0, per_path=True)
+        _, Pfb, _ = level_sums(opt, n - 50_000, 3, 4, offset=50_000, per_path=True)
+        assert np.array_equal(np.concatenate([Pfa, Pfb]), Pf)
+        # another seed gives other paths
+        s3 = level_sums(getattr(mm, cname)(seed=6), n, 3, 4)
+        assert s3[2] != s[2]
+
+
+def test_coupling_fine_equals_previous_level_distribution(cuda_lib):
+    """Telescoping check: E[Pc at level l] = E[Pf at level l-1] (same discretisation)."""
+    for cname in ("Euro_GBM", "Asian_GBM", "Lookback_GBM", "Euro_Merton", "Asian_Merton", "Lookback_Merton"):
+        n = 4_000_000
+        a = level_sums(getattr(mm, cname)(seed=1), n, 3, 4)
+        b = level_sums(getattr(mm, cname)(seed=2), n, 2, 4)
+        mc, vc = a[4] / n, a[5] / n - (a[4] / n) ** 2
+        mf, vf = b[2] / n, b[3] / n - (b[2] / n) ** 2
+        assert abs(mc - mf) < 4 * np.sqrt(vc / n + vf / n), cname
+
+
+def test_generic_M_and_edge_sizes(cuda_lib, c_oracle):
+    # odd M takes the generic (counter) path; compare with the C port
+    for cname in ("Euro_GBM", "Asian_Merton"):
+        model, pay = CLASS_CODES[cname]
+        n = 2_000_000
+        s = level_sums(getattr(mm, cname)(seed=3), n, 3, 3)
+        ref = c_oracle.level_sums(O.Params(), model, pay, 3, 3, 300_000, seed=4, nthreads=8)
+        m, v = s[0] / n, s[1] / n - (s[0] / n) ** 2
+        rm = ref[0] / 300_000
+        assert abs(m - rm) < 4 * np.sqrt(v / n + v / 300_000)
+    opt = mm.Euro_GBM()
+    assert not level_sums(opt, 0, 2, 2).any()                      # empty request
+    s1 = level_sums(opt, 1, 2, 2)                                  # a single path
+    assert s1[3] == pytest.approx(s1[2] ** 2)
+    big = level_sums(opt, 1000, 10, 4)                             # 1 048 576 steps per path
+    assert np.isfinite(big).all()
+
+
+def test_fp32_opt_in_runs_and_is_close(cuda_lib):
+    n = 2_000_000
+    opt64, opt32 = mm.Asian_GBM(seed=9), mm.Asian_GBM(seed=9, fp32=True)
+    a, b = level_sums(opt64, n, 3, 4), level_sums(opt32, n, 3, 4)
+    assert a[2] / n == pytest.approx(b[2] / n, rel=1e-4)
+    assert a[0] / n == pytest.approx(b[0] / n, abs=5e-3)
+
+
+def test_looper_host_call_and_sweep(cuda_lib):
+    opt = mm.Lookback_GBM(seed=77)
+    s = opt.looper(200_000, 2, 4, False)
+    assert s.shape == (7,) and s.dtype == np.float64
+    opt2 = mm.Lookback_GBM(seed=77)
+    sw = opt2.level_sweep(Lmax=4, Nsamples=200_000, M=4)
+    assert sw.shape == (7, 5)
+    assert np.array_equal(sw[:, 2], s)                             # same ids, same sums, sweep or single
+    # second call on the same object uses fresh ids
+    assert not np.array_equal(opt.looper(200_000, 2, 4, False), s)
+    Pf, Pc = mm.Euro_GBM().payoff(1000, 0, 2)
+    assert Pf.shape == (1000,) and np.all(Pc == 100.0)             # l==0: raw coarse output (:82)

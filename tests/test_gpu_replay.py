@@ -1,0 +1,116 @@
+"""GPU: replay parity - the CUDA path fed the reference's own draws (north-star check (a)).
+
+Through the C ABI (mlmcb_replay_gbm / mlmcb_replay_merton) on every golden case generated from the
+unmodified reference.  Bar: GBM with the reference-order arithmetic policy is BIT-EXACT; the
+production (FMA) policy and Merton are within 1e-12 * max(|P|, K e^{-rT})."""
+import numpy as np
+import pytest
+
+import multilevel_mc_sdes_b200 as mm
+from oracle import np_oracle as O
+from tests.helpers import case_kwargs, gbm_cases, merton_cases, oracle_params, payoff_tol, regen_Z
+
+pytestmark = pytest.mark.gpu
+
+
+def _opt(cname, kw_name):
+    return getattr(mm, cname)(**case_kwargs(cname, kw_name))
+
+
+def test_gbm_replay_exact_policy_is_bit_exact(golden, cuda_lib):
+    n = 0
+    for c in gbm_cases(golden["payoffs_gbm"]):
+        Pf, Pc = _opt(c["cname"], c["kw_name"]).payoff_replay(regen_Z(c), c["l"], c["M"], arith="exact")
+        assert np.array_equal(Pf, c["Pf"]), (c["cname"], c["kw_name"], c["l"], c["M"])
+        assert np.array_equal(Pc, c["Pc"]), (c["cname"], c["kw_name"], c["l"], c["M"])
+        n += 1
+    assert n > 100
+
+
+def test_gbm_replay_production_policy_within_1e12(golden, cuda_lib):
+    worst = 0.0
+    for c in gbm_cases(golden["payoffs_gbm"]):
+        p = oracle_params(c["cname"], c["kw_name"])
+        Pf, Pc = _opt(c["cname"], c["kw_name"]).payoff_replay(regen_Z(c), c["l"], c["M"], arith="fast")
+        if c["cname"] == "Digital_GBM":
+            # an indicator may flip only if X is within rounding of K (astronomically rare)
+            assert np.array_equal(Pf, c["Pf"]) and np.array_equal(Pc, c["Pc"])
+            continue
+        ef, ec = np.abs(Pf - c["Pf"]), np.abs(Pc - c["Pc"])
+        assert np.all(ef <= payoff_tol(p, c["Pf"])), (c["cname"], c["l"], c["M"], ef.max())
+        assert np.all(ec <= payoff_tol(p, c["Pc"])), (c["cname"], c["l"], c["M"], ec.max())
+        worst = max(worst, (ef / payoff_tol(p, c["Pf"])).max())
+    assert worst < 1.0
+
+
+@pytest.mark.parametrize("arith", ["exact", "fast"])
+def test_merton_replay_within_1e12(golden, cuda_lib, arith):
+    n = 0
+    for c in merton_cases(golden["payoffs_merton"]):
+        p = oracle_params(c["cname"], c["kw_name"])
+        Pf, Pc = _opt(c["cname"], c["kw_name"]).payoff_replay(c["packed"], c["l"], c["M"], arith=arith)
+        if c["cname"] == "Digital_Merton":
+            assert np.array_equal(Pf, c["Pf"]) and np.array_equal(Pc, c["Pc"])
+        else:
+            assert np.all(np.abs(Pf - c["Pf"]) <= payoff_tol(p, c["Pf"])), (c["idx"], np.abs(Pf - c["Pf"]).max())
+            assert np.all(np.abs(Pc - c["Pc"]) <= payoff_tol(p, c["Pc"])), (c["idx"], np.abs(Pc - c["Pc"]).max())
+        n += 1
+    assert n > 60
+
+
+def test_replay_large_level_against_oracle(cuda_lib, c_oracle):
+    """l=8, M=4 (65 536 fine steps) and l=10, M=2: sizes past the fixtures, checked against the
+    pinned C restatement on the same seeded normals."""
+    for (l, M, n) in ((8, 4, 96), (10, 2, 128)):
+        rs = np.random.RandomState(1234 + l)
+        Z = rs.randn(M ** l, n)
+        for cname, pay in (("Euro_GBM", O.EURO), ("Asian_GBM", O.ASIAN), ("Lookback_GBM", O.LOOKBACK)):
+            p = O.Params()
+            ref_f, ref_c = c_oracle.gbm_replay(p, pay, l, M, Z)
+            opt = getattr(mm, cname)()
+            Pf, Pc = opt.payoff_replay(Z, l, M, arith="exact")
+            assert np.array_equal(Pf, ref_f) and np.array_equal(Pc, ref_c)
+            Pf, Pc = opt.payoff_replay(Z, l, M, arith="fast")
+            assert np.all(np.abs(Pf - ref_f) <= payoff_tol(p, ref_f))
+            assert np.all(np.abs(Pc - ref_c) <= payoff_tol(p, ref_c))
+
+
+def test_replay_sums_row_order(cuda_lib, golden):
+    """d_out7 of the replay entry point follows looper's row order (:955) and l==0 convention (:949)."""
+    import ctypes as C
+    import torch
+    from multilevel_mc_sdes_b200 import _lib
+    for c in list(gbm_cases(golden["payoffs_gbm"]))[:12]:
+        opt = _opt(c["cname"], c["kw_name"])
+        Z = torch.as_tensor(regen_Z(c), device="cuda")
+        n = c["n"]
+        Pf = torch.empty(n, dtype=torch.float64, device="cuda")
+        Pc = torch.empty(n, dtype=torch.float64, device="cuda")
+        out = torch.zeros(7, dtype=torch.float64, device="cuda")
+        p = opt._params()
+        _lib.check(cuda_lib.mlmcb_replay_gbm(C.byref(p), opt._payoff_kind, c["l"], c["M"], n, Z.data_ptr(),
+                                             _lib.ARITH_EXACT, 0, 0, Pf.data_ptr(), Pc.data_ptr(), out.data_ptr()))
+        torch.cuda.synchronize()
+        want = O.seven_sums(c["Pf"], c["Pc"], c["l"])
+        np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-13, atol=1e-9)
+
+
+def test_replay_edge_cases(cuda_lib):
+    opt = mm.Euro_GBM()
+    # a single path, l=0
+    Pf, Pc = opt.payoff_replay(np.array([[0.3]]), 0, 2, arith="exact")
+    p = O.Params()
+    ref = O.level_payoffs(p, O.GBM, O.EURO, 0, 2, Z=np.array([[0.3]]))
+    assert Pf[0] == ref[0][0] and Pc[0] == 100.0
+    # wrong number of rows is rejected before any launch
+    with pytest.raises(ValueError):
+        opt.payoff_replay(np.zeros((3, 4)), 2, 2)
+    # Merton path with no jumps at all before T and one with several
+    m = mm.Euro_Merton()
+    packed = dict(zW=np.array([0.1, -0.2, 0.3, 0.4, 0.5, 0.0, -1.0, 0.7]), offW=np.array([0, 2, 8], dtype=np.int64),
+                  zQ=np.array([0.2, -0.3, 0.1, 1.0]), offQ=np.array([0, 0, 4], dtype=np.int64),
+                  E=np.array([5.0, 0.1, 0.3, 0.2, 0.05, 9.0]), offE=np.array([0, 1, 6], dtype=np.int64))
+    Pf, Pc = m.payoff_replay(packed, 1, 2, arith="exact")
+    want = O.level_payoffs(O.Params(), O.MERTON, O.EURO, 1, 2, n=2, draws=O.ReplayDraws(packed))
+    np.testing.assert_allclose(Pf, want[0], rtol=1e-13)
+    np.testing.assert_allclose(Pc, want[1], rtol=1e-13)

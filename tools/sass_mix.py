@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""Instruction mix of the innermost loop(s) of one kernel in a built library.
+
+    python tools/sass_mix.py <lib.so> '<demangled-name substring>' [--dump]
+
+Finds backward branches in the kernel's SASS, takes each loop body [target, branch] and prints
+an opcode histogram grouped by pipe, plus instructions per fine step (loop handles 4 steps).
+Static counts only; the dynamic numbers come from ncu (profiles/).
+"""
+import collections
+import re
+import subprocess
+import sys
+
+PIPES = [
+    ("fp64", r"^(DFMA|DADD|DMUL|DSETP|DMNMX)"),
+    ("fma/imad", r"^(FFMA|FMUL|FADD|IMAD|HFMA2)"),
+    ("alu", r"^(LOP3|IADD3|IADD|SHF|PRMT|ISETP|FSETP|SEL|FSEL|MOV|LEA|FMNMX|LOP|PLOP3|VIADD|IABS|FLO|POPC|I2FP|VIMNMX|UMOV|FCHK|R2P|P2R|FSWZADD|IMNMX)"),
+    ("xu(mufu/cvt)", r"^(MUFU|I2F|F2F|F2I|FRND)"),
+    ("uniform", r"^(U[A-Z0-9]+|R2UR|S2UR|LDCU)"),
+    ("mem", r"^(LD|ST|ATOM|RED|LDC|LDS|STS|LDG|STG|LDL|STL)"),
+    ("ctrl", r"^(BRA|BSSY|BSYNC|EXIT|WARPSYNC|BAR|CALL|RET|NOP|YIELD|BREAK|BMOV)"),
+]
+
+
+def kernels(lib):
+    out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    cur, body, res = None, [], {}
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            if cur:
+                res[cur] = body
+            cur, body = m.group(1), []
+            continue
+        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
+        if m and cur:
+            body.append((int(m.group(1), 16), m.group(2).strip()))
+    if cur:
+        res[cur] = body
+    return res
+
+
+def main():
+    lib, pat = sys.argv[1], sys.argv[2]
+    dump = "--dump" in sys.argv
+    ks = kernels(lib)
+    names = subprocess.run(["c++filt"] + list(ks), capture_output=True, text=True).stdout.splitlines()
+    for mangled, name in zip(ks, names):
+        if pat not in name:
+            continue
+        body = ks[mangled]
+        print("==", name.split("(")[0], f"({len(body)} instrs)")
+        loops = []
+        for addr, ins in body:
+            m = re.search(r"BRA(?:\.U)?\s+(?:\S+,\s+)?(0x[0-9a-f]+)", ins)
+            if m and int(m.group(1), 16) <= addr:
+                loops.append((int(m.group(1), 16), addr))
+        for lo, hi in loops:
+            ins = [i for a, i in body if lo <= a <= hi]
+            ops = [re.sub(r"^@!?U?P\d+\s+", "", i).split()[0] for i in ins]
+            if not any(o.startswith(("DFMA", "FFMA")) for o in ops):
+                continue
+            hist = collections.Counter()
+            full = collections.Counter(o.split(".")[0] for o in ops)
+            for o in ops:
+                for pipe, rx in PIPES:
+                    if re.match(rx, o):
+                        hist[pipe] += 1
+                        break
+                else:
+                    hist["other:" + o.split(".")[0]] += 1
+            print(f"  loop 0x{lo:x}-0x{hi:x}: {len(ins)} instrs = {len(ins) / 4:.1f}/step  ", dict(hist))
+            print("     ", dict(full.most_common()))
+            if dump:
+                for a, i in body:
+                    if lo <= a <= hi:
+                        print(f"      {a:05x}  {i}")
+
+
+if __name__ == "__main__":
+    main()
