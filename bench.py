@@ -114,7 +114,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.sm, self.reasons, self.sm_max = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.proc = None
 
     def run(self):
@@ -128,7 +128,7 @@ class ClockSampler(threading.Thread):
             return
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            if self._stop.is_set():
+            if self._halt.is_set():
                 break
             parts = [p.strip() for p in line.split(",")]
             try:
@@ -141,7 +141,7 @@ class ClockSampler(threading.Thread):
                     self.reasons.add(nm)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)

@@ -14,11 +14,16 @@ def price(sums, N):
 def test_readme_example_within_eps_of_BS(cuda_lib):
     """BASELINE config #1: Euro_GBM(125,105,.02,.5).mlmc(0.01) vs BS() = 35.17419437739385, with
     alpha_0 = beta_0 = None exactly as the README writes it."""
-    opt = mm.Euro_GBM(X0=125, K=105, r=0.02, sig=0.5, verbose=False)
-    sums, N = opt.mlmc(eps=0.01)
-    assert sums.shape == (7, len(N)) and N.dtype == np.float64
-    assert abs(price(sums, N) - opt.BS()) < 0.01
-    assert opt.alpha_0 is not None and opt.beta_0 is not None      # warm_start side effect (:1037)
+    errs = []
+    for seed in range(5):
+        opt = mm.Euro_GBM(X0=125, K=105, r=0.02, sig=0.5, verbose=False, seed=seed)
+        sums, N = opt.mlmc(eps=0.01)
+        assert sums.shape == (7, len(N)) and N.dtype == np.float64
+        errs.append(abs(price(sums, N) - opt.BS()))
+        assert opt.alpha_0 is not None and opt.beta_0 is not None  # warm_start side effect (:1037)
+    # eps is an RMS target (half bias^2, half variance, :1021/:1025): the typical run is inside
+    # eps, no run is far outside
+    assert np.median(errs) < 0.01 and max(errs) < 0.03, errs
 
 
 def test_rms_error_over_seeds_is_below_eps(cuda_lib):

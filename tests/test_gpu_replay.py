@@ -50,7 +50,11 @@ def test_merton_replay_within_1e12(golden, cuda_lib, arith):
         p = oracle_params(c["cname"], c["kw_name"])
         Pf, Pc = _opt(c["cname"], c["kw_name"]).payoff_replay(c["packed"], c["l"], c["M"], arith=arith)
         if c["cname"] == "Digital_Merton":
-            assert np.array_equal(Pf, c["Pf"]) and np.array_equal(Pc, c["Pc"])
+            assert np.array_equal(Pf, c["Pf"])
+            if c["l"] == 0:      # second item is the raw coarse value (:133), which jumps do move
+                assert np.all(np.abs(Pc - c["Pc"]) <= 1e-12 * np.abs(c["Pc"]))
+            else:
+                assert np.array_equal(Pc, c["Pc"])
         else:
             assert np.all(np.abs(Pf - c["Pf"]) <= payoff_tol(p, c["Pf"])), (c["idx"], np.abs(Pf - c["Pf"]).max())
             assert np.all(np.abs(Pc - c["Pc"]) <= payoff_tol(p, c["Pc"])), (c["idx"], np.abs(Pc - c["Pc"]).max())
