@@ -63,7 +63,7 @@ int device_info(int dev, DeviceInfo** out) {
 int ipow_checked(int M, int l, ull* out) {
     ull n = 1;
     for (int i = 0; i < l; ++i) {
-        if (n > (1ull << 40) / (ull)M) return fail(MLMCB_EINVAL, "M**l = %d**%d exceeds 2^40 fine steps", M, l);
+        if (n > (1ull << 33) / (ull)M) return fail(MLMCB_EINVAL, "M**l = %d**%d exceeds 2^33 fine steps", M, l);
         n *= (ull)M;
     }
     *out = n;

@@ -20,6 +20,9 @@
 //   AR_EXACT  the reference's left-to-right expression order with explicitly rounded
 //             __dmul_rn/__dadd_rn (never contracted) - replay mode, bit-exact vs numpy for GBM.
 #pragma once
+#ifndef MLMCB_PACKED_F32
+#define MLMCB_PACKED_F32 1
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -76,16 +79,16 @@ __device__ __forceinline__ U4 philox10(const LevelConsts& C, uint32_t c0, uint32
     return c;
 }
 
-// Counter layout (128 bit):  c0,c1 = draw-block index (60 bit) | stream kind (4 bit, top of c1)
+// Counter layout (128 bit):  c0 = draw-block index (32 bit: 4 steps per block, M**l <= 2^33),
+//                            c1 = stream kind (4 bit, top of the word)
 //                            c2,c3 = global path id (48 bit) | level (8 bit) | 0
 // key = 64-bit seed.  Distinct (seed, level, path id, kind, block) -> distinct counter, so
 // repeated looper calls (advancing path_offset), levels, ranks and the Merton jump stream never
 // reuse a draw.
 enum { STREAM_GRID = 0, STREAM_JUMP = 1 };
 
-__device__ __forceinline__ U4 philox_at(const LevelConsts& C, ull pid, uint32_t kind, ull blk) {
-    return philox10(C, (uint32_t)blk, (uint32_t)(blk >> 32) | (kind << 28),
-                    (uint32_t)pid, ((uint32_t)(pid >> 32) & 0xFFFFu) | C.ctr3_tag);
+__device__ __forceinline__ U4 philox_at(const LevelConsts& C, ull pid, uint32_t kind, uint32_t blk) {
+    return philox10(C, blk, kind << 28, (uint32_t)pid, ((uint32_t)(pid >> 32) & 0xFFFFu) | C.ctr3_tag);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -96,17 +99,66 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float lg2_approx(float x) {   // MUFU.LG2, no denormal fix-up (x >= 2^-33)
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
-// fp32 Box-Muller from two 32-bit words: u in (0,1] for the radius (tail reaches 6.6 sigma),
-// a 32-bit angle.  MUFU.LG2 + MUFU.SQRT for the radius, polynomial sin/cos of pi*x.
+// fp32 Box-Muller.  Radius: u = (w+0.5)*2^-32 in (0,1] from a full 32-bit word (tail reaches
+// 6.7 sigma), r = sqrt(-2 ln u) with MUFU.LG2 + MUFU.SQRT.  Angle: theta = pi*h, h in [-1/2,1/2)
+// from a signed 32-bit word, cos/sin by degree-8/9 minimax polynomials in h (abs error 2e-7, no
+// range reduction, no MUFU), and one spare random bit flips the sign of r so (r cos, r sin)
+// covers the whole circle.  21 instructions per pair, 2 of them on the XU pipe.
+#define MLMCB_Q0 3.1415927410125732f
+#define MLMCB_Q1 -5.167710304260254f
+#define MLMCB_Q2 2.5500776767730713f
+#define MLMCB_Q3 -0.5982921719551086f
+#define MLMCB_Q4 0.07765940576791763f
+#define MLMCB_C0 0.9999999403953552f
+#define MLMCB_C1 -4.934792995452881f
+#define MLMCB_C2 4.058412075042725f
+#define MLMCB_C3 -1.3318802118301392f
+#define MLMCB_C4 0.2196968048810959f
+#define MLMCB_NEG2LN2 -1.3862943611198906f
+
 __device__ __forceinline__ void bm_pair_f32(uint32_t ru, uint32_t ra, float& z0, float& z1) {
     float u = fmaf(__uint2float_rn(ru), 0x1p-32f, 0x1p-33f);
-    float rad = sqrt_approx(__log2f(u) * -1.3862943611198906f);     // sqrt(-2 ln u)
-    float x = __int2float_rn((int)ra) * 0x1p-31f;                   // angle / pi in [-1,1)
-    float sn, cs;
-    sincospif(x, &sn, &cs);
-    z0 = rad * cs;
-    z1 = rad * sn;
+    float rad = sqrt_approx(lg2_approx(u) * MLMCB_NEG2LN2);            // sqrt(-2 ln u)
+    rad = __uint_as_float(__float_as_uint(rad) ^ (ru << 31));       // random sign: whole circle
+    float h = __int2float_rn((int)ra) * 0x1p-32f;                   // angle / pi in [-1/2,1/2)
+    float T = h * h;
+    float q = fmaf(T, MLMCB_Q4, MLMCB_Q3), c = fmaf(T, MLMCB_C4, MLMCB_C3);
+    q = fmaf(q, T, MLMCB_Q2); c = fmaf(c, T, MLMCB_C2);
+    q = fmaf(q, T, MLMCB_Q1); c = fmaf(c, T, MLMCB_C1);
+    q = fmaf(q, T, MLMCB_Q0); c = fmaf(c, T, MLMCB_C0);
+    z0 = rad * c;                                                    // r cos(pi h)
+    z1 = (rad * h) * q;                                              // r sin(pi h)
+}
+
+// The same for two pairs at once with Blackwell's packed fp32 pipe (FFMA2/FMUL2): the two
+// independent pairs of one Philox block ride in the .x/.y halves, halving the fp32 issue slots.
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+
+__device__ __forceinline__ void bm_quad_f32(U4 w, float z[4]) {
+#if MLMCB_PACKED_F32
+    float2 u = __ffma2_rn(make_float2(__uint2float_rn(w.x), __uint2float_rn(w.z)), f2(0x1p-32f), f2(0x1p-33f));
+    float2 s = __fmul2_rn(make_float2(lg2_approx(u.x), lg2_approx(u.y)), f2(MLMCB_NEG2LN2));
+    float2 rad = make_float2(sqrt_approx(s.x), sqrt_approx(s.y));
+    rad.x = __uint_as_float(__float_as_uint(rad.x) ^ (w.x << 31));
+    rad.y = __uint_as_float(__float_as_uint(rad.y) ^ (w.z << 31));
+    float2 h = __fmul2_rn(make_float2(__int2float_rn((int)w.y), __int2float_rn((int)w.w)), f2(0x1p-32f));
+    float2 T = __fmul2_rn(h, h);
+    float2 q = __ffma2_rn(T, f2(MLMCB_Q4), f2(MLMCB_Q3)), c = __ffma2_rn(T, f2(MLMCB_C4), f2(MLMCB_C3));
+    q = __ffma2_rn(q, T, f2(MLMCB_Q2)); c = __ffma2_rn(c, T, f2(MLMCB_C2));
+    q = __ffma2_rn(q, T, f2(MLMCB_Q1)); c = __ffma2_rn(c, T, f2(MLMCB_C1));
+    q = __ffma2_rn(q, T, f2(MLMCB_Q0)); c = __ffma2_rn(c, T, f2(MLMCB_C0));
+    float2 zc = __fmul2_rn(rad, c), zs = __fmul2_rn(__fmul2_rn(rad, h), q);
+    z[0] = zc.x; z[1] = zs.x; z[2] = zc.y; z[3] = zs.y;
+#else
+    bm_pair_f32(w.x, w.y, z[0], z[1]);
+    bm_pair_f32(w.z, w.w, z[2], z[3]);
+#endif
 }
 
 __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {   // (0,1), 53 random bits
@@ -126,7 +178,7 @@ template <typename R> __device__ __forceinline__ R fma_(R a, R b, R c);
 template <> __device__ __forceinline__ double fma_<double>(double a, double b, double c) { return fma(a, b, c); }
 template <> __device__ __forceinline__ float fma_<float>(float a, float b, float c) { return fmaf(a, b, c); }
 template <typename R> __device__ __forceinline__ R min_(R a, R b);
-template <> __device__ __forceinline__ double min_<double>(double a, double b) { return fmin(a, b); }
+template <> __device__ __forceinline__ double min_<double>(double a, double b) { return b < a ? b : a; }   // DSETP + 2 SEL; no NaN on this path
 template <> __device__ __forceinline__ float min_<float>(float a, float b) { return fminf(a, b); }
 
 // Four grid-step normals for (path, block b) = steps 4b+1 .. 4b+4.
@@ -134,13 +186,11 @@ template <typename R, int SAMP>
 struct PhiloxSource {
     const LevelConsts& C;
     ull pid;
-    __device__ __forceinline__ void load4(ull b, R z[4]) const {
+    __device__ __forceinline__ void load4(uint32_t b, R z[4]) const {
         if (SAMP == SAMP_F32BM) {
-            U4 r = philox_at(C, pid, STREAM_GRID, b);
-            float f0, f1, f2, f3;
-            bm_pair_f32(r.x, r.y, f0, f1);
-            bm_pair_f32(r.z, r.w, f2, f3);
-            z[0] = (R)f0; z[1] = (R)f1; z[2] = (R)f2; z[3] = (R)f3;
+            float f[4];
+            bm_quad_f32(philox_at(C, pid, STREAM_GRID, b), f);
+            z[0] = (R)f[0]; z[1] = (R)f[1]; z[2] = (R)f[2]; z[3] = (R)f[3];
         } else {
             U4 r = philox_at(C, pid, STREAM_GRID, 2 * b), s = philox_at(C, pid, STREAM_GRID, 2 * b + 1);
             double d0, d1, d2, d3;
@@ -155,10 +205,10 @@ struct PhiloxSource {
 struct ReplaySource {
     const double* Z;
     ull n, i, nsteps;
-    __device__ __forceinline__ void load4(ull b, double z[4]) const {
+    __device__ __forceinline__ void load4(uint32_t b, double z[4]) const {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            ull s = 4 * b + k;
+            ull s = 4 * (ull)b + k;
             z[k] = s < nsteps ? Z[s * n + i] : 0.0;
         }
     }
@@ -270,6 +320,13 @@ __device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source
         if (FN == FN_AVG) Ff += Xf;                                      \
         if (FN == FN_MIN) Ff = min_<R>(Ff, Xf);                          \
     }
+#define MLMCB_FINE_NOSUM(zz)                                             \
+    {                                                                    \
+        R t_ = fma_<R>(bf, (zz), af);                                    \
+        Xf = fma_<R>(Xf, t_, Xf);                                        \
+        if (FN == FN_AVG) Ff += Xf;                                      \
+        if (FN == FN_MIN) Ff = min_<R>(Ff, Xf);                          \
+    }
 #define MLMCB_COARSE()                                                   \
     {                                                                    \
         R t_ = fma_<R>(bf, sz, ac);                                      \
@@ -279,16 +336,23 @@ __device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source
         if (FN == FN_MIN) Fc = min_<R>(Fc, Xc);                          \
     }
 
-    const ull nblk = C.nsteps >> 2;
-    for (ull b = 0; b < nblk; ++b) {
+    const uint32_t nblk = (uint32_t)(C.nsteps >> 2);
+    for (uint32_t b = 0; b < nblk; ++b) {
         R z[4];
         src.load4(b, z);
+        if (MT == 4) {               // coarse increment as a tree, off the fine chain
+            const R s4 = (z[0] + z[1]) + (z[2] + z[3]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            MLMCB_FINE(z[k]);
-            if (MT == 4) { if (k == 3) MLMCB_COARSE(); }
-            else if (MT == 2) { if (k & 1) MLMCB_COARSE(); }
-            else { if (++cm == M) { cm = 0; MLMCB_COARSE(); } }
+            for (int k = 0; k < 4; ++k) MLMCB_FINE_NOSUM(z[k]);
+            sz = s4;
+            MLMCB_COARSE();
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                MLMCB_FINE(z[k]);
+                if (MT == 2) { if (k & 1) MLMCB_COARSE(); }
+                else { if (++cm == M) { cm = 0; MLMCB_COARSE(); } }
+            }
         }
     }
     const int rem = (int)(C.nsteps & 3);
@@ -304,6 +368,7 @@ __device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source
         }
     }
 #undef MLMCB_FINE
+#undef MLMCB_FINE_NOSUM
 #undef MLMCB_COARSE
 
     if (FN == FN_AVG) {              // trapezoid: dt*(X0/2 + sum_{j<=N} X_j - X_N/2)/T   :369-386
@@ -457,7 +522,7 @@ struct JD {
 // Jump-stream draws for jump number jk of a path: inter-arrival time, jump-size normal and the
 // Brownian normal of the adaptive step that ends at that jump.
 template <typename R, int SAMP>
-__device__ __forceinline__ void jump_draws(const LevelConsts& C, ull pid, ull jk, double& gap, R& zq, R& zw) {
+__device__ __forceinline__ void jump_draws(const LevelConsts& C, ull pid, uint32_t jk, double& gap, R& zq, R& zw) {
     if (SAMP == SAMP_F32BM) {
         U4 r = philox_at(C, pid, STREAM_JUMP, jk);
         gap = -log(u53(r.x, r.y)) * C.inv_lam;
@@ -483,18 +548,18 @@ __device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid,
     JD<R, FN, AR_FAST> st;
     st.init(C);
     const R af = (R)C.a_f, bf = (R)C.b_f, ac = (R)C.a_c;
-    ull jk = 0;
+    uint32_t jk = 0;
     double gap, tau;
     R zq, zwj;
     jump_draws<R, SAMP>(C, pid, jk, gap, zq, zwj);
     tau = gap;                                                           // :454
     int cm = 0;
     const int M = C.M;
-    const ull nblk = (C.nsteps + 3) >> 2;
-    for (ull b = 0; b < nblk; ++b) {
+    const uint32_t nblk = (uint32_t)((C.nsteps + 3) >> 2);
+    for (uint32_t b = 0; b < nblk; ++b) {
         R z[4];
         src.load4(b, z);
-        const ull j0 = 4 * b;
+        const ull j0 = 4 * (ull)b;
         const bool full = j0 + 4 <= C.nsteps;
         const double t_end = (double)(j0 + 4) * C.dt;
         if (MT != 0 && full && tau >= t_end) {
@@ -648,12 +713,12 @@ __global__ void sampler_probe_kernel(const __grid_constant__ LevelConsts C, ull 
     const ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C.n_paths) return;
     PhiloxSource<double, SAMP> src{C, C.path_offset + i};
-    for (ull b = 0; 4 * b < n_steps; ++b) {
+    for (uint32_t b = 0; 4 * (ull)b < n_steps; ++b) {
         double z[4];
         src.load4(b, z);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (4 * b + k < n_steps) out[(4 * b + k) * C.n_paths + i] = z[k];
+            if (4 * (ull)b + k < n_steps) out[(4 * (ull)b + k) * C.n_paths + i] = z[k];
     }
 }
 
