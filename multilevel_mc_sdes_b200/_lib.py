@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmlmcb.so")
+LIB_PATH = os.environ.get("MLMCB_LIB") or os.path.join(_HERE, "csrc", "libmlmcb.so")   # MLMCB_LIB: kernel experiments
 
 GBM, MERTON = 0, 1
 EURO, ASIAN, LOOKBACK, DIGITAL = 0, 1, 2, 3

@@ -21,7 +21,10 @@
 //             __dmul_rn/__dadd_rn (never contracted) - replay mode, bit-exact vs numpy for GBM.
 #pragma once
 #ifndef MLMCB_PACKED_F32
-#define MLMCB_PACKED_F32 1
+#define MLMCB_PACKED_F32 0          // FFMA2 costs two dispatch cycles on B200: no gain (profiles/r01_pipe_mix.txt)
+#endif
+#ifndef MLMCB_PHILOX_ROUNDS
+#define MLMCB_PHILOX_ROUNDS 10      // experiments only; the shipped library is Philox4x32-10
 #endif
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -54,6 +57,7 @@ struct LevelConsts {
     double avg_wf, avg_wc;          // dt/T and M*dt/T
     // Merton
     double lam, inv_lam, jm, js;
+    float poly_q4, poly_c4;         // leading sin/cos coefficients as uniform operands (no per-block MOV)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -75,7 +79,7 @@ __host__ __device__ __forceinline__ U4 philox_round(U4 c, uint32_t k0, uint32_t 
 __device__ __forceinline__ U4 philox10(const LevelConsts& C, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
     U4 c = {c0, c1, c2, c3};
 #pragma unroll
-    for (int r = 0; r < 10; ++r) c = philox_round(c, C.k0[r], C.k1[r]);
+    for (int r = 0; r < MLMCB_PHILOX_ROUNDS; ++r) c = philox_round(c, C.k0[r], C.k1[r]);
     return c;
 }
 
@@ -122,13 +126,15 @@ __device__ __forceinline__ float lg2_approx(float x) {   // MUFU.LG2, no denorma
 #define MLMCB_C4 0.2196968048810959f
 #define MLMCB_NEG2LN2 -1.3862943611198906f
 
-__device__ __forceinline__ void bm_pair_f32(uint32_t ru, uint32_t ra, float& z0, float& z1) {
-    float u = fmaf(__uint2float_rn(ru), 0x1p-32f, 0x1p-33f);
-    float rad = sqrt_approx(lg2_approx(u) * MLMCB_NEG2LN2);            // sqrt(-2 ln u)
-    rad = __uint_as_float(__float_as_uint(rad) ^ (ru << 31));       // random sign: whole circle
+__device__ __forceinline__ void bm_pair_f32(const float q4, const float c4, uint32_t ru, uint32_t ra, float& z0, float& z1) {
+    // ru as a signed word: |x| gives the uniform (31 bits + the 0.5 offset), sign(x) the half-plane
+    const float x = __int2float_rn((int)ru);
+    const float u = fmaf(fabsf(x), 0x1p-31f, 0x1p-32f);              // (0,1]
+    float rad = sqrt_approx(lg2_approx(u) * MLMCB_NEG2LN2);         // sqrt(-2 ln u)
+    rad = __uint_as_float((__float_as_uint(rad) & 0x7fffffffu) | (__float_as_uint(x) & 0x80000000u));   // one LOP3
     float h = __int2float_rn((int)ra) * 0x1p-32f;                   // angle / pi in [-1/2,1/2)
     float T = h * h;
-    float q = fmaf(T, MLMCB_Q4, MLMCB_Q3), c = fmaf(T, MLMCB_C4, MLMCB_C3);
+    float q = fmaf(T, q4, MLMCB_Q3), c = fmaf(T, c4, MLMCB_C3);
     q = fmaf(q, T, MLMCB_Q2); c = fmaf(c, T, MLMCB_C2);
     q = fmaf(q, T, MLMCB_Q1); c = fmaf(c, T, MLMCB_C1);
     q = fmaf(q, T, MLMCB_Q0); c = fmaf(c, T, MLMCB_C0);
@@ -140,8 +146,8 @@ __device__ __forceinline__ void bm_pair_f32(uint32_t ru, uint32_t ra, float& z0,
 // independent pairs of one Philox block ride in the .x/.y halves, halving the fp32 issue slots.
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 
-__device__ __forceinline__ void bm_quad_f32(U4 w, float z[4]) {
-#if MLMCB_PACKED_F32
+__device__ __forceinline__ void bm_quad_f32(const LevelConsts& C, U4 w, float z[4]) {
+#if MLMCB_PACKED_F32 == 1
     float2 u = __ffma2_rn(make_float2(__uint2float_rn(w.x), __uint2float_rn(w.z)), f2(0x1p-32f), f2(0x1p-33f));
     float2 s = __fmul2_rn(make_float2(lg2_approx(u.x), lg2_approx(u.y)), f2(MLMCB_NEG2LN2));
     float2 rad = make_float2(sqrt_approx(s.x), sqrt_approx(s.y));
@@ -155,9 +161,39 @@ __device__ __forceinline__ void bm_quad_f32(U4 w, float z[4]) {
     q = __ffma2_rn(q, T, f2(MLMCB_Q0)); c = __ffma2_rn(c, T, f2(MLMCB_C0));
     float2 zc = __fmul2_rn(rad, c), zs = __fmul2_rn(__fmul2_rn(rad, h), q);
     z[0] = zc.x; z[1] = zs.x; z[2] = zc.y; z[3] = zs.y;
+#elif MLMCB_PACKED_F32 == 2
+    // only the two Horner chains packed (8 FFMA2): balances fmaheavy against the issue slots
+    float ua = fmaf(__uint2float_rn(w.x), 0x1p-32f, 0x1p-33f), ub = fmaf(__uint2float_rn(w.z), 0x1p-32f, 0x1p-33f);
+    float ra = sqrt_approx(lg2_approx(ua) * MLMCB_NEG2LN2), rb = sqrt_approx(lg2_approx(ub) * MLMCB_NEG2LN2);
+    ra = __uint_as_float(__float_as_uint(ra) ^ (w.x << 31));
+    rb = __uint_as_float(__float_as_uint(rb) ^ (w.z << 31));
+    float ha = __int2float_rn((int)w.y) * 0x1p-32f, hb = __int2float_rn((int)w.w) * 0x1p-32f;
+    float2 T = make_float2(ha * ha, hb * hb);
+    float2 q = __ffma2_rn(T, f2(MLMCB_Q4), f2(MLMCB_Q3)), c = __ffma2_rn(T, f2(MLMCB_C4), f2(MLMCB_C3));
+    q = __ffma2_rn(q, T, f2(MLMCB_Q2)); c = __ffma2_rn(c, T, f2(MLMCB_C2));
+    q = __ffma2_rn(q, T, f2(MLMCB_Q1)); c = __ffma2_rn(c, T, f2(MLMCB_C1));
+    q = __ffma2_rn(q, T, f2(MLMCB_Q0)); c = __ffma2_rn(c, T, f2(MLMCB_C0));
+    z[0] = ra * c.x; z[1] = (ra * ha) * q.x; z[2] = rb * c.y; z[3] = (rb * hb) * q.y;
+#elif MLMCB_PACKED_F32 == 3
+    // one Horner chain packed per pair: (q,c) of the same pair ride together (4 FFMA2 per pair)
+    float ua = fmaf(__uint2float_rn(w.x), 0x1p-32f, 0x1p-33f), ub = fmaf(__uint2float_rn(w.z), 0x1p-32f, 0x1p-33f);
+    float ra = sqrt_approx(lg2_approx(ua) * MLMCB_NEG2LN2), rb = sqrt_approx(lg2_approx(ub) * MLMCB_NEG2LN2);
+    ra = __uint_as_float(__float_as_uint(ra) ^ (w.x << 31));
+    rb = __uint_as_float(__float_as_uint(rb) ^ (w.z << 31));
+    float ha = __int2float_rn((int)w.y) * 0x1p-32f, hb = __int2float_rn((int)w.w) * 0x1p-32f;
+    float Ta = ha * ha, Tb = hb * hb;
+    float2 pa = __ffma2_rn(f2(Ta), make_float2(MLMCB_Q4, MLMCB_C4), make_float2(MLMCB_Q3, MLMCB_C3));
+    pa = __ffma2_rn(pa, f2(Ta), make_float2(MLMCB_Q2, MLMCB_C2));
+    pa = __ffma2_rn(pa, f2(Ta), make_float2(MLMCB_Q1, MLMCB_C1));
+    pa = __ffma2_rn(pa, f2(Ta), make_float2(MLMCB_Q0, MLMCB_C0));
+    float qb = fmaf(Tb, MLMCB_Q4, MLMCB_Q3), cb = fmaf(Tb, MLMCB_C4, MLMCB_C3);
+    qb = fmaf(qb, Tb, MLMCB_Q2); cb = fmaf(cb, Tb, MLMCB_C2);
+    qb = fmaf(qb, Tb, MLMCB_Q1); cb = fmaf(cb, Tb, MLMCB_C1);
+    qb = fmaf(qb, Tb, MLMCB_Q0); cb = fmaf(cb, Tb, MLMCB_C0);
+    z[0] = ra * pa.y; z[1] = (ra * ha) * pa.x; z[2] = rb * cb; z[3] = (rb * hb) * qb;
 #else
-    bm_pair_f32(w.x, w.y, z[0], z[1]);
-    bm_pair_f32(w.z, w.w, z[2], z[3]);
+    bm_pair_f32(C.poly_q4, C.poly_c4, w.x, w.y, z[0], z[1]);
+    bm_pair_f32(C.poly_q4, C.poly_c4, w.z, w.w, z[2], z[3]);
 #endif
 }
 
@@ -189,7 +225,7 @@ struct PhiloxSource {
     __device__ __forceinline__ void load4(uint32_t b, R z[4]) const {
         if (SAMP == SAMP_F32BM) {
             float f[4];
-            bm_quad_f32(philox_at(C, pid, STREAM_GRID, b), f);
+            bm_quad_f32(C, philox_at(C, pid, STREAM_GRID, b), f);
             z[0] = (R)f[0]; z[1] = (R)f[1]; z[2] = (R)f[2]; z[3] = (R)f[3];
         } else {
             U4 r = philox_at(C, pid, STREAM_GRID, 2 * b), s = philox_at(C, pid, STREAM_GRID, 2 * b + 1);
@@ -527,7 +563,7 @@ __device__ __forceinline__ void jump_draws(const LevelConsts& C, ull pid, uint32
         U4 r = philox_at(C, pid, STREAM_JUMP, jk);
         gap = -log(u53(r.x, r.y)) * C.inv_lam;
         float a, b;
-        bm_pair_f32(r.z, r.w, a, b);
+        bm_pair_f32(C.poly_q4, C.poly_c4, r.z, r.w, a, b);
         zq = (R)a; zw = (R)b;
     } else {
         U4 r = philox_at(C, pid, STREAM_JUMP, 2 * jk), s = philox_at(C, pid, STREAM_JUMP, 2 * jk + 1);

