@@ -247,8 +247,27 @@ def run_b200(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    # the real bound of this kernel: warp-instruction dispatch
+    issue = None
+    try:
+        mix = json.load(open(os.path.join(ROOT, "multilevel_mc_sdes_b200", "csrc", "sass_mix.json")))[sampler]
+        f_sm = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        slots_per_s = 148 * 4 * f_sm                              # dispatch cycles/s over all SMSPs
+        warp_steps_per_s = steps_per_s_gpu / 32.0
+        cyc = slots_per_s / warp_steps_per_s
+        issue = {
+            "warp_inst_per_fine_step_static": mix["inst_per_4_steps"] / 4.0,
+            "dispatch_cycles_per_fine_step_model": mix["dispatch_cycles_per_4_steps"] / 4.0,
+            "measured_smsp_cycles_per_warp_step": cyc,
+            "issue_frac": mix["inst_per_4_steps"] / 4.0 / cyc,
+            "dispatch_frac": mix["dispatch_cycles_per_4_steps"] / 4.0 / cyc,
+            "note": "ALU-class and IMAD instructions occupy the dispatch port 2 cycles on B200 "
+                    "(profiles/r01_pipe_mix.txt); dispatch_frac is the fraction of that bound reached",
+        }
+    except Exception:
+        pass
     roofline = {
-        "bound": "fp64_pipe", "achieved": achieved / 1e9, "peak": dfma_lane_per_s / 1e9,
+        "bound": "fp64_pipe", "achieved": achieved / 1e9, "peak": dfma_lane_per_s / 1e9, "issue": issue,
         "unit": "G FP64 issue-slots/s (algorithmic 44.5 per coupled fine step, SURVEY 8(d))",
         "frac": achieved / dfma_lane_per_s, "traffic": None,
         "peak_source": "DFMA chain micro-benchmark (mlmcb_pipe_probe) measured in this run; "

@@ -42,7 +42,25 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libmlmcb.so")
     if verbose:
         sys.stderr.write(r.stderr)
+    write_sass_mix()
     return LIB
+
+
+def write_sass_mix():
+    """Static instruction mix of the benchmarked kernel's inner loop -> csrc/sass_mix.json
+    (bench.py reports it next to the measured cycles per step)."""
+    import json
+    tools = os.path.join(os.path.dirname(HERE), "tools")
+    sys.path.insert(0, tools)
+    try:
+        import sass_mix
+        out = {k: sass_mix.hot_loop_mix(LIB, pat) for k, pat in
+               (("f32bm", "level_kernel<double, 0, 0, 4, 0>"), ("f64bm", "level_kernel<double, 0, 0, 4, 1>"))}
+        json.dump(out, open(os.path.join(CSRC, "sass_mix.json"), "w"), indent=1)
+    except Exception as e:  # cuobjdump missing: not fatal
+        sys.stderr.write(f"sass_mix skipped: {e}\n")
+    finally:
+        sys.path.remove(tools)
 
 
 if __name__ == "__main__":

@@ -41,7 +41,48 @@ def kernels(lib):
     return res
 
 
+def hot_loop_mix(lib, pat):
+    """-> dict for the hottest loop of the first kernel whose demangled name contains `pat`:
+    instruction count per 4 fine steps, split by dispatch class, and the 2-cycle-weighted figure
+    (ALU-class and IMAD occupy the dispatch port for 2 cycles on B200, everything else 1)."""
+    ks = kernels(lib)
+    names = subprocess.run(["c++filt"] + list(ks), capture_output=True, text=True).stdout.splitlines()
+    for mangled, name in zip(ks, names):
+        if pat not in name:
+            continue
+        body = ks[mangled]
+        best = None
+        for addr, ins in body:
+            m = re.search(r"BRA(?:\.U)?\s+(?:\S+,\s+)?(0x[0-9a-f]+)", ins)
+            if not m or int(m.group(1), 16) > addr:
+                continue
+            lo = int(m.group(1), 16)
+            ops = [re.sub(r"^@!?U?P\d+\s+", "", i).split()[0] for a, i in body if lo <= a <= addr]
+            if not any(o.startswith("DFMA") or o.startswith("FFMA") for o in ops):
+                continue
+            if best is None or len(ops) < len(best):
+                best = ops
+        if best is None:
+            return None
+        cls = collections.Counter()
+        for o in best:
+            for pipe, rx in PIPES:
+                if re.match(rx, o):
+                    cls[pipe] += 1
+                    break
+            else:
+                cls["other"] += 1
+        two = cls["alu"] + sum(1 for o in best if o.startswith("IMAD"))
+        return {"kernel": name.split("(")[0], "inst_per_4_steps": len(best), "classes": dict(cls),
+                "dispatch_cycles_per_4_steps": len(best) + two}
+    return None
+
+
 def main():
+    if "--json" in sys.argv:
+        import json
+        print(json.dumps(hot_loop_mix(sys.argv[1], sys.argv[2])))
+        return
     lib, pat = sys.argv[1], sys.argv[2]
     dump = "--dump" in sys.argv
     ks = kernels(lib)
