@@ -53,8 +53,11 @@ def write_sass_mix():
     tools = os.path.join(os.path.dirname(HERE), "tools")
     sys.path.insert(0, tools)
     try:
+        import re
         import sass_mix
-        out = {k: sass_mix.hot_loop_mix(LIB, pat) for k, pat in
+        hdr = open(os.path.join(CSRC, "mlmcb_kernels.cuh")).read()
+        unroll = int(re.search(r"#define MLMCB_UNROLL (\d+)", hdr).group(1))
+        out = {k: sass_mix.hot_loop_mix(LIB, pat, 4 * unroll) for k, pat in
                (("f32bm", "level_kernel<double, 0, 0, 4, 0>"), ("f64bm", "level_kernel<double, 0, 0, 4, 1>"))}
         json.dump(out, open(os.path.join(CSRC, "sass_mix.json"), "w"), indent=1)
     except Exception as e:  # cuobjdump missing: not fatal

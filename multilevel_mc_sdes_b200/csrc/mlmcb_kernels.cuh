@@ -23,6 +23,12 @@
 #ifndef MLMCB_PACKED_F32
 #define MLMCB_PACKED_F32 0          // FFMA2 costs two dispatch cycles on B200: no gain (profiles/r01_pipe_mix.txt)
 #endif
+#ifndef MLMCB_UNROLL
+#define MLMCB_UNROLL 2              // two Philox blocks in flight per thread (measured best with 8 blocks/SM)
+#endif
+#ifndef MLMCB_MINBLOCKS
+#define MLMCB_MINBLOCKS 8           // GBM/f32bm kernels: cap at 64 registers -> 8 blocks of 128 threads per SM
+#endif
 #ifndef MLMCB_PHILOX_ROUNDS
 #define MLMCB_PHILOX_ROUNDS 10      // experiments only; the shipped library is Philox4x32-10
 #endif
@@ -39,6 +45,7 @@ enum { SAMP_F32BM = 0, SAMP_F64BM = 1 };
 enum { PAY_EURO = 0, PAY_ASIAN = 1, PAY_LOOKBACK = 2, PAY_DIGITAL = 3 };
 
 constexpr int kThreads = 128;
+constexpr int kUnroll = MLMCB_UNROLL;
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 
@@ -83,16 +90,19 @@ __device__ __forceinline__ U4 philox10(const LevelConsts& C, uint32_t c0, uint32
     return c;
 }
 
-// Counter layout (128 bit):  c0 = draw-block index (32 bit: 4 steps per block, M**l <= 2^33),
-//                            c1 = stream kind (4 bit, top of the word)
+// Counter layout (128 bit):  c0 = stream kind (grid steps / jump stream)
+//                            c1 = draw-block index (32 bit: 4 steps per block, M**l <= 2^33)
 //                            c2,c3 = global path id (48 bit) | level (8 bit) | 0
 // key = 64-bit seed.  Distinct (seed, level, path id, kind, block) -> distinct counter, so
 // repeated looper calls (advancing path_offset), levels, ranks and the Merton jump stream never
-// reuse a draw.
+// reuse a draw.  The block index sits in c1 - a word the first round only XORs - so that, with
+// everything else fixed along a path, both multiplies of round 1 and one multiply each of rounds
+// 2 and 3 are loop-invariant and hoisted by the compiler: 16 instead of 20 IMAD.WIDE per block
+// for the same Philox4x32-10 output.
 enum { STREAM_GRID = 0, STREAM_JUMP = 1 };
 
 __device__ __forceinline__ U4 philox_at(const LevelConsts& C, ull pid, uint32_t kind, uint32_t blk) {
-    return philox10(C, blk, kind << 28, (uint32_t)pid, ((uint32_t)(pid >> 32) & 0xFFFFu) | C.ctr3_tag);
+    return philox10(C, kind, blk, (uint32_t)pid, ((uint32_t)(pid >> 32) & 0xFFFFu) | C.ctr3_tag);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -373,6 +383,7 @@ __device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source
     }
 
     const uint32_t nblk = (uint32_t)(C.nsteps >> 2);
+#pragma unroll kUnroll
     for (uint32_t b = 0; b < nblk; ++b) {
         R z[4];
         src.load4(b, z);
@@ -671,7 +682,7 @@ __device__ __forceinline__ void emit(const LevelConsts& C, ull i, double vf, dou
 }
 
 template <typename R, int MODEL, int FN, int MT, int SAMP>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (MODEL == 0 && SAMP == SAMP_F32BM) ? MLMCB_MINBLOCKS : 1)
 level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
              double* out7, double* Pf_out, double* Pc_out) {
     Sums7 acc;

@@ -41,7 +41,7 @@ def kernels(lib):
     return res
 
 
-def hot_loop_mix(lib, pat):
+def hot_loop_mix(lib, pat, steps_per_iter=4):
     """-> dict for the hottest loop of the first kernel whose demangled name contains `pat`:
     instruction count per 4 fine steps, split by dispatch class, and the 2-cycle-weighted figure
     (ALU-class and IMAD occupy the dispatch port for 2 cycles on B200, everything else 1)."""
@@ -73,8 +73,10 @@ def hot_loop_mix(lib, pat):
             else:
                 cls["other"] += 1
         two = cls["alu"] + sum(1 for o in best if o.startswith("IMAD"))
-        return {"kernel": name.split("(")[0], "inst_per_4_steps": len(best), "classes": dict(cls),
-                "dispatch_cycles_per_4_steps": len(best) + two}
+        k = 4.0 / steps_per_iter
+        return {"kernel": name.split("(")[0], "steps_per_loop_iteration": steps_per_iter,
+                "inst_per_4_steps": len(best) * k, "classes_per_iteration": dict(cls),
+                "dispatch_cycles_per_4_steps": (len(best) + two) * k}
     return None
 
 
