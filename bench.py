@@ -81,12 +81,12 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    per_core = 2500                      # one step = cores x 2500 paths  (~0.4 s per step per core)
+    per_core = 10000                     # one step = one reference-sized chunk (Npl=1e4, :919) per core, ~1 s
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         for w in range(args.warmup):
-            pool.map(_ref_worker, [(w * cores + i, 256) for i in range(cores)])
+            pool.map(_ref_worker, [(w * cores + i, 1000) for i in range(cores)])
         t0 = time.perf_counter()
         for k in range(args.steps):
             pool.map(_ref_worker, [(7919 * (k + 1) + i, per_core) for i in range(cores)])
