@@ -43,7 +43,11 @@ enum {
     MLMCB_SAMPLER_F32BM = 0,   /* default: 32-bit uniforms, fp32 Box-Muller, promoted to fp64      */
     MLMCB_SAMPLER_F64BM = 1,   /* canonical: 53-bit uniforms, fp64 Box-Muller (log/sqrt/sincospi)  */
     MLMCB_SAMPLER_MASK  = 0xF,
-    MLMCB_FP32_PATHS    = 0x10 /* opt-in: path arithmetic in fp32 (sums stay fp64)                 */
+    MLMCB_FP32_PATHS    = 0x10,/* opt-in: path arithmetic in fp32 (sums stay fp64)                 */
+    MLMCB_ANTITHETIC    = 0x20 /* antithetic estimator (looper(anti=True) :941-942): GBM Euro/Asian
+                                  only (anti_EA_payoff :292-317, diffusion_anti_path(_avg) :162-290),
+                                  even M; other products -> MLMCB_ENOTIMPL, odd M -> MLMCB_EINVAL.
+                                  May also be ORed into `arith` of mlmcb_replay_gbm.                */
 };
 /* arithmetic policy for replay */
 enum {

@@ -190,8 +190,33 @@ int ws_free(Workspace* w, cudaStream_t st) {
 int check_flags(int flags) {
     const int samp = flags & MLMCB_SAMPLER_MASK;
     if (samp != MLMCB_SAMPLER_F32BM && samp != MLMCB_SAMPLER_F64BM) return fail(MLMCB_EINVAL, "unknown sampler %d", samp);
-    if (flags & ~(MLMCB_SAMPLER_MASK | MLMCB_FP32_PATHS)) return fail(MLMCB_EINVAL, "unknown flag bits 0x%x", flags);
+    if (flags & ~(MLMCB_SAMPLER_MASK | MLMCB_FP32_PATHS | MLMCB_ANTITHETIC))
+        return fail(MLMCB_EINVAL, "unknown flag bits 0x%x", flags);
     return 0;
+}
+
+// looper(anti=True): only Euro_GBM / Asian_GBM define anti_payoff (:1379/:1406); M must be even (:178)
+int check_anti(int model, int payoff, int M) {
+    if (model != MLMCB_GBM || (payoff != MLMCB_EURO && payoff != MLMCB_ASIAN))
+        return fail(MLMCB_ENOTIMPL, "Option instance has no implemented anti_payoff method");
+    if (M % 2 != 0)
+        return fail(MLMCB_EINVAL, "Cannot calculate antithetic estimator for odd coarseness factor M - please use even M");
+    return 0;
+}
+
+template <typename R, int SAMP>
+LevelKernel pick_anti_fn(int fn, int mt) {
+    if (fn == FN_AVG)
+        return mt == 2 ? level_anti_kernel<R, FN_AVG, 2, SAMP> : mt == 4 ? level_anti_kernel<R, FN_AVG, 4, SAMP>
+                                                                         : level_anti_kernel<R, FN_AVG, 0, SAMP>;
+    return mt == 2 ? level_anti_kernel<R, FN_FINAL, 2, SAMP> : mt == 4 ? level_anti_kernel<R, FN_FINAL, 4, SAMP>
+                                                                       : level_anti_kernel<R, FN_FINAL, 0, SAMP>;
+}
+LevelKernel pick_anti_kernel(int payoff, int M, int flags) {
+    const int fn = fn_of(payoff), mt = mt_of(M), samp = flags & MLMCB_SAMPLER_MASK;
+    if (flags & MLMCB_FP32_PATHS)
+        return samp == MLMCB_SAMPLER_F64BM ? pick_anti_fn<float, SAMP_F64BM>(fn, mt) : pick_anti_fn<float, SAMP_F32BM>(fn, mt);
+    return samp == MLMCB_SAMPLER_F64BM ? pick_anti_fn<double, SAMP_F64BM>(fn, mt) : pick_anti_fn<double, SAMP_F32BM>(fn, mt);
 }
 
 int level_sums_impl(const mlmcb_params* p, int model, int payoff, int l, int M, ull n_paths, ull seed,
@@ -201,8 +226,11 @@ int level_sums_impl(const mlmcb_params* p, int model, int payoff, int l, int M, 
     if (int rc = check_flags(flags)) return rc;
     LevelConsts C;
     if (int rc = make_consts(p, model, payoff, l, M, n_paths, seed, path_offset, &C)) return rc;
+    if (flags & MLMCB_ANTITHETIC) {
+        if (int rc = check_anti(model, payoff, M)) return rc;
+    }
     if (n_paths == 0) { CU(cudaMemsetAsync(d_out7, 0, 7 * sizeof(double), st)); return 0; }
-    LevelKernel k = pick_kernel(model, payoff, M, flags);
+    LevelKernel k = (flags & MLMCB_ANTITHETIC) ? pick_anti_kernel(payoff, M, flags) : pick_kernel(model, payoff, M, flags);
     int grid = 1;
     if (int rc = geometry(k, device, n_paths, &grid, nullptr)) return rc;
     Workspace w;
@@ -325,7 +353,12 @@ int mlmcb_level_sweep_host(const mlmcb_params* p, int model, int payoff, int M, 
 int mlmcb_replay_gbm(const mlmcb_params* p, int payoff, int l, int M, uint64_t n_paths, const double* d_Z,
                      int arith, int device, void* cuda_stream, double* d_Pf, double* d_Pc, double* d_out7) {
     if (!d_Z || !d_Pf || !d_Pc) return fail(MLMCB_EINVAL, "NULL device pointer");
+    const bool anti = (arith & MLMCB_ANTITHETIC) != 0;
+    arith &= ~MLMCB_ANTITHETIC;
     if (arith != MLMCB_ARITH_FAST && arith != MLMCB_ARITH_EXACT) return fail(MLMCB_EINVAL, "unknown arith %d", arith);
+    if (anti) {
+        if (int rc = check_anti(MLMCB_GBM, payoff, M)) return rc;
+    }
     DeviceGuard g(device);
     if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -337,7 +370,10 @@ int mlmcb_replay_gbm(const mlmcb_params* p, int payoff, int l, int M, uint64_t n
         {replay_gbm_kernel<FN_FINAL, AR_FAST>, replay_gbm_kernel<FN_FINAL, AR_EXACT>},
         {replay_gbm_kernel<FN_AVG, AR_FAST>, replay_gbm_kernel<FN_AVG, AR_EXACT>},
         {replay_gbm_kernel<FN_MIN, AR_FAST>, replay_gbm_kernel<FN_MIN, AR_EXACT>}};
-    K k = table[fn_of(payoff)][arith];
+    static const K anti_table[2][2] = {
+        {replay_gbm_anti_kernel<FN_FINAL, AR_FAST>, replay_gbm_anti_kernel<FN_FINAL, AR_EXACT>},
+        {replay_gbm_anti_kernel<FN_AVG, AR_FAST>, replay_gbm_anti_kernel<FN_AVG, AR_EXACT>}};
+    K k = anti ? anti_table[fn_of(payoff)][arith] : table[fn_of(payoff)][arith];
     int grid = (int)((n_paths + kThreads - 1) / kThreads);
     if (grid > 65535) grid = 65535;
     Workspace w;
@@ -406,7 +442,11 @@ int mlmcb_launch_geometry(int model, int payoff, int M, int flags, int device, i
     DeviceGuard g(device);
     if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
     int grid = 0, mb = 0;
-    if (int rc = geometry(pick_kernel(model, payoff, M, flags), device, ~0ull >> 16, &grid, &mb)) return rc;
+    if (flags & MLMCB_ANTITHETIC) {
+        if (int rc = check_anti(model, payoff, M)) return rc;
+    }
+    LevelKernel k = (flags & MLMCB_ANTITHETIC) ? pick_anti_kernel(payoff, M, flags) : pick_kernel(model, payoff, M, flags);
+    if (int rc = geometry(k, device, ~0ull >> 16, &grid, &mb)) return rc;
     if (threads_per_block) *threads_per_block = kThreads;
     if (max_blocks) *max_blocks = mb;
     return 0;

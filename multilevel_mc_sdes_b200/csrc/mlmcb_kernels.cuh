@@ -463,6 +463,134 @@ __device__ __forceinline__ void gbm_path_exact(const LevelConsts& C, const doubl
 }
 
 // ------------------------------------------------------------------------------------------
+// Antithetic GBM triple (fine, antithetic-fine, coarse): diffusion_anti_path :162-217 and
+// diffusion_anti_path_avg :219-290.  The antithetic path swaps the two Brownian increments of
+// every pair of fine steps; M must be even (:178).  FN is FN_FINAL or FN_AVG.
+// ------------------------------------------------------------------------------------------
+template <typename R, int FN, int MT, typename Source>
+__device__ __forceinline__ void gbm_anti_path_fast(const LevelConsts& C, const Source& src,
+                                                   double& vf, double& va, double& vc) {
+    const R af = (R)C.a_f, bf = (R)C.b_f, ac = (R)C.a_c;
+    R Xf = (R)C.X0, Xa = (R)C.X0, Xc = (R)C.X0, sz = (R)0;
+    R Ff = (R)0, Fa = (R)0, Fc = (R)0;
+    int cm = 0;
+    const int M = C.M;
+    if (C.is_l0) {                                                       // :213-215 / :282-285
+        R z[4];
+        src.load4(0, z);
+        R t_ = fma_<R>(bf, z[0], af);
+        Xf = fma_<R>(Xf, t_, Xf);
+        vf = va = FN == FN_AVG ? C.avg_wf * (0.5 * C.X0 + 0.5 * (double)Xf) : (double)Xf;
+        vc = C.X0;
+        return;
+    }
+#define MLMCB_PAIR(zo, ze)                                               \
+    {                                                                    \
+        R to_ = fma_<R>(bf, (zo), af), te_ = fma_<R>(bf, (ze), af);      \
+        Xf = fma_<R>(Xf, to_, Xf); Xa = fma_<R>(Xa, te_, Xa);            \
+        if (FN == FN_AVG) { Ff += Xf; Fa += Xa; }                        \
+        Xf = fma_<R>(Xf, te_, Xf); Xa = fma_<R>(Xa, to_, Xa);            \
+        if (FN == FN_AVG) { Ff += Xf; Fa += Xa; }                        \
+        sz += (zo) + (ze);                                               \
+    }
+#define MLMCB_COARSE()                                                   \
+    {                                                                    \
+        R t_ = fma_<R>(bf, sz, ac);                                      \
+        Xc = fma_<R>(Xc, t_, Xc);                                        \
+        sz = (R)0;                                                       \
+        if (FN == FN_AVG) Fc += Xc;                                      \
+    }
+    const uint32_t nblk = (uint32_t)(C.nsteps >> 2);
+    for (uint32_t b = 0; b < nblk; ++b) {
+        R z[4];
+        src.load4(b, z);
+        MLMCB_PAIR(z[0], z[1]);
+        if (MT == 2) MLMCB_COARSE()
+        else if (MT == 0) { cm += 2; if (cm == M) { cm = 0; MLMCB_COARSE(); } }
+        MLMCB_PAIR(z[2], z[3]);
+        if (MT == 2 || MT == 4) MLMCB_COARSE()
+        else { cm += 2; if (cm == M) { cm = 0; MLMCB_COARSE(); } }
+    }
+    if (C.nsteps & 2) {                                                  // M=2,l=1 or M=6: one trailing pair
+        R z[4];
+        src.load4(nblk, z);
+        MLMCB_PAIR(z[0], z[1]);
+        cm += 2;
+        if (cm == M) { cm = 0; MLMCB_COARSE(); }
+    }
+#undef MLMCB_PAIR
+#undef MLMCB_COARSE
+    if (FN == FN_AVG) {
+        const double h0 = 0.5 * C.X0;
+        vf = C.avg_wf * ((double)Ff + fma(-0.5, (double)Xf, h0));
+        va = C.avg_wf * ((double)Fa + fma(-0.5, (double)Xa, h0));
+        vc = C.avg_wc * ((double)Fc + fma(-0.5, (double)Xc, h0));
+    } else {
+        vf = (double)Xf; va = (double)Xa; vc = (double)Xc;
+    }
+}
+
+// reference expression order (replay, bit-exact vs numpy)
+template <int FN>
+__device__ __forceinline__ void gbm_anti_path_exact(const LevelConsts& C, const double* Z, ull n, ull i,
+                                                    double& vf, double& va, double& vc) {
+    const double dt = C.dt, Mdt = C.Mdt, mu = C.mu, sig = C.sig, Md = C.Md;
+#define MLMCB_INC(X, h, dW) __dadd_rn(__dmul_rn(__dmul_rn(mu, (X)), (h)), __dmul_rn(__dmul_rn(sig, (X)), (dW)))
+    double Xf = C.X0, Xa = C.X0, Xc = C.X0, dWc = 0.0;
+    double Af = __dmul_rn(__dmul_rn(0.5, dt), Xf), Aa = __dmul_rn(__dmul_rn(0.5, dt), Xa);      // :247-248
+    double Ac = __dmul_rn(__dmul_rn(__dmul_rn(0.5, Md), dt), Xc);                               // :249
+    if (C.is_l0) {
+        Xf = __dadd_rn(Xf, MLMCB_INC(Xf, dt, __dmul_rn(Z[i], C.sqrt_dt)));                       // :214
+        if (FN == FN_AVG) { Af = __dadd_rn(Af, __dmul_rn(__dmul_rn(0.5, dt), Xf)); vf = __ddiv_rn(Af, C.T); }   // :284
+        else vf = Xf;
+        va = vf; vc = Xc;
+        return;
+    }
+    int cm = 0;
+    for (ull k = 0; k + 1 < C.nsteps; k += 2) {
+        const double dWo = __dmul_rn(Z[k * n + i], C.sqrt_dt), dWe = __dmul_rn(Z[(k + 1) * n + i], C.sqrt_dt);   // :195-196
+        Xf = __dadd_rn(Xf, MLMCB_INC(Xf, dt, dWo));                      // :200
+        Xa = __dadd_rn(Xa, MLMCB_INC(Xa, dt, dWe));                      // :201
+        if (FN == FN_AVG) { Af = __dadd_rn(Af, __dmul_rn(dt, Xf)); Aa = __dadd_rn(Aa, __dmul_rn(dt, Xa)); }    // :263-264
+        Xf = __dadd_rn(Xf, MLMCB_INC(Xf, dt, dWe));                      // :205
+        Xa = __dadd_rn(Xa, MLMCB_INC(Xa, dt, dWo));                      // :206
+        if (FN == FN_AVG) { Af = __dadd_rn(Af, __dmul_rn(dt, Xf)); Aa = __dadd_rn(Aa, __dmul_rn(dt, Xa)); }    // :271-272
+        dWc = __dadd_rn(dWc, __dadd_rn(dWo, dWe));                       // :208
+        cm += 2;
+        if (cm == C.M) {
+            cm = 0;
+            Xc = __dadd_rn(Xc, MLMCB_INC(Xc, Mdt, dWc));                 // :210
+            if (FN == FN_AVG) Ac = __dadd_rn(Ac, __dmul_rn(__dmul_rn(dt, Md), Xc));      // :278
+            dWc = 0.0;
+        }
+    }
+#undef MLMCB_INC
+    if (FN == FN_AVG) {
+        Af = __dsub_rn(Af, __dmul_rn(__dmul_rn(0.5, Xf), dt));           // :287
+        Aa = __dsub_rn(Aa, __dmul_rn(__dmul_rn(0.5, Xa), dt));           // :288
+        Ac = __dsub_rn(Ac, __dmul_rn(__dmul_rn(0.5, Xc), Mdt));          // :289
+        vf = __ddiv_rn(Af, C.T); va = __ddiv_rn(Aa, C.T); vc = __ddiv_rn(Ac, C.T);
+    } else {
+        vf = Xf; va = Xa; vc = Xc;
+    }
+}
+
+// anti_EA_payoff :292-317
+__device__ __forceinline__ void emit_anti(const LevelConsts& C, ull i, double vf, double va, double vc,
+                                          Sums7& acc, double* Pf_out, double* Pc_out) {
+    double Pf = payoff_fine(C, vf, 0.0), Pc;
+    if (C.is_l0) {
+        Pc = vc;                                                         // :311
+    } else {
+        Pf = __dmul_rn(0.5, __dadd_rn(Pf, payoff_fine(C, va, 0.0)));     // :317
+        Pc = payoff_coarse(C, vc, 0.0);
+    }
+    acc.add(Pf, Pc, C.is_l0);
+    if (Pf_out) Pf_out[i] = Pf;
+    if (Pc_out) Pc_out[i] = Pc;
+}
+
+// ------------------------------------------------------------------------------------------
 // Merton jump-adapted coupled path state (JD_path* :428-651).  Times are always double.
 // G = trapezoid integral (FN_AVG) or running minimum (FN_MIN).
 // ------------------------------------------------------------------------------------------
@@ -718,6 +846,42 @@ replay_gbm_kernel(const __grid_constant__ LevelConsts C, const double* Z, double
             gbm_path_fast<double, FN, 0>(C, src, vf, vc, gf, gc);
         }
         emit(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
+    }
+    grid_finish(acc, partials, ticket, out7);
+}
+
+template <typename R, int FN, int MT, int SAMP>
+__global__ void __launch_bounds__(kThreads)
+level_anti_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
+                  double* out7, double* Pf_out, double* Pc_out) {
+    Sums7 acc;
+    acc.clear();
+    const ull stride = (ull)gridDim.x * blockDim.x;
+    for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
+        PhiloxSource<R, SAMP> src{C, C.path_offset + i};
+        double vf, va, vc;
+        gbm_anti_path_fast<R, FN, MT>(C, src, vf, va, vc);
+        emit_anti(C, i, vf, va, vc, acc, Pf_out, Pc_out);
+    }
+    grid_finish(acc, partials, ticket, out7);
+}
+
+template <int FN, int AR>
+__global__ void __launch_bounds__(kThreads)
+replay_gbm_anti_kernel(const __grid_constant__ LevelConsts C, const double* Z, double* partials, unsigned* ticket,
+                       double* out7, double* Pf_out, double* Pc_out) {
+    Sums7 acc;
+    acc.clear();
+    const ull stride = (ull)gridDim.x * blockDim.x;
+    for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
+        double vf, va, vc;
+        if (AR == AR_EXACT) {
+            gbm_anti_path_exact<FN>(C, Z, C.n_paths, i, vf, va, vc);
+        } else {
+            ReplaySource src{Z, C.n_paths, i, C.nsteps};
+            gbm_anti_path_fast<double, FN, 0>(C, src, vf, va, vc);
+        }
+        emit_anti(C, i, vf, va, vc, acc, Pf_out, Pc_out);
     }
     grid_finish(acc, partials, ticket, out7);
 }

@@ -104,6 +104,7 @@ class Option:
 
     _model = None
     _payoff_kind = None
+    _has_anti = False             # Euro_GBM / Asian_GBM bind anti_payoff + anti_path (:1379-1381, :1406-1408)
 
     def __init__(self, alpha_0=None, beta_0=None, X0=100, K=100, T=1, r=0.05, *,
                  seed=0, device=0, sampler="f32bm", fp32=False, distributed=False, verbose=True):
@@ -125,7 +126,11 @@ class Option:
 
     # -- virtuals the reference declares (:816-915) ------------------------------------------
     def anti_payoff(self, N_loop, l, M):
-        raise NotImplementedError("Option instance has no implemented anti_payoff method")
+        """(0.5*(Pf+Pa), Pc) of the antithetic estimator (anti_EA_payoff :292-317); products without
+        one raise NotImplementedError as in the reference (:844)."""
+        if not self._has_anti:
+            raise NotImplementedError("Option instance has no implemented anti_payoff method")
+        return self._payoff_arrays(N_loop, l, M, _lib.ANTITHETIC)
 
     def path(self, N_loop, l, M):
         raise NotImplementedError("Option instance has no implemented path method")
@@ -201,6 +206,9 @@ class Option:
         """(Pf, Pc) for N_loop fresh coupled paths at level l; at l==0 the second item is the raw
         coarse path output, as in the reference (:82)."""
         self._check_product()
+        return self._payoff_arrays(N_loop, l, M, 0)
+
+    def _payoff_arrays(self, N_loop, l, M, extra_flags):
         import torch
         n = int(N_loop)
         start = self._take_ids(l, n)
@@ -210,7 +218,8 @@ class Option:
         out7 = torch.empty(7, dtype=torch.float64, device=dev)
         p = self._params()
         _lib.check(_lib.load().mlmcb_level_sums(
-            C.byref(p), self._model, self._payoff_kind, int(l), int(M), n, self.seed, start, self._flags(),
+            C.byref(p), self._model, self._payoff_kind, int(l), int(M), n, self.seed, start,
+            self._flags() | extra_flags,
             self.device, _stream_handle(self.device), out7.data_ptr(), Pf.data_ptr(), Pc.data_ptr()))
         return Pf.cpu().numpy(), Pc.cpu().numpy()
 
@@ -219,17 +228,14 @@ class Option:
         """suml (7,) float64 = [sum dP, sum dP^2, sum Pf, sum Pf^2, sum Pc, sum Pc^2, sum Pc*Pf];
         [sum Pf, sum Pf^2, sum Pf, sum Pf^2, 0,0,0] at l==0.  One kernel launch; Npl is accepted
         for signature compatibility (the GPU needs no chunking)."""
-        if anti == True:  # noqa: E712  (reference spelling :941)
-            return self._looper_anti(Nl, l, M)
-        return self._sweep([(int(Nl), int(l))], M)[0]
+        return self._sweep([(int(Nl), int(l))], M, anti=(anti == True))[0]  # noqa: E712 (reference spelling :941)
 
-    def _looper_anti(self, Nl, l, M):
-        self.anti_payoff(0, l, M)        # raises NotImplementedError, as the reference does (:844)
-
-    def _sweep(self, requests, M):
+    def _sweep(self, requests, M, anti=False):
         """requests: [(Nl, l), ...] -> list of 7-vectors.  All launches of one sweep run
         concurrently on the device; one D2H copy brings every row back."""
         self._check_product()
+        if anti and not self._has_anti:
+            raise NotImplementedError("Option instance has no implemented anti_payoff method")   # :844
         k = len(requests)
         if k == 0:
             return []
@@ -246,13 +252,13 @@ class Option:
         p = self._params()
         _lib.check(_lib.load().mlmcb_level_sweep_host(
             C.byref(p), self._model, self._payoff_kind, int(M), k, levels, n_arr, o_arr, self.seed,
-            self._flags(), self.device, _stream_handle(self.device),
+            self._flags() | (_lib.ANTITHETIC if anti else 0), self.device, _stream_handle(self.device),
             out.ctypes.data_as(C.POINTER(C.c_double))))
         out = self._allreduce(out)
         return [out[i].copy() for i in range(k)]
 
     # -- replay (parity check (a)) -----------------------------------------------------------
-    def payoff_replay(self, draws, l, M, arith="fast"):
+    def payoff_replay(self, draws, l, M, arith="fast", anti=False):
         """Feed the reference's own draws.  GBM: `draws` = Z (M**l, N) array, row j the
         np.random.randn(N) of step j+1.  Merton: dict with zW/offW, zQ/offQ, E/offE (CSR, the
         order the reference consumes them).  Returns (Pf, Pc) per path."""
@@ -260,6 +266,10 @@ class Option:
         import torch
         dev = torch.device("cuda", self.device)
         ar = {"fast": _lib.ARITH_FAST, "exact": _lib.ARITH_EXACT}[arith]
+        if anti:
+            if not self._has_anti:
+                raise NotImplementedError("Option instance has no implemented anti_payoff method")
+            ar |= _lib.ANTITHETIC
         p = self._params()
         st = _stream_handle(self.device)
         if self._model == GBM:
@@ -290,9 +300,11 @@ class Option:
     # -- MLMC driver (reference mlmc :960-1042) ----------------------------------------------
     def mlmc(self, eps, M=2, anti=False, N0=10 ** 3, warm_start=True):
         """Returns (sums (7,L+1) float64, N (L+1,) float64); price = sum(sums[0,:]/N)."""
-        if anti == True:  # noqa: E712
-            self.anti_payoff(0, 0, M)
-        sums, N, alpha, beta = mlmc_driver(self._sweep, eps, M, N0, self.alpha_0, self.beta_0)
+        use_anti = anti == True  # noqa: E712
+        if use_anti and not self._has_anti:
+            raise NotImplementedError("Option instance has no implemented anti_payoff method")
+        sums, N, alpha, beta = mlmc_driver(lambda reqs, M_: self._sweep(reqs, M_, anti=use_anti), eps, M, N0,
+                                           self.alpha_0, self.beta_0)
         if self.verbose:
             print(f'Estimated alpha = {alpha}')                 # :1034
             print(f'Estimated beta = {beta}')
@@ -305,9 +317,9 @@ class Option:
         return sums, N
 
     # -- numeric core of Giles_plot's fixed-level sweep (:1775-1777) -------------------------
-    def level_sweep(self, Lmax=8, Nsamples=10 ** 6, M=2):
-        """sums (7, Lmax+1) of looper(Nsamples, l, M) for l = 0..Lmax, issued as one sweep."""
-        rows = self._sweep([(int(Nsamples), l) for l in range(Lmax + 1)], M)
+    def level_sweep(self, Lmax=8, Nsamples=10 ** 6, M=2, anti=False):
+        """sums (7, Lmax+1) of looper(Nsamples, l, M, anti) for l = 0..Lmax, issued as one sweep."""
+        rows = self._sweep([(int(Nsamples), l) for l in range(Lmax + 1)], M, anti=anti)
         return np.stack(rows, axis=1)
 
 
@@ -345,6 +357,7 @@ class Merton_Option(Option):
 
 class Euro_GBM(GBM_Option):
     _payoff_kind = EURO
+    _has_anti = True
 
     def BS(self):                                               # :1383-1393
         D1 = (np.log(self.X0 / self.K) + (self.r + 0.5 * self.sig ** 2) * self.T) / (self.sig * np.sqrt(self.T))
@@ -354,6 +367,7 @@ class Euro_GBM(GBM_Option):
 
 class Asian_GBM(GBM_Option):
     _payoff_kind = ASIAN
+    _has_anti = True
 
     def BS(self):                                               # Turnbull-Wakeman approximation :1411-1429
         X0, r, T, sig, K = self.X0, self.r, self.T, self.sig, self.K

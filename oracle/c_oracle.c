@@ -114,6 +114,49 @@ static void gbm_one(const orc_params *p, int payoff, int l, int M, int64_t nstep
     *Pc = (l == 0) ? vc : payoff_of(p, payoff, vc, Mc, cc);        /* l==0: raw coarse output :82 */
 }
 
+/* ---- one antithetic GBM triple: diffusion_anti_path :162-217, _avg :219-290, anti_EA_payoff :292-317 -- *
+ * Returns Pf' = 0.5*(Pf+Pa) and Pc; at l==0 Pf and the raw coarse value (:311).                      */
+static void gbm_anti_one(const orc_params *p, int payoff, int l, int M, int64_t nsteps,
+                         const double *Z, int64_t zstride, orc_rng *g, double *Pf, double *Pc) {
+    const double T = p->T, X0 = p->X0, mu = p->r + p->drift, sig = p->sig;
+    const double dt = T / (double)nsteps, sqrt_dt = sqrt(dt);
+    double Xf = X0, Xc = X0, Xa = X0, dWc = 0.0;
+    double Af = 0.5 * dt * Xf, Aa = 0.5 * dt * Xa, Ac = 0.5 * M * dt * Xc;      /* :247-249 */
+    int64_t k = 0;
+    for (int64_t j = 2; j <= nsteps; j += 2) {
+        double zo = Z ? Z[k * zstride] : rng_normal(g), ze = Z ? Z[(k + 1) * zstride] : rng_normal(g);
+        k += 2;
+        double dWo = zo * sqrt_dt, dWe = ze * sqrt_dt;                            /* :195-196 */
+        Xf += gbm_inc(mu, sig, Xf, dt, dWo);                                      /* :200 */
+        Xa += gbm_inc(mu, sig, Xa, dt, dWe);                                      /* :201 */
+        if (payoff == ORC_ASIAN) { Af += dt * Xf; Aa += dt * Xa; }                /* :263-264 */
+        Xf += gbm_inc(mu, sig, Xf, dt, dWe);                                      /* :205 */
+        Xa += gbm_inc(mu, sig, Xa, dt, dWo);                                      /* :206 */
+        if (payoff == ORC_ASIAN) { Af += dt * Xf; Aa += dt * Xa; }                /* :271-272 */
+        dWc += dWo + dWe;                                                         /* :208 */
+        if (j % M == 0) {
+            Xc += gbm_inc(mu, sig, Xc, M * dt, dWc);                              /* :210 */
+            if (payoff == ORC_ASIAN) Ac += dt * M * Xc;                           /* :278 */
+            dWc = 0.0;
+        }
+    }
+    double vf, va, vc;
+    if (l == 0) {
+        double z = Z ? Z[0] : rng_normal(g);
+        Xf += gbm_inc(mu, sig, Xf, dt, z * sqrt_dt);                              /* :214 / :283 */
+        if (payoff == ORC_ASIAN) { Af += 0.5 * dt * Xf; vf = Af / T; } else vf = Xf;   /* :284 */
+        *Pf = payoff_of(p, payoff, vf, 0, 0);
+        *Pc = Xc;
+        return;
+    }
+    if (payoff == ORC_ASIAN) {
+        Af -= 0.5 * Xf * dt; Aa -= 0.5 * Xa * dt; Ac -= 0.5 * Xc * (M * dt);      /* :287-289 */
+        vf = Af / T; va = Aa / T; vc = Ac / T;
+    } else { vf = Xf; va = Xa; vc = Xc; }
+    *Pf = 0.5 * (payoff_of(p, payoff, vf, 0, 0) + payoff_of(p, payoff, va, 0, 0));    /* :317 */
+    *Pc = payoff_of(p, payoff, vc, 0, 0);
+}
+
 /* ---- one coupled Merton path: JD_path :428-492, _avg :494-571, _min :573-651 ------------ */
 typedef struct { const double *zW, *zQ, *E; int64_t iw, iq, ie; orc_rng *g; double scale; } jd_src;
 static inline double src_w(jd_src *s) { return s->zW ? s->zW[s->iw++] : rng_normal(s->g); }
@@ -186,6 +229,14 @@ int orc_gbm_replay(const orc_params *p, int payoff, int l, int M, int64_t n,
     return 0;
 }
 
+int orc_gbm_anti_replay(const orc_params *p, int payoff, int l, int M, int64_t n, const double *Z,
+                        double *Pf, double *Pc) {
+    if (M % 2 || (payoff != ORC_EURO && payoff != ORC_ASIAN)) return -1;
+    int64_t nsteps = ipow(M, l);
+    for (int64_t i = 0; i < n; ++i) gbm_anti_one(p, payoff, l, M, nsteps, Z + i, n, NULL, Pf + i, Pc + i);
+    return 0;
+}
+
 int orc_merton_replay(const orc_params *p, int payoff, int l, int M, int64_t n,
                       const double *zW, const int64_t *offW, const double *zQ, const int64_t *offQ,
                       const double *E, const int64_t *offE, double *Pf, double *Pc) {
@@ -203,7 +254,7 @@ int orc_merton_replay(const orc_params *p, int payoff, int l, int M, int64_t n,
  * libgomp).  out7 row order :955; l==0 row :949.  Thread t takes a contiguous slice of path
  * ids and the partial rows are added in thread order, so the result is deterministic.      */
 typedef struct {
-    const orc_params *p; int model, payoff, l, M; int64_t nsteps, lo, hi; uint64_t seed; double a[7];
+    const orc_params *p; int model, payoff, l, M, anti; int64_t nsteps, lo, hi; uint64_t seed; double a[7];
 } orc_job;
 
 static void *orc_worker(void *arg) {
@@ -213,7 +264,8 @@ static void *orc_worker(void *arg) {
     for (int64_t i = jb->lo; i < jb->hi; ++i) {
         orc_rng g; rng_seed(&g, jb->seed, (uint64_t)i + ((uint64_t)jb->l << 48));
         double Pf, Pc;
-        if (jb->model == ORC_GBM) gbm_one(jb->p, jb->payoff, jb->l, jb->M, jb->nsteps, NULL, 0, &g, &Pf, &Pc);
+        if (jb->anti) gbm_anti_one(jb->p, jb->payoff, jb->l, jb->M, jb->nsteps, NULL, 0, &g, &Pf, &Pc);
+        else if (jb->model == ORC_GBM) gbm_one(jb->p, jb->payoff, jb->l, jb->M, jb->nsteps, NULL, 0, &g, &Pf, &Pc);
         else {
             jd_src s = { NULL, NULL, NULL, 0, 0, 0, &g, 1.0 / jb->p->lam };
             mjd_one(jb->p, jb->payoff, jb->l, jb->M, jb->nsteps, &s, &Pf, &Pc);
@@ -227,14 +279,14 @@ static void *orc_worker(void *arg) {
     return NULL;
 }
 
-int orc_level_sums(const orc_params *p, int model, int payoff, int l, int M, int64_t n,
-                   uint64_t seed, int nthreads, double *out7) {
+static int level_sums_impl(const orc_params *p, int model, int payoff, int l, int M, int64_t n,
+                           uint64_t seed, int nthreads, int anti, double *out7) {
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     orc_job jobs[256]; pthread_t th[256];
     int64_t nsteps = ipow(M, l);
     for (int t = 0; t < nthreads; ++t) {
-        orc_job jb = { p, model, payoff, l, M, nsteps, n * t / nthreads, n * (t + 1) / nthreads, seed, {0} };
+        orc_job jb = { p, model, payoff, l, M, anti, nsteps, n * t / nthreads, n * (t + 1) / nthreads, seed, {0} };
         jobs[t] = jb;
     }
     for (int t = 1; t < nthreads; ++t) pthread_create(&th[t], NULL, orc_worker, &jobs[t]);
@@ -242,6 +294,18 @@ int orc_level_sums(const orc_params *p, int model, int payoff, int l, int M, int
     for (int t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
     for (int k = 0; k < 7; ++k) { double v = 0; for (int t = 0; t < nthreads; ++t) v += jobs[t].a[k]; out7[k] = v; }
     return 0;
+}
+
+int orc_level_sums(const orc_params *p, int model, int payoff, int l, int M, int64_t n,
+                   uint64_t seed, int nthreads, double *out7) {
+    return level_sums_impl(p, model, payoff, l, M, n, seed, nthreads, 0, out7);
+}
+
+/* looper(..., anti=True) :941-942 for Euro_GBM / Asian_GBM */
+int orc_level_sums_anti(const orc_params *p, int payoff, int l, int M, int64_t n,
+                        uint64_t seed, int nthreads, double *out7) {
+    if (M % 2 || (payoff != ORC_EURO && payoff != ORC_ASIAN)) return -1;
+    return level_sums_impl(p, ORC_GBM, payoff, l, M, n, seed, nthreads, 1, out7);
 }
 
 int orc_max_threads(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }

@@ -36,6 +36,9 @@ def lib():
                                         dp, ip, dp, ip, dp, ip, dp, dp]
         L.orc_level_sums.argtypes = [C.POINTER(OrcParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                      C.c_uint64, C.c_int, dp]
+        L.orc_gbm_anti_replay.argtypes = [C.POINTER(OrcParams), C.c_int, C.c_int, C.c_int, C.c_int64, dp, dp, dp]
+        L.orc_level_sums_anti.argtypes = [C.POINTER(OrcParams), C.c_int, C.c_int, C.c_int, C.c_int64,
+                                          C.c_uint64, C.c_int, dp]
         L.orc_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -68,6 +71,17 @@ def gbm_replay(p, payoff, l, M, Z):
     return Pf, Pc
 
 
+def gbm_anti_replay(p, payoff, l, M, Z):
+    Z = np.ascontiguousarray(Z, dtype=np.float64)
+    n = Z.shape[1]
+    assert Z.shape[0] == M ** l
+    Pf, Pc = np.empty(n), np.empty(n)
+    cp = to_params(p)
+    rc = lib().orc_gbm_anti_replay(C.byref(cp), payoff, l, M, n, _dp(Z), _dp(Pf), _dp(Pc))
+    assert rc == 0
+    return Pf, Pc
+
+
 def merton_replay(p, payoff, l, M, packed):
     n = len(packed["offW"]) - 1
     Pf, Pc = np.empty(n), np.empty(n)
@@ -82,6 +96,14 @@ def level_sums(p, model, payoff, l, M, n, seed=0, nthreads=1):
     out = np.zeros(7)
     cp = to_params(p)
     lib().orc_level_sums(C.byref(cp), model, payoff, l, M, int(n), int(seed), int(nthreads), _dp(out))
+    return out
+
+
+def level_sums_anti(p, payoff, l, M, n, seed=0, nthreads=1):
+    out = np.zeros(7)
+    cp = to_params(p)
+    rc = lib().orc_level_sums_anti(C.byref(cp), payoff, l, M, int(n), int(seed), int(nthreads), _dp(out))
+    assert rc == 0
     return out
 
 

@@ -164,6 +164,46 @@ def merton_cases(ref):
     return out
 
 
+def anti_cases(ref):
+    """anti_payoff (:292-317) per-path outputs for Euro_GBM / Asian_GBM, even M."""
+    out = {}
+    idx = 0
+    for cname in ("Euro_GBM", "Asian_GBM"):
+        for kw_name, kw in (("default", {}), ("alt2", ALT_GBM2)):
+            for M in (2, 4, 6):
+                for l in (0, 1, 2, 3, 5):
+                    if M == 6 and l > 3:
+                        continue
+                    steps = M ** l
+                    n = 96 if steps <= 64 else 32
+                    seed = 7000 + idx
+                    opt = getattr(ref, cname)(**kw)
+                    np.random.seed(seed)
+                    with Tap() as tap:
+                        Pf, Pc = opt.anti_payoff(n, l, M)
+                    Z = np.stack(tap.randn_calls)
+                    assert Z.shape == (steps, n)
+                    key = f"c{idx}"
+                    out[key + "_meta"] = np.array([cname, kw_name, str(l), str(M), str(n), str(seed)])
+                    out[key + "_Pf"] = np.asarray(Pf, dtype=np.float64)
+                    out[key + "_Pc"] = np.asarray(Pc, dtype=np.float64) * np.ones(n)
+                    idx += 1
+    # looper(anti=True) sums and the odd-M exception text
+    for j, (cname, l, M, Nl, Npl) in enumerate((("Euro_GBM", 2, 2, 1500, 1000), ("Asian_GBM", 3, 4, 700, 300),
+                                                 ("Asian_GBM", 0, 2, 900, 400))):
+        opt = getattr(ref, cname)()
+        np.random.seed(7700 + j)
+        out[f"l{j}_meta"] = np.array([cname, str(l), str(M), str(Nl), str(Npl), str(7700 + j)])
+        out[f"l{j}_sums"] = opt.looper(Nl, l, M, True, Npl)
+    try:
+        ref.Euro_GBM().looper(10, 2, 3, True)
+    except Exception as e:  # noqa: BLE001
+        out["odd_M_message"] = np.array(str(e))
+    out["n_cases"] = np.array(idx)
+    out["n_looper"] = np.array(3)
+    return out
+
+
 def looper_cases(ref):
     out = {}
     idx = 0
@@ -193,11 +233,14 @@ def mlmc_traces(ref):
         ("Lookback_GBM", dict(alpha_0=1, beta_0=1), 0.05, 4, 500, 13),
         ("Digital_GBM", dict(alpha_0=1, beta_0=0.5), 0.3, 4, 1000, 14),
         ("Euro_Merton", dict(alpha_0=1, beta_0=1), 0.3, 2, 1000, 15),
+        ("Asian_GBM", dict(alpha_0=1, beta_0=1, anti=True), 0.02, 4, 1000, 16),
         # regression branches: alpha_0=None with beta_0 given is legal Python 3 only if the
         # max(0,None) at :982 is bypassed; the reference raises TypeError there,
         # which test_mlmc_none_raises_in_reference pins.  Not traced here.
     ]
     for i, (cname, kw, eps, M, N0, seed) in enumerate(cases):
+        kw = dict(kw)
+        anti = kw.pop("anti", False)
         opt = getattr(ref, cname)(**kw)
         calls = []
         inner = opt.looper
@@ -210,8 +253,8 @@ def mlmc_traces(ref):
         opt.looper = looper
         np.random.seed(seed)
         with contextlib.redirect_stdout(io.StringIO()):
-            sums, N = opt.mlmc(eps, M=M, N0=N0, warm_start=True)
-        out[f"t{i}_meta"] = np.array([cname, repr(kw), repr(eps), str(M), str(N0), str(seed)])
+            sums, N = opt.mlmc(eps, M=M, anti=anti, N0=N0, warm_start=True)
+        out[f"t{i}_meta"] = np.array([cname, repr(kw), repr(eps), str(M), str(N0), str(seed), str(int(anti))])
         out[f"t{i}_req"] = np.array([(c[0], c[1]) for c in calls], dtype=np.int64)
         out[f"t{i}_ret"] = np.stack([c[2] for c in calls])
         out[f"t{i}_sums"] = sums
@@ -237,7 +280,8 @@ def closed_forms(ref):
 def main():
     ref = load_reference()
     os.makedirs(OUT, exist_ok=True)
-    for name, fn in (("payoffs_gbm", gbm_cases), ("payoffs_merton", merton_cases), ("looper", looper_cases),
+    for name, fn in (("payoffs_gbm", gbm_cases), ("payoffs_merton", merton_cases), ("payoffs_anti", anti_cases),
+                     ("looper", looper_cases),
                      ("mlmc_trace", mlmc_traces), ("closed_forms", closed_forms)):
         d = fn(ref)
         path = os.path.join(OUT, name + ".npz")

@@ -198,6 +198,78 @@ def gbm_paths(p, functional, l, M, Z=None, n=None):
     return Xf, Xc
 
 
+# ----------------------------------------------------------------------------- GBM antithetic paths
+def gbm_anti_paths(p, functional, l, M, Z=None, n=None):
+    """diffusion_anti_path :162-217 (functional EURO) / diffusion_anti_path_avg :219-290 (ASIAN).
+    Z rows follow the reference's call order: row 2k = dWf_odd of pair k, row 2k+1 = dWf_even
+    (:195-196); at l==0 the single row is the :214 / :283 draw.  Returns (f, a, c)."""
+    if M % 2 != 0:
+        raise Exception("Cannot calculate antithetic estimator for odd coarseness factor M - please use even M")
+    T, X0 = p.T, p.X0
+    Nsteps = M ** l
+    dt = T / Nsteps
+    sqrt_dt = np.sqrt(dt)
+    if Z is not None:
+        n = Z.shape[1]
+    draw = (lambda i: Z[i]) if Z is not None else (lambda i: np.random.randn(n))
+    Xf = X0 * np.ones(n)
+    Xc = X0 * np.ones(n)
+    Xa = X0 * np.ones(n)
+    if functional == ASIAN:
+        Af = 0.5 * dt * Xf                                          # :247
+        Aa = 0.5 * dt * Xa
+        Ac = 0.5 * M * dt * Xc
+    dWc = np.zeros(n)
+    k = 0
+    for j in range(2, Nsteps + 1, 2):
+        dWf_odd = draw(k) * sqrt_dt                                 # :195
+        dWf_even = draw(k + 1) * sqrt_dt                            # :196
+        k += 2
+        Xf += gbm_increment(p, Xf, dt, dWf_odd)                     # :200
+        Xa += gbm_increment(p, Xa, dt, dWf_even)                    # :201
+        if functional == ASIAN:
+            Af += dt * Xf                                           # :263
+            Aa += dt * Xa
+        Xf += gbm_increment(p, Xf, dt, dWf_even)                    # :205
+        Xa += gbm_increment(p, Xa, dt, dWf_odd)                     # :206
+        if functional == ASIAN:
+            Af += dt * Xf                                           # :271
+            Aa += dt * Xa
+        dWc += dWf_odd + dWf_even                                   # :208
+        if j % M == 0:
+            Xc += gbm_increment(p, Xc, M * dt, dWc)                 # :210
+            if functional == ASIAN:
+                Ac += dt * M * Xc                                   # :278
+            dWc = np.zeros(n)
+    if l == 0:
+        Xf += gbm_increment(p, Xf, dt, draw(0) * sqrt_dt)           # :214 / :283
+        if functional == ASIAN:
+            Af += 0.5 * dt * Xf                                     # :284
+            return Af / T, Af / T, Xc
+        return Xf, Xf, Xc
+    if functional == ASIAN:
+        Af -= 0.5 * Xf * dt                                         # :287-289
+        Aa -= 0.5 * Xa * dt
+        Ac -= 0.5 * Xc * (M * dt)
+        return Af / T, Aa / T, Ac / T
+    return Xf, Xa, Xc
+
+
+def anti_level_payoffs(p, payoff, l, M, n=None, Z=None):
+    """anti_EA_payoff :292-317 for Euro_GBM / Asian_GBM -> (0.5*(Pf+Pa), Pc); l==0: (Pf, Xc)."""
+    r, K, T = p.r, p.K, p.T
+    Xf, Xa, Xc = gbm_anti_paths(p, functional_of(payoff), l, M, Z=Z, n=n)
+    Pf = np.maximum(0, Xf - K)
+    Pf = np.exp(-r * T) * Pf
+    if l == 0:
+        return Pf, Xc
+    Pa = np.maximum(0, Xa - K)
+    Pa = np.exp(-r * T) * Pa
+    Pc = np.maximum(0, Xc - K)
+    Pc = np.exp(-r * T) * Pc
+    return 0.5 * (Pf + Pa), Pc
+
+
 # ----------------------------------------------------------------------------- Merton coupled paths
 def merton_paths(p, functional, l, M, n, draws=None):
     """JD_path :428-492 / JD_path_avg :494-571 / JD_path_min :573-651 (jump-adapted EM).
@@ -354,13 +426,16 @@ def seven_sums(Pf, Pc, l):
                      np.sum(Pc), np.sum(Pc ** 2), np.sum(Pc * Pf)])
 
 
-def looper(p, model, payoff, Nl, l, M, Npl=10 ** 4):
-    """Option.looper :919-957 (anti=False branch) on the numpy global RNG."""
+def looper(p, model, payoff, Nl, l, M, Npl=10 ** 4, anti=False):
+    """Option.looper :919-957 on the numpy global RNG."""
     num_rem = Nl
     suml = np.zeros(7)
     while num_rem > 0:
         N_loop = min(Npl, num_rem)
         num_rem -= N_loop
-        Pf, Pc = level_payoffs(p, model, payoff, l, M, n=N_loop)
+        if anti:
+            Pf, Pc = anti_level_payoffs(p, payoff, l, M, n=N_loop)          # :942
+        else:
+            Pf, Pc = level_payoffs(p, model, payoff, l, M, n=N_loop)
         suml += seven_sums(Pf, Pc, l)
     return suml

@@ -59,3 +59,10 @@ def payoff_tol(p, P):
     X0 stands in for K on lookbacks."""
     scale = (p.K if p.K is not None else p.X0) * np.exp(-p.r * p.T)
     return 1e-12 * np.maximum(np.abs(P), scale)
+
+
+def anti_cases(g):
+    for i in range(int(g["n_cases"])):
+        cname, kw_name, l, M, n, seed = [str(x) for x in g[f"c{i}_meta"]]
+        yield dict(idx=i, cname=cname, kw_name=kw_name, l=int(l), M=int(M), n=int(n), seed=int(seed),
+                   Pf=g[f"c{i}_Pf"], Pc=g[f"c{i}_Pc"], Z=None)

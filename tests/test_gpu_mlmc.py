@@ -57,3 +57,13 @@ def test_asian_matches_reference_limit(cuda_lib):
     opt = mm.Asian_GBM(verbose=False)
     sums, N = opt.mlmc(eps=0.005, M=4)
     assert abs(price(sums, N) - 5.7626) < 0.012
+
+
+def test_mlmc_antithetic(cuda_lib):
+    for cls in (mm.Euro_GBM, mm.Asian_GBM):
+        opt = cls(verbose=False, seed=3)
+        sums, N = opt.mlmc(eps=0.01, M=4, anti=True)
+        ref = opt.BS() if cls is mm.Euro_GBM else 5.7626
+        assert abs(price(sums, N) - ref) < 0.03
+    with pytest.raises(ValueError, match="odd coarseness factor"):
+        mm.Euro_GBM(verbose=False).mlmc(eps=0.1, M=3, anti=True)

@@ -166,3 +166,28 @@ def test_looper_host_call_and_sweep(cuda_lib):
     assert not np.array_equal(opt.looper(200_000, 2, 4, False), s)
     Pf, Pc = mm.Euro_GBM().payoff(1000, 0, 2)
     assert Pf.shape == (1000,) and np.all(Pc == 100.0)             # l==0: raw coarse output (:82)
+
+
+@pytest.mark.parametrize("cname,l,M", [(c, l, M) for c in ("Euro_GBM", "Asian_GBM") for (l, M) in ((0, 2), (1, 2), (2, 4), (3, 4), (2, 6))])
+def test_antithetic_level_moments(cuda_lib, c_oracle, cname, l, M):
+    """looper(anti=True): moments vs the pinned C port; the antithetic estimator keeps the mean of dP
+    and lowers its variance."""
+    _, pay = CLASS_CODES[cname]
+    n_gpu, n_cpu = 4_000_000, 400_000
+    ref = c_oracle.level_sums_anti(O.Params(), pay, l, M, n_cpu, seed=21 + l, nthreads=8)
+    opt = getattr(mm, cname)(seed=31)
+    s = opt.looper(n_gpu, l, M, True)
+    m_d, v_d, m_f, v_f = _moments(s, n_gpu, l)
+    rm_d, rv_d, rm_f, rv_f = _moments(ref, n_cpu, l)
+    se = lambda v: np.sqrt(v / n_gpu + v / n_cpu)
+    assert abs(m_d - rm_d) < 4 * se(max(v_d, rv_d)) + 1e-15
+    assert abs(m_f - rm_f) < 4 * se(max(v_f, rv_f))
+    if l > 0:
+        assert abs(v_d - rv_d) < 4 * rv_d * np.sqrt(300 / n_cpu)
+        plain = getattr(mm, cname)(seed=32).looper(n_gpu, l, M, False)
+        pm, pv, _, _ = _moments(plain, n_gpu, l)
+        assert abs(m_d - pm) < 4 * np.sqrt(v_d / n_gpu + pv / n_gpu)       # same expectation
+        assert v_d < pv                                                      # smaller variance
+        assert s[1] == pytest.approx(s[3] - 2 * s[6] + s[5], rel=1e-9, abs=1e-9 * s[3])
+    Pf, Pc = opt.anti_payoff(1000, l, M)
+    assert Pf.shape == (1000,) and Pc.shape == (1000,)

@@ -8,7 +8,7 @@ import pytest
 
 import multilevel_mc_sdes_b200 as mm
 from oracle import np_oracle as O
-from tests.helpers import case_kwargs, gbm_cases, merton_cases, oracle_params, payoff_tol, regen_Z
+from tests.helpers import CLASS_CODES, anti_cases, case_kwargs, gbm_cases, merton_cases, oracle_params, payoff_tol, regen_Z
 
 pytestmark = pytest.mark.gpu
 
@@ -118,3 +118,28 @@ def test_replay_edge_cases(cuda_lib):
     want = O.level_payoffs(O.Params(), O.MERTON, O.EURO, 1, 2, n=2, draws=O.ReplayDraws(packed))
     np.testing.assert_allclose(Pf, want[0], rtol=1e-13)
     np.testing.assert_allclose(Pc, want[1], rtol=1e-13)
+
+
+def test_antithetic_replay(golden, cuda_lib, c_oracle):
+    """anti_payoff (:292-317): reference-order policy bit-exact, production policy within 1e-12."""
+    n = 0
+    for c in anti_cases(golden["payoffs_anti"]):
+        p = oracle_params(c["cname"], c["kw_name"])
+        opt = _opt(c["cname"], c["kw_name"])
+        Z = regen_Z(c)
+        Pf, Pc = opt.payoff_replay(Z, c["l"], c["M"], arith="exact", anti=True)
+        assert np.array_equal(Pf, c["Pf"]) and np.array_equal(Pc, c["Pc"]), (c["cname"], c["l"], c["M"])
+        Pf, Pc = opt.payoff_replay(Z, c["l"], c["M"], arith="fast", anti=True)
+        assert np.all(np.abs(Pf - c["Pf"]) <= payoff_tol(p, c["Pf"])) and np.all(np.abs(Pc - c["Pc"]) <= payoff_tol(p, c["Pc"]))
+        n += 1
+    assert n > 40
+    # beyond the fixtures: l=7, M=4 (16 384 steps) against the pinned C restatement
+    Z = np.random.RandomState(77).randn(4 ** 7, 64)
+    for cname, pay in (("Euro_GBM", O.EURO), ("Asian_GBM", O.ASIAN)):
+        rf, rc = c_oracle.gbm_anti_replay(O.Params(), pay, 7, 4, Z)
+        Pf, Pc = getattr(mm, cname)().payoff_replay(Z, 7, 4, arith="exact", anti=True)
+        assert np.array_equal(Pf, rf) and np.array_equal(Pc, rc)
+    with pytest.raises(ValueError, match="odd coarseness factor"):
+        mm.Euro_GBM().payoff_replay(np.zeros((9, 4)), 2, 3, anti=True)
+    with pytest.raises(NotImplementedError):
+        mm.Lookback_GBM().payoff_replay(np.zeros((4, 4)), 2, 2, anti=True)

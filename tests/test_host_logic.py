@@ -72,7 +72,7 @@ def test_mlmc_driver_replays_reference_traces(golden):
     (Nl, l) sequence and return the same (sums, N) bit for bit (MLMC_RSCAM.py:960-1042)."""
     t = golden["mlmc_trace"]
     for i in range(int(t["n_cases"])):
-        meta = [str(x) for x in t[f"t{i}_meta"]]
+        meta = [str(x) for x in t[f"t{i}_meta"]]       # the anti=True trace drives the same host loop
         kw = eval(meta[1])
         eps, M, N0 = float(meta[2]), int(meta[3]), int(meta[4])
         req, ret = t[f"t{i}_req"], t[f"t{i}_ret"]
@@ -139,6 +139,9 @@ def test_option_surface_and_errors():
     with pytest.raises(NotImplementedError):
         mm.Euro_Merton().mlmc(0.1, anti=True)
     with pytest.raises(NotImplementedError):
+        mm.Digital_GBM().anti_payoff(10, 1, 2)
+    assert mm.Euro_GBM._has_anti and mm.Asian_GBM._has_anti and not mm.Lookback_GBM._has_anti
+    with pytest.raises(NotImplementedError):
         mm.Option().looper(10, 1, 2, False)                  # base class has no payoff (:829)
     with pytest.raises(ValueError):
         mm.Euro_GBM(sampler="ziggurat")
@@ -148,11 +151,12 @@ def test_option_surface_and_errors():
 
 def test_path_ids_advance_per_level(monkeypatch):
     """Every looper call must consume fresh path ids."""
-    seen = []
+    seen, flags_seen = [], []
 
     class FakeLib:
         def mlmcb_level_sweep_host(self, p, model, payoff, M, k, levels, n, off, seed, flags, dev, st, out):
             seen.append([(levels[i], n[i], off[i]) for i in range(k)])
+            flags_seen.append(flags)
             return 0
 
     monkeypatch.setattr(_lib, "load", lambda: FakeLib())
@@ -161,6 +165,9 @@ def test_path_ids_advance_per_level(monkeypatch):
     o.looper(500, 3, 4, False)
     o.looper(200, 2, 4, False)
     o.level_sweep(Lmax=3, Nsamples=10, M=4)
+    assert flags_seen[:3] == [0, 0, 0]
+    o.looper(5, 3, 4, True)
+    assert flags_seen[-1] == _lib.ANTITHETIC and seen[-1] == [(3, 5, 1510)]
     assert seen[0] == [(3, 1000, 0)] and seen[1] == [(3, 500, 1000)] and seen[2] == [(2, 200, 0)]
     assert seen[3] == [(0, 10, 0), (1, 10, 0), (2, 10, 200), (3, 10, 1500)]
 

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import np_oracle as O
-from tests.helpers import CLASS_CODES, gbm_cases, merton_cases, oracle_params, regen_Z
+from tests.helpers import CLASS_CODES, anti_cases, gbm_cases, merton_cases, oracle_params, regen_Z
 
 
 def test_np_oracle_gbm_bit_exact(golden):
@@ -94,3 +94,28 @@ def test_c_oracle_rng_mode_matches_closed_form(c_oracle):
         s = c_oracle.level_sums(p, O.GBM, O.EURO, l, 2, n, seed=3, nthreads=4)
         tot += s[0] / n
     assert abs(tot - 10.450583572185565) < 0.25   # bias at l=4 + sampling noise
+
+
+def test_oracles_antithetic_bit_exact(golden, c_oracle):
+    """anti_EA_payoff / diffusion_anti_path(_avg) :162-317: numpy and C restatements vs the reference."""
+    g = golden["payoffs_anti"]
+    n = 0
+    for c in anti_cases(g):
+        _, pay = CLASS_CODES[c["cname"]]
+        p = oracle_params(c["cname"], c["kw_name"])
+        Z = regen_Z(c)
+        Pf, Pc = O.anti_level_payoffs(p, pay, c["l"], c["M"], Z=Z.copy())
+        assert np.array_equal(Pf, c["Pf"]) and np.array_equal(np.asarray(Pc, dtype=float) * np.ones(c["n"]), c["Pc"])
+        Pf, Pc = c_oracle.gbm_anti_replay(p, pay, c["l"], c["M"], Z)
+        assert np.array_equal(Pf, c["Pf"]) and np.array_equal(Pc, c["Pc"]), c["idx"]
+        n += 1
+    assert n > 40
+    for j in range(int(g["n_looper"])):
+        cname, l, M, Nl, Npl, seed = [str(x) for x in g[f"l{j}_meta"]]
+        _, pay = CLASS_CODES[cname]
+        np.random.seed(int(seed))
+        s = O.looper(O.Params(), O.GBM, pay, int(Nl), int(l), int(M), Npl=int(Npl), anti=True)
+        assert np.array_equal(s, g[f"l{j}_sums"])
+    with pytest.raises(Exception, match="odd coarseness factor"):
+        O.anti_level_payoffs(O.Params(), O.EURO, 2, 3, n=4)
+    assert "odd coarseness factor" in str(g["odd_M_message"])
