@@ -2,7 +2,8 @@
 `Option.looper` / `Option.mlmc` contract.  See DESIGN.md; C ABI in include/mlmcb.h."""
 from .options import (Option, GBM_Option, Merton_Option, Euro_GBM, Asian_GBM, Lookback_GBM, Digital_GBM,
                       Euro_Merton, Asian_Merton, Lookback_Merton, Digital_Merton, mlmc_driver)
+from .giles import giles_analysis
 from . import _lib
 
 __all__ = ["Option", "GBM_Option", "Merton_Option", "Euro_GBM", "Asian_GBM", "Lookback_GBM", "Digital_GBM",
-           "Euro_Merton", "Asian_Merton", "Lookback_Merton", "Digital_Merton", "mlmc_driver", "_lib"]
+           "Euro_Merton", "Asian_Merton", "Lookback_Merton", "Digital_Merton", "mlmc_driver", "giles_analysis", "_lib"]

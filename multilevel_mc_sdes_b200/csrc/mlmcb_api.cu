@@ -111,6 +111,7 @@ int make_consts(const mlmcb_params* p, int model, int payoff, int l, int M, ull 
     C->a_f = C->mu * C->dt; C->b_f = C->sig * C->sqrt_dt; C->a_c = C->mu * C->Mdt;
     C->avg_wf = C->dt / C->T; C->avg_wc = C->Mdt / C->T;
     C->poly_q4 = MLMCB_Q4; C->poly_c4 = MLMCB_C4;
+    C->inv_blk_dt = 1.0 / (4.0 * C->dt);
     return 0;
 }
 

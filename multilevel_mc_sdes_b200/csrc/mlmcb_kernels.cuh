@@ -64,6 +64,7 @@ struct LevelConsts {
     double avg_wf, avg_wc;          // dt/T and M*dt/T
     // Merton
     double lam, inv_lam, jm, js;
+    double inv_blk_dt;              // 1/(4*dt): jump time -> block index
     float poly_q4, poly_c4;         // leading sin/cos coefficients as uniform operands (no per-block MOV)
 };
 
@@ -653,11 +654,12 @@ struct JD {
         dWc = (R)0; dtc = 0.0; tf = tau; tc = tau;                       // :470-473
     }
 
-    // the remainder step up to the grid time tn :477-482 (+ :637)
-    __device__ __forceinline__ void grid(const LevelConsts& C, double tn, R zw) {
-        double dt = tn - tf;                                             // :477
+    // the remainder step up to the grid time tn :477-482 (+ :637).  `whole` (production policy
+    // only): no jump fell inside this fine step, so dt is the grid step and its root is known.
+    __device__ __forceinline__ void grid(const LevelConsts& C, double tn, R zw, bool whole = false) {
+        const double dt = whole ? C.dt : tn - tf;                        // :477
         dtc += dt;                                                       // :478
-        R dWf = mul(zw, (R)sqrt(dt));                                    // :479
+        R dWf = mul(zw, (R)(whole ? C.sqrt_dt : sqrt(dt)));              // :479
         dWc = add(dWc, dWf);                                             // :480
         if (FN == FN_AVG) {                                              // :554-556
             Gf = add(Gf, half_area(Sf, dt));
@@ -714,34 +716,74 @@ __device__ __forceinline__ void jump_draws(const LevelConsts& C, ull pid, uint32
 }
 
 // Merton coupled path, Philox mode.  A 4-step block with no jump inside is exactly a GBM block
-// with drift c = r - lam*J_bar (fast path); a block that contains a jump takes the general
-// jump-adapted code above (rare: lam*T*4/nsteps per path).
+// with drift c = r - lam*J_bar; such blocks run in a tight loop identical to the GBM one, up to
+// the block that holds the next jump time (an integer compare per block).  A block that contains
+// a jump runs the general jump-adapted code above (rare: lam*T*4/nsteps per path), not unrolled.
+template <typename R, int FN, int SAMP>
+struct MjdWalker {
+    const LevelConsts& C;
+    ull pid;
+    JD<R, FN, AR_FAST> st;
+    uint32_t jk;
+    double tau;
+    R zq, zwj;
+    int cm;
+
+    __device__ __forceinline__ void start() {
+        st.init(C);
+        jk = 0; cm = 0;
+        double gap;
+        jump_draws<R, SAMP>(C, pid, jk, gap, zq, zwj);
+        tau = gap;                                                       // :454
+    }
+    // steps j0+1 .. j0+cnt through the reference's control flow (:455-487)
+    __device__ __forceinline__ void slow_block(ull j0, int cnt, R z0, R z1, R z2, R z3) {
+#pragma unroll 1
+        for (int k = 0; k < cnt; ++k) {
+            const R zk = k == 0 ? z0 : k == 1 ? z1 : k == 2 ? z2 : z3;
+            const double tn = (double)(j0 + k + 1) * C.dt;               // :456
+            bool whole = true;
+            while (tau < tn) {                                           // :457
+                st.jump(C, tau, zwj, zq);
+                ++jk;
+                double gap;
+                jump_draws<R, SAMP>(C, pid, jk, gap, zq, zwj);
+                tau += gap;                                              // :474
+                whole = false;
+            }
+            st.grid(C, tn, zk, whole);
+            if (++cm == C.M) { cm = 0; st.coarse(C, tn); }               // :483
+        }
+    }
+    // number of leading whole blocks [0, jb) that end at or before tau (no jump inside), <= cap
+    __device__ __forceinline__ uint32_t jump_block(uint32_t cap) const {
+        const double q = tau * C.inv_blk_dt;
+        uint32_t jb = q >= (double)cap ? cap : (uint32_t)q;
+        // agree exactly with the slow path's test `tau < (double)j*dt` at the block boundary
+        while (jb > 0 && tau < (double)(4ull * jb) * C.dt) --jb;
+        return jb;
+    }
+};
+
 template <typename R, int FN, int MT, int SAMP>
 __device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid,
                                                 double& vf, double& vc, double& gf, double& gc) {
     PhiloxSource<R, SAMP> src{C, pid};
-    JD<R, FN, AR_FAST> st;
-    st.init(C);
+    MjdWalker<R, FN, SAMP> w{C, pid};
+    w.start();
     const R af = (R)C.a_f, bf = (R)C.b_f, ac = (R)C.a_c;
-    uint32_t jk = 0;
-    double gap, tau;
-    R zq, zwj;
-    jump_draws<R, SAMP>(C, pid, jk, gap, zq, zwj);
-    tau = gap;                                                           // :454
-    int cm = 0;
-    const int M = C.M;
-    const uint32_t nblk = (uint32_t)((C.nsteps + 3) >> 2);
-    for (uint32_t b = 0; b < nblk; ++b) {
+    const uint32_t nfull = (uint32_t)(C.nsteps >> 2);
+    // jb = first block that may hold this path's next jump.  The block loop stays uniform across
+    // the warp (all lanes at the same b): lanes with b < jb take the GBM-like block, the others
+    // the jump-adapted one, and the warp reconverges at the end of every block.
+    uint32_t jb = MT != 0 ? w.jump_block(nfull) : 0;
+    R Xf = w.st.Sf, Xc = w.st.Sc, Gf = w.st.Gf, Gc = w.st.Gc;
+    for (uint32_t b = 0; b < nfull; ++b) {
         R z[4];
         src.load4(b, z);
-        const ull j0 = 4 * (ull)b;
-        const bool full = j0 + 4 <= C.nsteps;
-        const double t_end = (double)(j0 + 4) * C.dt;
-        if (MT != 0 && full && tau >= t_end) {
-            // ---- no jump in this block: regular steps, state is clean at both block ends
-            R Xf = st.Sf, Xc = st.Sc, sz = (R)0;
+        if (b < jb) {
             if (FN == FN_AVG) {
-                R acc = (R)0.5 * Xf, accc = (R)0.5 * Xc;
+                R acc = (R)0.5 * Xf, accc = (R)0.5 * Xc, sz = (R)0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     R t_ = fma_<R>(bf, z[k], af);
@@ -756,45 +798,51 @@ __device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid,
                         else accc += (k == 3) ? (R)0.5 * Xc : Xc;
                     }
                 }
-                st.Gf = fma_<R>((R)C.dt, acc, st.Gf);
-                st.Gc = fma_<R>((R)C.Mdt, accc, st.Gc);
-            } else {
+                Gf = fma_<R>((R)C.dt, acc, Gf);
+                Gc = fma_<R>((R)C.Mdt, accc, Gc);
+            } else if (MT == 4) {
+                const R s4 = (z[0] + z[1]) + (z[2] + z[3]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     R t_ = fma_<R>(bf, z[k], af);
                     Xf = fma_<R>(Xf, t_, Xf);
-                    sz += z[k];
-                    if (FN == FN_MIN) st.Gf = min_<R>(st.Gf, Xf);
-                    if ((MT == 4 && k == 3) || (MT == 2 && (k & 1))) {
-                        R tc_ = fma_<R>(bf, sz, ac);
-                        Xc = fma_<R>(Xc, tc_, Xc);
-                        sz = (R)0;
-                        if (FN == FN_MIN) st.Gc = min_<R>(st.Gc, Xc);
-                    }
+                    if (FN == FN_MIN) Gf = min_<R>(Gf, Xf);
                 }
-            }
-            st.Sf = Xf; st.Sc = Xc;
-            st.tf = st.tc = t_end;
-        } else {
-            // ---- general jump-adapted steps
+                R tc_ = fma_<R>(bf, s4, ac);
+                Xc = fma_<R>(Xc, tc_, Xc);
+                if (FN == FN_MIN) Gc = min_<R>(Gc, Xc);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const ull j = j0 + k + 1;
-                if (j <= C.nsteps) {
-                    const double tn = (double)j * C.dt;                  // :456
-                    while (tau < tn) {                                   // :457
-                        st.jump(C, tau, zwj, zq);
-                        ++jk;
-                        jump_draws<R, SAMP>(C, pid, jk, gap, zq, zwj);
-                        tau += gap;                                      // :474
-                    }
-                    st.grid(C, tn, z[k]);
-                    if (++cm == M) { cm = 0; st.coarse(C, tn); }         // :483
+                for (int k = 0; k < 4; k += 2) {
+                    R t0 = fma_<R>(bf, z[k], af), t1 = fma_<R>(bf, z[k + 1], af);
+                    Xf = fma_<R>(Xf, t0, Xf);
+                    if (FN == FN_MIN) Gf = min_<R>(Gf, Xf);
+                    Xf = fma_<R>(Xf, t1, Xf);
+                    if (FN == FN_MIN) Gf = min_<R>(Gf, Xf);
+                    R tc_ = fma_<R>(bf, z[k] + z[k + 1], ac);
+                    Xc = fma_<R>(Xc, tc_, Xc);
+                    if (FN == FN_MIN) Gc = min_<R>(Gc, Xc);
                 }
             }
+        } else {
+            // the block that holds a jump (or every block when M is generic): state is clean at
+            // the block start, so the walker restarts its clocks there
+            w.st.Sf = Xf; w.st.Sc = Xc; w.st.Gf = Gf; w.st.Gc = Gc;
+            if (MT != 0) w.st.tf = w.st.tc = (double)(4ull * b) * C.dt;
+            w.slow_block(4ull * b, 4, z[0], z[1], z[2], z[3]);
+            Xf = w.st.Sf; Xc = w.st.Sc; Gf = w.st.Gf; Gc = w.st.Gc;
+            if (MT != 0) jb = w.jump_block(nfull);
         }
     }
-    st.outputs(C, vf, vc, gf, gc);
+    w.st.Sf = Xf; w.st.Sc = Xc; w.st.Gf = Gf; w.st.Gc = Gc;
+    const int rem = (int)(C.nsteps & 3);
+    if (rem) {                           // l==0 (1 step), M=2,l=1 (2 steps), odd M
+        R z[4];
+        src.load4(nfull, z);
+        if (MT != 0) w.st.tf = w.st.tc = (double)(4ull * nfull) * C.dt;
+        w.slow_block(4ull * nfull, rem, z[0], z[1], z[2], z[3]);
+    }
+    w.st.outputs(C, vf, vc, gf, gc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -810,7 +858,7 @@ __device__ __forceinline__ void emit(const LevelConsts& C, ull i, double vf, dou
 }
 
 template <typename R, int MODEL, int FN, int MT, int SAMP>
-__global__ void __launch_bounds__(kThreads, (MODEL == 0 && SAMP == SAMP_F32BM) ? MLMCB_MINBLOCKS : 1)
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? 1 : (MODEL == 0 ? MLMCB_MINBLOCKS : 6))
 level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
              double* out7, double* Pf_out, double* Pc_out) {
     Sums7 acc;

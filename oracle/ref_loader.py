@@ -35,7 +35,16 @@ def _stub_matplotlib():
         m = types.ModuleType("matplotlib." + sub)
         setattr(root, sub, m)
         sys.modules["matplotlib." + sub] = m
-    sys.modules["matplotlib.legend"].Legend = type("Legend", (), {})
+    # inert stand-ins for the few names Giles_plot touches (:1829, :1862, :1870-1873), so the
+    # reference's own function can be run against recording axes in tests/test_giles_core.py
+
+    class Legend:
+        def __init__(self, *a, **k):
+            self._legend_box = types.SimpleNamespace()
+
+    sys.modules["matplotlib.legend"].Legend = Legend
+    sys.modules["matplotlib.ticker"].MaxNLocator = lambda *a, **k: None
+    sys.modules["matplotlib.pyplot"].Line2D = lambda *a, **k: None
     sys.modules["matplotlib"] = root
 
 

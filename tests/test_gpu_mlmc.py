@@ -67,3 +67,16 @@ def test_mlmc_antithetic(cuda_lib):
         assert abs(price(sums, N) - ref) < 0.03
     with pytest.raises(ValueError, match="odd coarseness factor"):
         mm.Euro_GBM(verbose=False).mlmc(eps=0.1, M=3, anti=True)
+
+
+def test_giles_analysis_on_gpu(cuda_lib):
+    """BASELINE config #3 shape: fixed-level sweep + regressions (Giles_plot core :1741-1823)."""
+    opt = mm.Lookback_GBM(verbose=False, alpha_0=1, beta_0=1)
+    out = mm.giles_analysis(opt, [0.1, 0.05], M=4, Lmax=6, Nsamples=2_000_000)
+    assert out["log_var_dP"].shape == (6,) and len(out["N"]) == 2
+    assert 0.7 < out["alpha"] < 1.3 and 0.7 < out["beta"] < 1.3       # Euler-Maruyama, lookback with offset
+    assert np.all(np.diff(out["log_var_dP"]) < 0)
+    assert out["cost_mlmc"][1] < out["cost_mc"][1]                    # MLMC beats plain MC at the finer eps
+    euro = mm.Euro_GBM(verbose=False, alpha_0=1, beta_0=1)
+    out = mm.giles_analysis(euro, [0.1], M=2, anti=True, Lmax=5, Nsamples=1_000_000)
+    assert out["log_var_dP_anti"].shape == (5,) and len(out["N_anti"]) == 1
