@@ -44,6 +44,11 @@ enum {
     MLMCB_SAMPLER_F64BM = 1,   /* canonical: 53-bit uniforms, fp64 Box-Muller (log/sqrt/sincospi)  */
     MLMCB_SAMPLER_MASK  = 0xF,
     MLMCB_FP32_PATHS    = 0x10,/* opt-in: path arithmetic in fp32 (sums stay fp64)                 */
+    MLMCB_MILSTEIN      = 0x40,/* Milstein instead of Euler-Maruyama increments: the reference's demo
+                                  notebook swaps `sde` for milstein_GBM / milstein_Merton
+                                  (ExampleUsages.ipynb cell 1: + 0.5*X*sig**2*(dW**2-dt)).  fp64 paths and
+                                  the default sampler only, not with MLMCB_ANTITHETIC -> MLMCB_ENOTIMPL.
+                                  May also be ORed into `arith` of the replay entry points.          */
     MLMCB_ANTITHETIC    = 0x20 /* antithetic estimator (looper(anti=True) :941-942): GBM Euro/Asian
                                   only (anti_EA_payoff :292-317, diffusion_anti_path(_avg) :162-290),
                                   even M; other products -> MLMCB_ENOTIMPL, odd M -> MLMCB_EINVAL.

@@ -11,6 +11,7 @@ EURO, ASIAN, LOOKBACK, DIGITAL = 0, 1, 2, 3
 SAMPLER_F32BM, SAMPLER_F64BM = 0, 1
 FP32_PATHS = 0x10
 ANTITHETIC = 0x20
+MILSTEIN = 0x40
 ARITH_FAST, ARITH_EXACT = 0, 1
 OK, EINVAL, ECUDA, ENOTIMPL = 0, -1, -2, -3
 

@@ -112,6 +112,11 @@ int make_consts(const mlmcb_params* p, int model, int payoff, int l, int M, ull 
     C->avg_wf = C->dt / C->T; C->avg_wc = C->Mdt / C->T;
     C->poly_q4 = MLMCB_Q4; C->poly_c4 = MLMCB_C4;
     C->inv_blk_dt = 1.0 / (4.0 * C->dt);
+    C->sig2 = pow(p->sig, 2.0);                                                      // self.sig**2
+    C->half_sig2 = 0.5 * C->sig2;
+    C->c_mil = C->half_sig2 * C->dt;
+    C->a_fm = (C->mu - C->half_sig2) * C->dt;
+    C->a_cm = (C->mu - C->half_sig2) * C->Mdt;
     return 0;
 }
 
@@ -120,28 +125,29 @@ int mt_of(int M) { return M == 2 ? 2 : M == 4 ? 4 : 0; }
 
 typedef void (*LevelKernel)(const LevelConsts, double*, unsigned*, double*, double*, double*);
 
-template <typename R, int MODEL, int FN, int SAMP>
+template <typename R, int MODEL, int FN, int SAMP, int SCH>
 LevelKernel pick_mt(int mt) {
     switch (mt) {
-    case 2: return level_kernel<R, MODEL, FN, 2, SAMP>;
-    case 4: return level_kernel<R, MODEL, FN, 4, SAMP>;
-    default: return level_kernel<R, MODEL, FN, 0, SAMP>;
+    case 2: return level_kernel<R, MODEL, FN, 2, SAMP, SCH>;
+    case 4: return level_kernel<R, MODEL, FN, 4, SAMP, SCH>;
+    default: return level_kernel<R, MODEL, FN, 0, SAMP, SCH>;
     }
 }
-template <typename R, int MODEL, int SAMP>
+template <typename R, int MODEL, int SAMP, int SCH>
 LevelKernel pick_fn(int fn, int mt) {
     switch (fn) {
-    case FN_AVG: return pick_mt<R, MODEL, FN_AVG, SAMP>(mt);
-    case FN_MIN: return pick_mt<R, MODEL, FN_MIN, SAMP>(mt);
-    default: return pick_mt<R, MODEL, FN_FINAL, SAMP>(mt);
+    case FN_AVG: return pick_mt<R, MODEL, FN_AVG, SAMP, SCH>(mt);
+    case FN_MIN: return pick_mt<R, MODEL, FN_MIN, SAMP, SCH>(mt);
+    default: return pick_mt<R, MODEL, FN_FINAL, SAMP, SCH>(mt);
     }
 }
-template <typename R, int SAMP>
+template <typename R, int SAMP, int SCH = SCH_EM>
 LevelKernel pick_model(int model, int fn, int mt) {
-    return model == MLMCB_GBM ? pick_fn<R, 0, SAMP>(fn, mt) : pick_fn<R, 1, SAMP>(fn, mt);
+    return model == MLMCB_GBM ? pick_fn<R, 0, SAMP, SCH>(fn, mt) : pick_fn<R, 1, SAMP, SCH>(fn, mt);
 }
 LevelKernel pick_kernel(int model, int payoff, int M, int flags) {
     const int fn = fn_of(payoff), mt = mt_of(M), samp = flags & MLMCB_SAMPLER_MASK;
+    if (flags & MLMCB_MILSTEIN) return pick_model<double, SAMP_F32BM, SCH_MILSTEIN>(model, fn, mt);
     if (flags & MLMCB_FP32_PATHS)
         return samp == MLMCB_SAMPLER_F64BM ? pick_model<float, SAMP_F64BM>(model, fn, mt)
                                            : pick_model<float, SAMP_F32BM>(model, fn, mt);
@@ -191,8 +197,10 @@ int ws_free(Workspace* w, cudaStream_t st) {
 int check_flags(int flags) {
     const int samp = flags & MLMCB_SAMPLER_MASK;
     if (samp != MLMCB_SAMPLER_F32BM && samp != MLMCB_SAMPLER_F64BM) return fail(MLMCB_EINVAL, "unknown sampler %d", samp);
-    if (flags & ~(MLMCB_SAMPLER_MASK | MLMCB_FP32_PATHS | MLMCB_ANTITHETIC))
+    if (flags & ~(MLMCB_SAMPLER_MASK | MLMCB_FP32_PATHS | MLMCB_ANTITHETIC | MLMCB_MILSTEIN))
         return fail(MLMCB_EINVAL, "unknown flag bits 0x%x", flags);
+    if ((flags & MLMCB_MILSTEIN) && ((flags & (MLMCB_FP32_PATHS | MLMCB_ANTITHETIC)) || samp != MLMCB_SAMPLER_F32BM))
+        return fail(MLMCB_ENOTIMPL, "Milstein is built for fp64 paths with the default sampler, without the antithetic estimator");
     return 0;
 }
 
@@ -354,10 +362,11 @@ int mlmcb_level_sweep_host(const mlmcb_params* p, int model, int payoff, int M, 
 int mlmcb_replay_gbm(const mlmcb_params* p, int payoff, int l, int M, uint64_t n_paths, const double* d_Z,
                      int arith, int device, void* cuda_stream, double* d_Pf, double* d_Pc, double* d_out7) {
     if (!d_Z || !d_Pf || !d_Pc) return fail(MLMCB_EINVAL, "NULL device pointer");
-    const bool anti = (arith & MLMCB_ANTITHETIC) != 0;
-    arith &= ~MLMCB_ANTITHETIC;
+    const bool anti = (arith & MLMCB_ANTITHETIC) != 0, mil = (arith & MLMCB_MILSTEIN) != 0;
+    arith &= ~(MLMCB_ANTITHETIC | MLMCB_MILSTEIN);
     if (arith != MLMCB_ARITH_FAST && arith != MLMCB_ARITH_EXACT) return fail(MLMCB_EINVAL, "unknown arith %d", arith);
     if (anti) {
+        if (mil) return fail(MLMCB_ENOTIMPL, "Milstein is not built with the antithetic estimator");
         if (int rc = check_anti(MLMCB_GBM, payoff, M)) return rc;
     }
     DeviceGuard g(device);
@@ -368,13 +377,17 @@ int mlmcb_replay_gbm(const mlmcb_params* p, int payoff, int l, int M, uint64_t n
     if (n_paths == 0) return 0;
     typedef void (*K)(const LevelConsts, const double*, double*, unsigned*, double*, double*, double*);
     static const K table[3][2] = {
-        {replay_gbm_kernel<FN_FINAL, AR_FAST>, replay_gbm_kernel<FN_FINAL, AR_EXACT>},
-        {replay_gbm_kernel<FN_AVG, AR_FAST>, replay_gbm_kernel<FN_AVG, AR_EXACT>},
-        {replay_gbm_kernel<FN_MIN, AR_FAST>, replay_gbm_kernel<FN_MIN, AR_EXACT>}};
+        {replay_gbm_kernel<FN_FINAL, AR_FAST, 0>, replay_gbm_kernel<FN_FINAL, AR_EXACT, 0>},
+        {replay_gbm_kernel<FN_AVG, AR_FAST, 0>, replay_gbm_kernel<FN_AVG, AR_EXACT, 0>},
+        {replay_gbm_kernel<FN_MIN, AR_FAST, 0>, replay_gbm_kernel<FN_MIN, AR_EXACT, 0>}};
+    static const K mil_table[3][2] = {
+        {replay_gbm_kernel<FN_FINAL, AR_FAST, 1>, replay_gbm_kernel<FN_FINAL, AR_EXACT, 1>},
+        {replay_gbm_kernel<FN_AVG, AR_FAST, 1>, replay_gbm_kernel<FN_AVG, AR_EXACT, 1>},
+        {replay_gbm_kernel<FN_MIN, AR_FAST, 1>, replay_gbm_kernel<FN_MIN, AR_EXACT, 1>}};
     static const K anti_table[2][2] = {
         {replay_gbm_anti_kernel<FN_FINAL, AR_FAST>, replay_gbm_anti_kernel<FN_FINAL, AR_EXACT>},
         {replay_gbm_anti_kernel<FN_AVG, AR_FAST>, replay_gbm_anti_kernel<FN_AVG, AR_EXACT>}};
-    K k = anti ? anti_table[fn_of(payoff)][arith] : table[fn_of(payoff)][arith];
+    K k = anti ? anti_table[fn_of(payoff)][arith] : mil ? mil_table[fn_of(payoff)][arith] : table[fn_of(payoff)][arith];
     int grid = (int)((n_paths + kThreads - 1) / kThreads);
     if (grid > 65535) grid = 65535;
     Workspace w;
@@ -391,6 +404,8 @@ int mlmcb_replay_merton(const mlmcb_params* p, int payoff, int l, int M, uint64_
                         double* d_Pf, double* d_Pc, double* d_out7) {
     if (!d_zW || !d_offW || !d_zQ || !d_offQ || !d_E || !d_offE || !d_Pf || !d_Pc)
         return fail(MLMCB_EINVAL, "NULL device pointer");
+    const bool mil = (arith & MLMCB_MILSTEIN) != 0;
+    arith &= ~MLMCB_MILSTEIN;
     if (arith != MLMCB_ARITH_FAST && arith != MLMCB_ARITH_EXACT) return fail(MLMCB_EINVAL, "unknown arith %d", arith);
     DeviceGuard g(device);
     if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
@@ -401,10 +416,14 @@ int mlmcb_replay_merton(const mlmcb_params* p, int payoff, int l, int M, uint64_
     typedef void (*K)(const LevelConsts, const double*, const long long*, const double*, const long long*,
                       const double*, const long long*, double*, unsigned*, double*, double*, double*);
     static const K table[3][2] = {
-        {replay_mjd_kernel<FN_FINAL, AR_FAST>, replay_mjd_kernel<FN_FINAL, AR_EXACT>},
-        {replay_mjd_kernel<FN_AVG, AR_FAST>, replay_mjd_kernel<FN_AVG, AR_EXACT>},
-        {replay_mjd_kernel<FN_MIN, AR_FAST>, replay_mjd_kernel<FN_MIN, AR_EXACT>}};
-    K k = table[fn_of(payoff)][arith];
+        {replay_mjd_kernel<FN_FINAL, AR_FAST, 0>, replay_mjd_kernel<FN_FINAL, AR_EXACT, 0>},
+        {replay_mjd_kernel<FN_AVG, AR_FAST, 0>, replay_mjd_kernel<FN_AVG, AR_EXACT, 0>},
+        {replay_mjd_kernel<FN_MIN, AR_FAST, 0>, replay_mjd_kernel<FN_MIN, AR_EXACT, 0>}};
+    static const K mil_table[3][2] = {
+        {replay_mjd_kernel<FN_FINAL, AR_FAST, 1>, replay_mjd_kernel<FN_FINAL, AR_EXACT, 1>},
+        {replay_mjd_kernel<FN_AVG, AR_FAST, 1>, replay_mjd_kernel<FN_AVG, AR_EXACT, 1>},
+        {replay_mjd_kernel<FN_MIN, AR_FAST, 1>, replay_mjd_kernel<FN_MIN, AR_EXACT, 1>}};
+    K k = mil ? mil_table[fn_of(payoff)][arith] : table[fn_of(payoff)][arith];
     int grid = (int)((n_paths + kThreads - 1) / kThreads);
     if (grid > 65535) grid = 65535;
     Workspace w;

@@ -42,6 +42,7 @@ typedef unsigned long long ull;
 enum { FN_FINAL = 0, FN_AVG = 1, FN_MIN = 2 };
 enum { AR_FAST = 0, AR_EXACT = 1 };
 enum { SAMP_F32BM = 0, SAMP_F64BM = 1 };
+enum { SCH_EM = 0, SCH_MILSTEIN = 1 };
 enum { PAY_EURO = 0, PAY_ASIAN = 1, PAY_LOOKBACK = 2, PAY_DIGITAL = 3 };
 
 constexpr int kThreads = 128;
@@ -65,6 +66,8 @@ struct LevelConsts {
     // Merton
     double lam, inv_lam, jm, js;
     double inv_blk_dt;              // 1/(4*dt): jump time -> block index
+    // Milstein scheme (ExampleUsages.ipynb cell 1: + 0.5*X*sig**2*(dW**2-dt))
+    double sig2, half_sig2, a_fm, a_cm, c_mil;
     float poly_q4, poly_c4;         // leading sin/cos coefficients as uniform operands (no per-block MOV)
 };
 
@@ -343,6 +346,18 @@ __device__ __forceinline__ void grid_finish(const Sums7& a, double* partials, un
     if (threadIdx.x < 7) out7[threadIdx.x] = tot;
 }
 
+// Per-step multiplicative update X <- X + X*t(z).  Euler-Maruyama: t = a + b z.  Milstein adds
+// 0.5 sig^2 (dW^2 - dt) = c z^2 - c with c = 0.5 sig^2 dt, i.e. t = (a - c) + b z + c z^2; the
+// coarse step sees dWc = sqrt(dt)*sum z over M dt:  t_c = (a_c - M c) + b s + c s^2.
+template <typename R, int SCH>
+struct StepCoef {
+    R a, b, c, ac;
+    __device__ __forceinline__ explicit StepCoef(const LevelConsts& C)
+        : a((R)(SCH ? C.a_fm : C.a_f)), b((R)C.b_f), c((R)C.c_mil), ac((R)(SCH ? C.a_cm : C.a_c)) {}
+    __device__ __forceinline__ R t(R z) const { return SCH ? fma_<R>(fma_<R>(c, z, b), z, a) : fma_<R>(b, z, a); }
+    __device__ __forceinline__ R tc(R s) const { return SCH ? fma_<R>(fma_<R>(c, s, b), s, ac) : fma_<R>(b, s, ac); }
+};
+
 // ------------------------------------------------------------------------------------------
 // GBM coupled path, production arithmetic.  Source supplies normals four steps at a time.
 // MT = 2 or 4: coarse refinement factor known at compile time (coarse steps fall on fixed
@@ -350,10 +365,10 @@ __device__ __forceinline__ void grid_finish(const Sums7& a, double* partials, un
 // Returns the path outputs the reference path function returns: terminal values (FN_FINAL),
 // averages (FN_AVG) or terminal values + minima (FN_MIN).
 // ------------------------------------------------------------------------------------------
-template <typename R, int FN, int MT, typename Source>
+template <typename R, int FN, int MT, int SCH, typename Source>
 __device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source& src,
                                               double& vf, double& vc, double& gf, double& gc) {
-    const R af = (R)C.a_f, bf = (R)C.b_f, ac = (R)C.a_c;
+    const StepCoef<R, SCH> co(C);
     R Xf = (R)C.X0, Xc = (R)C.X0, sz = (R)0;
     R Ff = FN == FN_MIN ? (R)C.X0 : (R)0, Fc = Ff;
     int cm = 0;
@@ -361,7 +376,7 @@ __device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source
 
 #define MLMCB_FINE(zz)                                                   \
     {                                                                    \
-        R t_ = fma_<R>(bf, (zz), af);                                    \
+        R t_ = co.t(zz);                                    \
         Xf = fma_<R>(Xf, t_, Xf);                                        \
         sz += (zz);                                                      \
         if (FN == FN_AVG) Ff += Xf;                                      \
@@ -369,14 +384,14 @@ __device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source
     }
 #define MLMCB_FINE_NOSUM(zz)                                             \
     {                                                                    \
-        R t_ = fma_<R>(bf, (zz), af);                                    \
+        R t_ = co.t(zz);                                    \
         Xf = fma_<R>(Xf, t_, Xf);                                        \
         if (FN == FN_AVG) Ff += Xf;                                      \
         if (FN == FN_MIN) Ff = min_<R>(Ff, Xf);                          \
     }
 #define MLMCB_COARSE()                                                   \
     {                                                                    \
-        R t_ = fma_<R>(bf, sz, ac);                                      \
+        R t_ = co.tc(sz);                                      \
         Xc = fma_<R>(Xc, t_, Xc);                                        \
         sz = (R)0;                                                       \
         if (FN == FN_AVG) Fc += Xc;                                      \
@@ -430,7 +445,12 @@ __device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source
 }
 
 // GBM coupled path, reference expression order (replay, bit-exact vs numpy).
-template <int FN>
+// Milstein increment in the notebook's order: ... + 0.5*X*(sig**2)*(dW**2-dt)
+__device__ __forceinline__ double milstein_term(const LevelConsts& C, double X, double h, double dW) {
+    return __dmul_rn(__dmul_rn(__dmul_rn(0.5, X), C.sig2), __dsub_rn(__dmul_rn(dW, dW), h));
+}
+
+template <int FN, int SCH>
 __device__ __forceinline__ void gbm_path_exact(const LevelConsts& C, const double* Z, ull n, ull i,
                                                double& vf, double& vc, double& gf, double& gc) {
     const double dt = C.dt, Mdt = C.Mdt, mu = C.mu, sig = C.sig, Md = C.Md;
@@ -442,12 +462,20 @@ __device__ __forceinline__ void gbm_path_exact(const LevelConsts& C, const doubl
     for (ull j = 0; j < C.nsteps; ++j) {
         double dWf = __dmul_rn(Z[j * n + i], C.sqrt_dt);                 // :343
         dWc = __dadd_rn(dWc, dWf);                                       // :344
-        Xf = __dadd_rn(Xf, __dadd_rn(__dmul_rn(__dmul_rn(mu, Xf), dt), __dmul_rn(__dmul_rn(sig, Xf), dWf)));   // :345
+        {
+            double inc = __dadd_rn(__dmul_rn(__dmul_rn(mu, Xf), dt), __dmul_rn(__dmul_rn(sig, Xf), dWf));
+            if (SCH) inc = __dadd_rn(inc, milstein_term(C, Xf, dt, dWf));
+            Xf = __dadd_rn(Xf, inc);                                     // :345
+        }
         if (FN == FN_AVG) Af = __dadd_rn(Af, __dmul_rn(Xf, dt));         // :377
         if (FN == FN_MIN) Mf = fmin(Xf, Mf);                             // :420
         if (++cm == C.M) {
             cm = 0;
-            Xc = __dadd_rn(Xc, __dadd_rn(__dmul_rn(__dmul_rn(mu, Xc), Mdt), __dmul_rn(__dmul_rn(sig, Xc), dWc)));  // :347
+            {
+                double inc = __dadd_rn(__dmul_rn(__dmul_rn(mu, Xc), Mdt), __dmul_rn(__dmul_rn(sig, Xc), dWc));
+                if (SCH) inc = __dadd_rn(inc, milstein_term(C, Xc, Mdt, dWc));
+                Xc = __dadd_rn(Xc, inc);                                 // :347
+            }
             if (FN == FN_AVG) Ac = __dadd_rn(Ac, __dmul_rn(__dmul_rn(Xc, Md), dt));   // :380
             if (FN == FN_MIN) Mc = fmin(Xc, Mc);                         // :423
             dWc = 0.0;
@@ -595,7 +623,7 @@ __device__ __forceinline__ void emit_anti(const LevelConsts& C, ull i, double vf
 // Merton jump-adapted coupled path state (JD_path* :428-651).  Times are always double.
 // G = trapezoid integral (FN_AVG) or running minimum (FN_MIN).
 // ------------------------------------------------------------------------------------------
-template <typename R, int FN, int AR>
+template <typename R, int FN, int AR, int SCH = SCH_EM>
 struct JD {
     R Sf, Sc, Gf, Gc, dWc;
     double dtc, tf, tc;
@@ -609,8 +637,12 @@ struct JD {
 
     // diffusion part of Merton_Option.sde :1314  dx_ = c*X*dt + sig*X*dW
     __device__ __forceinline__ R dx(const LevelConsts& C, R X, double dt, R dW) const {
-        if (AR == AR_EXACT)
-            return (R)__dadd_rn(__dmul_rn(__dmul_rn(C.mu, (double)X), dt), __dmul_rn(__dmul_rn(C.sig, (double)X), (double)dW));
+        if (AR == AR_EXACT) {
+            double d = __dadd_rn(__dmul_rn(__dmul_rn(C.mu, (double)X), dt), __dmul_rn(__dmul_rn(C.sig, (double)X), (double)dW));
+            if (SCH) d = __dadd_rn(d, milstein_term(C, (double)X, dt, (double)dW));
+            return (R)d;
+        }
+        if (SCH) return X * fma_<R>(fma_<R>((R)C.half_sig2, dW, (R)C.sig), dW, (R)((C.mu - C.half_sig2) * dt));
         return X * fma_<R>((R)C.sig, dW, (R)(C.mu * dt));
     }
     __device__ __forceinline__ R half_area(R S, double dt) const {       // 0.5*dt*S :532
@@ -719,11 +751,11 @@ __device__ __forceinline__ void jump_draws(const LevelConsts& C, ull pid, uint32
 // with drift c = r - lam*J_bar; such blocks run in a tight loop identical to the GBM one, up to
 // the block that holds the next jump time (an integer compare per block).  A block that contains
 // a jump runs the general jump-adapted code above (rare: lam*T*4/nsteps per path), not unrolled.
-template <typename R, int FN, int SAMP>
+template <typename R, int FN, int SAMP, int SCH>
 struct MjdWalker {
     const LevelConsts& C;
     ull pid;
-    JD<R, FN, AR_FAST> st;
+    JD<R, FN, AR_FAST, SCH> st;
     uint32_t jk;
     double tau;
     R zq, zwj;
@@ -765,13 +797,13 @@ struct MjdWalker {
     }
 };
 
-template <typename R, int FN, int MT, int SAMP>
+template <typename R, int FN, int MT, int SAMP, int SCH>
 __device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid,
                                                 double& vf, double& vc, double& gf, double& gc) {
     PhiloxSource<R, SAMP> src{C, pid};
-    MjdWalker<R, FN, SAMP> w{C, pid};
+    MjdWalker<R, FN, SAMP, SCH> w{C, pid};
     w.start();
-    const R af = (R)C.a_f, bf = (R)C.b_f, ac = (R)C.a_c;
+    const StepCoef<R, SCH> co(C);
     const uint32_t nfull = (uint32_t)(C.nsteps >> 2);
     // jb = first block that may hold this path's next jump.  The block loop stays uniform across
     // the warp (all lanes at the same b): lanes with b < jb take the GBM-like block, the others
@@ -786,12 +818,12 @@ __device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid,
                 R acc = (R)0.5 * Xf, accc = (R)0.5 * Xc, sz = (R)0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    R t_ = fma_<R>(bf, z[k], af);
+                    R t_ = co.t(z[k]);
                     Xf = fma_<R>(Xf, t_, Xf);
                     sz += z[k];
                     acc += (k == 3) ? (R)0.5 * Xf : Xf;
                     if ((MT == 4 && k == 3) || (MT == 2 && (k & 1))) {
-                        R tc_ = fma_<R>(bf, sz, ac);
+                        R tc_ = co.tc(sz);
                         Xc = fma_<R>(Xc, tc_, Xc);
                         sz = (R)0;
                         if (MT == 4) accc = fma_<R>((R)0.5, Xc, accc);
@@ -804,22 +836,22 @@ __device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid,
                 const R s4 = (z[0] + z[1]) + (z[2] + z[3]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    R t_ = fma_<R>(bf, z[k], af);
+                    R t_ = co.t(z[k]);
                     Xf = fma_<R>(Xf, t_, Xf);
                     if (FN == FN_MIN) Gf = min_<R>(Gf, Xf);
                 }
-                R tc_ = fma_<R>(bf, s4, ac);
+                R tc_ = co.tc(s4);
                 Xc = fma_<R>(Xc, tc_, Xc);
                 if (FN == FN_MIN) Gc = min_<R>(Gc, Xc);
             } else {
 #pragma unroll
                 for (int k = 0; k < 4; k += 2) {
-                    R t0 = fma_<R>(bf, z[k], af), t1 = fma_<R>(bf, z[k + 1], af);
+                    R t0 = co.t(z[k]), t1 = co.t(z[k + 1]);
                     Xf = fma_<R>(Xf, t0, Xf);
                     if (FN == FN_MIN) Gf = min_<R>(Gf, Xf);
                     Xf = fma_<R>(Xf, t1, Xf);
                     if (FN == FN_MIN) Gf = min_<R>(Gf, Xf);
-                    R tc_ = fma_<R>(bf, z[k] + z[k + 1], ac);
+                    R tc_ = co.tc(z[k] + z[k + 1]);
                     Xc = fma_<R>(Xc, tc_, Xc);
                     if (FN == FN_MIN) Gc = min_<R>(Gc, Xc);
                 }
@@ -857,7 +889,7 @@ __device__ __forceinline__ void emit(const LevelConsts& C, ull i, double vf, dou
     if (Pc_out) Pc_out[i] = Pc;
 }
 
-template <typename R, int MODEL, int FN, int MT, int SAMP>
+template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH>
 __global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? 1 : (MODEL == 0 ? MLMCB_MINBLOCKS : 6))
 level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
              double* out7, double* Pf_out, double* Pc_out) {
@@ -869,16 +901,16 @@ level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* 
         double vf, vc, gf, gc;
         if (MODEL == 0) {
             PhiloxSource<R, SAMP> src{C, pid};
-            gbm_path_fast<R, FN, MT>(C, src, vf, vc, gf, gc);
+            gbm_path_fast<R, FN, MT, SCH>(C, src, vf, vc, gf, gc);
         } else {
-            mjd_path_philox<R, FN, MT, SAMP>(C, pid, vf, vc, gf, gc);
+            mjd_path_philox<R, FN, MT, SAMP, SCH>(C, pid, vf, vc, gf, gc);
         }
         emit(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
     }
     grid_finish(acc, partials, ticket, out7);
 }
 
-template <int FN, int AR>
+template <int FN, int AR, int SCH>
 __global__ void __launch_bounds__(kThreads)
 replay_gbm_kernel(const __grid_constant__ LevelConsts C, const double* Z, double* partials, unsigned* ticket,
                   double* out7, double* Pf_out, double* Pc_out) {
@@ -888,10 +920,10 @@ replay_gbm_kernel(const __grid_constant__ LevelConsts C, const double* Z, double
     for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
         double vf, vc, gf, gc;
         if (AR == AR_EXACT) {
-            gbm_path_exact<FN>(C, Z, C.n_paths, i, vf, vc, gf, gc);
+            gbm_path_exact<FN, SCH>(C, Z, C.n_paths, i, vf, vc, gf, gc);
         } else {
             ReplaySource src{Z, C.n_paths, i, C.nsteps};
-            gbm_path_fast<double, FN, 0>(C, src, vf, vc, gf, gc);
+            gbm_path_fast<double, FN, 0, SCH>(C, src, vf, vc, gf, gc);
         }
         emit(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
     }
@@ -934,7 +966,7 @@ replay_gbm_anti_kernel(const __grid_constant__ LevelConsts C, const double* Z, d
     grid_finish(acc, partials, ticket, out7);
 }
 
-template <int FN, int AR>
+template <int FN, int AR, int SCH>
 __global__ void __launch_bounds__(kThreads)
 replay_mjd_kernel(const __grid_constant__ LevelConsts C, const double* zW, const long long* offW,
                   const double* zQ, const long long* offQ, const double* E, const long long* offE,
@@ -943,7 +975,7 @@ replay_mjd_kernel(const __grid_constant__ LevelConsts C, const double* zW, const
     acc.clear();
     const ull stride = (ull)gridDim.x * blockDim.x;
     for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
-        JD<double, FN, AR> st;
+        JD<double, FN, AR, SCH> st;
         st.init(C);
         long long iw = offW[i], iq = offQ[i], ie = offE[i];
         double tau = 0.0;

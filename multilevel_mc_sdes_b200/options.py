@@ -13,7 +13,8 @@ call consumes fresh ids).  `mlmc` is the reference driver restated l
 (host code; it only decides how many samples each level gets), None-safe for alpha_0/beta_0.
 
 Extra constructor kwargs (keyword-only, all optional): seed, device, sampler ("f32bm"|"f64bm"),
-fp32 (path arithmetic in fp32, opt-in), distributed (shard each level call over the
+fp32 (path arithmetic in fp32, opt-in), scheme ("em" | "milstein": the time-stepper the demo notebook
+swaps in through `opt.sde`, ExampleUsages.ipynb cells 1 and 6), distributed (shard each level call over the
 torch.distributed world and all-reduce the 7 sums).
 """
 import ctypes as C
@@ -107,7 +108,7 @@ class Option:
     _has_anti = False             # Euro_GBM / Asian_GBM bind anti_payoff + anti_path (:1379-1381, :1406-1408)
 
     def __init__(self, alpha_0=None, beta_0=None, X0=100, K=100, T=1, r=0.05, *,
-                 seed=0, device=0, sampler="f32bm", fp32=False, distributed=False, verbose=True):
+                 seed=0, device=0, sampler="f32bm", fp32=False, scheme="em", distributed=False, verbose=True):
         self.alpha_0 = alpha_0
         self.beta_0 = beta_0
         self.X0 = X0
@@ -120,6 +121,9 @@ class Option:
         self.device = int(device)
         self.sampler = sampler
         self.fp32 = bool(fp32)
+        if scheme not in ("em", "milstein"):
+            raise ValueError('scheme must be "em" or "milstein"')
+        self.scheme = scheme
         self.distributed = bool(distributed)
         self.verbose = verbose
         self._next_path = {}          # level -> next unused global path id
@@ -169,7 +173,8 @@ class Option:
         return p
 
     def _flags(self):
-        return _SAMPLERS[self.sampler] | (_lib.FP32_PATHS if self.fp32 else 0)
+        return (_SAMPLERS[self.sampler] | (_lib.FP32_PATHS if self.fp32 else 0)
+                | (_lib.MILSTEIN if self.scheme == "milstein" else 0))
 
     def _check_product(self):
         if self._model is None or self._payoff_kind is None:
@@ -266,6 +271,8 @@ class Option:
         import torch
         dev = torch.device("cuda", self.device)
         ar = {"fast": _lib.ARITH_FAST, "exact": _lib.ARITH_EXACT}[arith]
+        if self.scheme == "milstein":
+            ar |= _lib.MILSTEIN
         if anti:
             if not self._has_anti:
                 raise NotImplementedError("Option instance has no implemented anti_payoff method")
@@ -335,6 +342,8 @@ class GBM_Option(Option):
         self.mu = (r + drift)                                   # :1347
 
     def sde(self, X, dt, t_, dW):
+        if self.scheme == "milstein":                           # notebook cell 1, milstein_GBM
+            return self.mu * X * dt + self.sig * X * dW + 0.5 * X * (self.sig ** 2) * (dW ** 2 - dt)
         return self.mu * X * dt + self.sig * X * dW             # :1363
 
 
@@ -352,6 +361,8 @@ class Merton_Option(Option):
 
     def sde(self, X, dt, t_, dW, dJ=0):
         dx_ = (self.r - self.lam * self.J_bar) * X * dt + self.sig * X * dW     # :1314
+        if self.scheme == "milstein":                           # notebook cell 1, milstein_Merton
+            dx_ = dx_ + 0.5 * X * (self.sig ** 2) * (dW ** 2 - dt)
         return dx_ + (dx_ + X) * dJ
 
 

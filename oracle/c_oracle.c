@@ -27,6 +27,7 @@ typedef struct {
     double beta;                             /* Lookback offset constant :1443 / :1691      */
     double disc;                             /* np.exp(-r*T) as evaluated by the caller :80 */
     double J_bar;                            /* np.exp(jumpmean+0.5*jumpstd**2)-1 :1291     */
+    double milstein;                         /* != 0: the notebook's milstein_GBM / milstein_Merton increments */
 } orc_params;
 
 enum { ORC_GBM = 0, ORC_MERTON = 1 };
@@ -34,13 +35,21 @@ enum { ORC_EURO = 0, ORC_ASIAN = 1, ORC_LOOKBACK = 2, ORC_DIGITAL = 3 };
 
 static int64_t ipow(int M, int l) { int64_t n = 1; for (int i = 0; i < l; ++i) n *= M; return n; }
 
-/* GBM_Option.sde :1363  mu*X*dt + sig*X*dW */
+/* Scheme switch for the increments below; set per call from orc_params.milstein (the replay and
+ * level functions are not re-entrant across schemes, which the tests do not need). */
+static __thread int g_milstein = 0;
+static __thread double g_sig2 = 0.0;
+static void set_scheme(const orc_params *p) { g_milstein = p->milstein != 0.0; g_sig2 = pow(p->sig, 2.0); }
+
+/* GBM_Option.sde :1363  mu*X*dt + sig*X*dW ; notebook cell 1 milstein_GBM adds 0.5*X*(sig**2)*(dW**2-dt) */
 static inline double gbm_inc(double mu, double sig, double X, double dt, double dW) {
+    if (g_milstein) return mu * X * dt + sig * X * dW + 0.5 * X * g_sig2 * (dW * dW - dt);
     return mu * X * dt + sig * X * dW;
 }
-/* Merton_Option.sde :1314-1315 */
+/* Merton_Option.sde :1314-1315 ; notebook cell 1 milstein_Merton */
 static inline double mjd_inc(double c, double sig, double X, double dt, double dW, double dJ) {
-    double dx = c * X * dt + sig * X * dW;
+    double dx = g_milstein ? c * X * dt + sig * X * dW + 0.5 * X * g_sig2 * (dW * dW - dt)
+                           : c * X * dt + sig * X * dW;
     return dx + (dx + X) * dJ;
 }
 
@@ -225,6 +234,7 @@ int orc_gbm_replay(const orc_params *p, int payoff, int l, int M, int64_t n,
                    const double *Z /* [M**l][n], step-major as np.random.randn(N_loop) per step */,
                    double *Pf, double *Pc) {
     int64_t nsteps = ipow(M, l);
+    set_scheme(p);
     for (int64_t i = 0; i < n; ++i) gbm_one(p, payoff, l, M, nsteps, Z + i, n, NULL, Pf + i, Pc + i);
     return 0;
 }
@@ -233,6 +243,7 @@ int orc_gbm_anti_replay(const orc_params *p, int payoff, int l, int M, int64_t n
                         double *Pf, double *Pc) {
     if (M % 2 || (payoff != ORC_EURO && payoff != ORC_ASIAN)) return -1;
     int64_t nsteps = ipow(M, l);
+    set_scheme(p);
     for (int64_t i = 0; i < n; ++i) gbm_anti_one(p, payoff, l, M, nsteps, Z + i, n, NULL, Pf + i, Pc + i);
     return 0;
 }
@@ -241,6 +252,7 @@ int orc_merton_replay(const orc_params *p, int payoff, int l, int M, int64_t n,
                       const double *zW, const int64_t *offW, const double *zQ, const int64_t *offQ,
                       const double *E, const int64_t *offE, double *Pf, double *Pc) {
     int64_t nsteps = ipow(M, l);
+    set_scheme(p);
     for (int64_t i = 0; i < n; ++i) {
         jd_src s = { zW, zQ, E, offW[i], offQ[i], offE[i], NULL, 1.0 / p->lam };
         mjd_one(p, payoff, l, M, nsteps, &s, Pf + i, Pc + i);
@@ -260,6 +272,7 @@ typedef struct {
 static void *orc_worker(void *arg) {
     orc_job *jb = (orc_job *)arg;
     double *a = jb->a;
+    set_scheme(jb->p);
     for (int k = 0; k < 7; ++k) a[k] = 0;
     for (int64_t i = jb->lo; i < jb->hi; ++i) {
         orc_rng g; rng_seed(&g, jb->seed, (uint64_t)i + ((uint64_t)jb->l << 48));

@@ -11,7 +11,8 @@ _SO = os.path.join(_HERE, "libmlmc_oracle.so")
 
 class OrcParams(C.Structure):
     _fields_ = [(k, C.c_double) for k in
-                ("X0", "K", "T", "r", "sig", "drift", "lam", "jumpmean", "jumpstd", "beta", "disc", "J_bar")]
+                ("X0", "K", "T", "r", "sig", "drift", "lam", "jumpmean", "jumpstd", "beta", "disc", "J_bar",
+                 "milstein")]
 
 
 def build(force=False):
@@ -50,7 +51,8 @@ def to_params(p):
                      float(getattr(p, "drift", 0.0)), float(getattr(p, "lam", 1.0)),
                      float(getattr(p, "jumpmean", 0.0)), float(getattr(p, "jumpstd", 0.0)),
                      float(getattr(p, "beta", 0.5826)), float(np.exp(-p.r * p.T)),
-                     float(np.exp(getattr(p, "jumpmean", 0.0) + 0.5 * getattr(p, "jumpstd", 0.0) ** 2) - 1))
+                     float(np.exp(getattr(p, "jumpmean", 0.0) + 0.5 * getattr(p, "jumpstd", 0.0) ** 2) - 1),
+                     1.0 if getattr(p, "scheme", "em") == "milstein" else 0.0)
 
 
 def _dp(a):

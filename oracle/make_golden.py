@@ -204,6 +204,82 @@ def anti_cases(ref):
     return out
 
 
+# The demo notebook (ExampleUsages.ipynb cell 1) swaps the time-stepper by binding these two
+# functions over `opt.sde` with types.MethodType (cell 6).  They are the specification of the
+# Milstein option of the new backend, so they are restated here to drive the unmodified reference.
+def milstein_GBM(self, X, dt, t_, dW):
+    return self.mu * X * dt + self.sig * X * dW + 0.5 * X * (self.sig ** 2) * (dW ** 2 - dt)
+
+
+def milstein_Merton(self, X, dt, t_, dW, dJ=0):
+    dx_ = (self.r - self.lam * self.J_bar) * X * dt + self.sig * X * dW + 0.5 * X * (self.sig ** 2) * (dW ** 2 - dt)
+    return dx_ + (dx_ + X) * dJ
+
+
+def milstein_cases(ref):
+    import types
+    out = {}
+    idx = 0
+    for cname in GBM_CLASSES:
+        for kw_name, kw in (("default", {}), ("alt2", ALT_GBM2)):
+            for M in (2, 4, 3):
+                for l in (0, 1, 2, 3, 5):
+                    if M == 3 and l > 2:
+                        continue
+                    steps = M ** l
+                    n = 96 if steps <= 64 else 32
+                    seed = 8000 + idx
+                    kw2 = dict(kw)
+                    opt = getattr(ref, cname)(**kw2)
+                    opt.sde = types.MethodType(milstein_GBM, opt)
+                    np.random.seed(seed)
+                    Pf, Pc = opt.payoff(n, l, M)
+                    out[f"g{idx}_meta"] = np.array([cname, kw_name, str(l), str(M), str(n), str(seed)])
+                    out[f"g{idx}_Pf"] = np.asarray(Pf, dtype=np.float64)
+                    out[f"g{idx}_Pc"] = np.asarray(Pc, dtype=np.float64) * np.ones(n)
+                    idx += 1
+    out["n_gbm"] = np.array(idx)
+    idx = 0
+    for cname in MJD_CLASSES:
+        for kw_name, kw in (("default", {}), ("alt", ALT_MJD)):
+            for M in (2, 4):
+                for l in (0, 1, 2, 3):
+                    n = 32
+                    seed = 8500 + idx
+                    kw2 = dict(kw)
+                    opt = getattr(ref, cname)(**kw2)
+                    opt.sde = types.MethodType(milstein_Merton, opt)
+                    np.random.seed(seed)
+                    Pf_all, Pc_all, zw, zq, ex = [], [], [], [], []
+                    for _ in range(n):
+                        with Tap() as tap:
+                            tap.wrap_jumptime(opt)
+                            Pf, Pc = opt.payoff(1, l, M)
+                            opt.jumptime = np.random.exponential
+                        Pf_all.append(float(Pf[0]))
+                        Pc_all.append(float(np.asarray(Pc).reshape(-1)[0]))
+                        zw.append([float(v) for v in tap.randn_calls])
+                        zq.append(tap.stdn)
+                        ex.append(tap.expo)
+
+                    def csr(rows):
+                        off = np.zeros(len(rows) + 1, dtype=np.int64)
+                        off[1:] = np.cumsum([len(r) for r in rows])
+                        return np.array([v for r in rows for v in r], dtype=np.float64), off
+
+                    key = f"m{idx}"
+                    out[key + "_meta"] = np.array([cname, kw_name, str(l), str(M), str(n), str(seed)])
+                    out[key + "_Pf"] = np.array(Pf_all)
+                    out[key + "_Pc"] = np.array(Pc_all)
+                    for nm, rows in (("W", zw), ("Q", zq), ("E", ex)):
+                        flat, off = csr(rows)
+                        out[key + "_z" + nm] = flat
+                        out[key + "_off" + nm] = off
+                    idx += 1
+    out["n_merton"] = np.array(idx)
+    return out
+
+
 def looper_cases(ref):
     out = {}
     idx = 0
@@ -281,6 +357,7 @@ def main():
     ref = load_reference()
     os.makedirs(OUT, exist_ok=True)
     for name, fn in (("payoffs_gbm", gbm_cases), ("payoffs_merton", merton_cases), ("payoffs_anti", anti_cases),
+                     ("payoffs_milstein", milstein_cases),
                      ("looper", looper_cases),
                      ("mlmc_trace", mlmc_traces), ("closed_forms", closed_forms)):
         d = fn(ref)

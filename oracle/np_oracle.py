@@ -31,7 +31,8 @@ class Params:
     GBM_Option :1330-1347, Merton_Option :1273-1296, Lookback beta :1443/:1691)."""
 
     def __init__(self, X0=100, K=100, T=1, r=0.05, sig=0.2, drift=0, lam=1, jumpmean=0.1,
-                 jumpstd=0.2, beta=0.5826):
+                 jumpstd=0.2, beta=0.5826, scheme="em"):
+        self.scheme = scheme                                        # "em" | "milstein" (notebook cell 1)
         self.X0, self.K, self.T, self.r, self.sig, self.drift = X0, K, T, r, sig, drift
         self.lam, self.jumpmean, self.jumpstd, self.beta = lam, jumpmean, jumpstd, beta
         self.mu = r + drift                                         # :1347
@@ -139,13 +140,19 @@ class ReplayDraws:
 
 # ----------------------------------------------------------------------------- SDE increments
 def gbm_increment(p, X, dt, dW):
-    """GBM_Option.sde :1363  (t_ is ignored by the reference)."""
+    """GBM_Option.sde :1363  (t_ is ignored by the reference); with scheme="milstein" the
+    `milstein_GBM` the demo notebook binds in its place (ExampleUsages.ipynb cell 1)."""
+    if p.scheme == "milstein":
+        return p.mu * X * dt + p.sig * X * dW + 0.5 * X * (p.sig ** 2) * (dW ** 2 - dt)
     return p.mu * X * dt + p.sig * X * dW
 
 
 def merton_increment(p, X, dt, dW, dJ=0):
-    """Merton_Option.sde :1314-1315."""
-    dx_ = (p.r - p.lam * p.J_bar) * X * dt + p.sig * X * dW
+    """Merton_Option.sde :1314-1315 / notebook `milstein_Merton`."""
+    if p.scheme == "milstein":
+        dx_ = (p.r - p.lam * p.J_bar) * X * dt + p.sig * X * dW + 0.5 * X * (p.sig ** 2) * (dW ** 2 - dt)
+    else:
+        dx_ = (p.r - p.lam * p.J_bar) * X * dt + p.sig * X * dW
     return dx_ + (dx_ + X) * dJ
 
 

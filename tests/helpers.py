@@ -50,8 +50,8 @@ def merton_cases(g):
                    Pf=g[f"c{i}_Pf"], Pc=g[f"c{i}_Pc"], packed=packed)
 
 
-def oracle_params(cname, kw_name):
-    return O.Params(**case_kwargs(cname, kw_name))
+def oracle_params(cname, kw_name, scheme="em"):
+    return O.Params(scheme=scheme, **case_kwargs(cname, kw_name))
 
 
 def payoff_tol(p, P):
@@ -66,3 +66,19 @@ def anti_cases(g):
         cname, kw_name, l, M, n, seed = [str(x) for x in g[f"c{i}_meta"]]
         yield dict(idx=i, cname=cname, kw_name=kw_name, l=int(l), M=int(M), n=int(n), seed=int(seed),
                    Pf=g[f"c{i}_Pf"], Pc=g[f"c{i}_Pc"], Z=None)
+
+
+def milstein_gbm_cases(g):
+    for i in range(int(g["n_gbm"])):
+        cname, kw_name, l, M, n, seed = [str(x) for x in g[f"g{i}_meta"]]
+        yield dict(idx=i, cname=cname, kw_name=kw_name, l=int(l), M=int(M), n=int(n), seed=int(seed),
+                   Pf=g[f"g{i}_Pf"], Pc=g[f"g{i}_Pc"], Z=None)
+
+
+def milstein_merton_cases(g):
+    for i in range(int(g["n_merton"])):
+        cname, kw_name, l, M, n, seed = [str(x) for x in g[f"m{i}_meta"]]
+        packed = dict(zW=g[f"m{i}_zW"], offW=g[f"m{i}_offW"], zQ=g[f"m{i}_zQ"], offQ=g[f"m{i}_offQ"],
+                      E=g[f"m{i}_zE"], offE=g[f"m{i}_offE"])
+        yield dict(idx=i, cname=cname, kw_name=kw_name, l=int(l), M=int(M), n=int(n), seed=int(seed),
+                   Pf=g[f"m{i}_Pf"], Pc=g[f"m{i}_Pc"], packed=packed)

@@ -190,3 +190,31 @@ def test_antithetic_level_moments(cuda_lib, c_oracle, cname, l, M):
         assert s[1] == pytest.approx(s[3] - 2 * s[6] + s[5], rel=1e-9, abs=1e-9 * s[3])
     Pf, Pc = opt.anti_payoff(1000, l, M)
     assert Pf.shape == (1000,) and Pc.shape == (1000,)
+
+
+@pytest.mark.parametrize("cname", ["Euro_GBM", "Asian_GBM", "Lookback_GBM", "Euro_Merton", "Asian_Merton"])
+def test_milstein_level_moments(cuda_lib, c_oracle, cname):
+    model, pay = CLASS_CODES[cname]
+    n_gpu, n_cpu = 4_000_000, 400_000
+    for (l, M) in ((0, 2), (2, 4), (3, 2)):
+        ref = c_oracle.level_sums(O.Params(scheme="milstein"), model, pay, l, M, n_cpu, seed=5 + l, nthreads=8)
+        s = getattr(mm, cname)(seed=77, scheme="milstein").looper(n_gpu, l, M, False)
+        m_d, v_d, m_f, v_f = _moments(s, n_gpu, l)
+        rm_d, rv_d, rm_f, rv_f = _moments(ref, n_cpu, l)
+        se = lambda v: np.sqrt(v / n_gpu + v / n_cpu)
+        assert abs(m_d - rm_d) < 4 * se(max(v_d, rv_d)) + 1e-15, (l, M, m_d, rm_d)
+        assert abs(m_f - rm_f) < 4 * se(max(v_f, rv_f))
+        if l > 0:
+            assert abs(v_d - rv_d) < 4 * rv_d * np.sqrt(300 / n_cpu)
+    # Milstein has strong order 1: the variance of dP falls ~M^2 per level for the European payoff
+    if cname == "Euro_GBM":
+        o = mm.Euro_GBM(seed=1, scheme="milstein")
+        v = []
+        for l in (2, 3, 4):
+            s = o.looper(2_000_000, l, 4, False)
+            v.append(s[1] / 2e6 - (s[0] / 2e6) ** 2)
+        assert 10 < v[0] / v[1] < 24 and 10 < v[1] / v[2] < 24
+    with pytest.raises(NotImplementedError):
+        mm.Euro_GBM(scheme="milstein").looper(100, 2, 2, True)        # not built with the antithetic estimator
+    with pytest.raises(NotImplementedError):
+        mm.Euro_GBM(scheme="milstein", sampler="f64bm").looper(100, 2, 2, False)

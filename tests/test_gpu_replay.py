@@ -8,6 +8,7 @@ import pytest
 
 import multilevel_mc_sdes_b200 as mm
 from oracle import np_oracle as O
+from tests.helpers import milstein_gbm_cases, milstein_merton_cases
 from tests.helpers import CLASS_CODES, anti_cases, case_kwargs, gbm_cases, merton_cases, oracle_params, payoff_tol, regen_Z
 
 pytestmark = pytest.mark.gpu
@@ -143,3 +144,33 @@ def test_antithetic_replay(golden, cuda_lib, c_oracle):
         mm.Euro_GBM().payoff_replay(np.zeros((9, 4)), 2, 3, anti=True)
     with pytest.raises(NotImplementedError):
         mm.Lookback_GBM().payoff_replay(np.zeros((4, 4)), 2, 2, anti=True)
+
+
+def test_milstein_replay(golden, cuda_lib):
+    """scheme="milstein": GBM reference-order policy bit-exact, everything else within 1e-12."""
+    g = golden["payoffs_milstein"]
+    n = 0
+    for c in milstein_gbm_cases(g):
+        p = oracle_params(c["cname"], c["kw_name"])
+        opt = getattr(mm, c["cname"])(scheme="milstein", **case_kwargs(c["cname"], c["kw_name"]))
+        Z = regen_Z(c)
+        Pf, Pc = opt.payoff_replay(Z, c["l"], c["M"], arith="exact")
+        assert np.array_equal(Pf, c["Pf"]) and np.array_equal(Pc, c["Pc"]), (c["cname"], c["l"], c["M"])
+        Pf, Pc = opt.payoff_replay(Z, c["l"], c["M"], arith="fast")
+        if c["cname"] == "Digital_GBM":
+            assert np.array_equal(Pf, c["Pf"]) and np.array_equal(Pc, c["Pc"])
+        else:
+            assert np.all(np.abs(Pf - c["Pf"]) <= payoff_tol(p, c["Pf"])) and np.all(np.abs(Pc - c["Pc"]) <= payoff_tol(p, c["Pc"]))
+        n += 1
+    for c in milstein_merton_cases(g):
+        p = oracle_params(c["cname"], c["kw_name"])
+        opt = getattr(mm, c["cname"])(scheme="milstein", **case_kwargs(c["cname"], c["kw_name"]))
+        for arith in ("exact", "fast"):
+            Pf, Pc = opt.payoff_replay(c["packed"], c["l"], c["M"], arith=arith)
+            if c["cname"] == "Digital_Merton":
+                assert np.array_equal(Pf, c["Pf"])
+            else:
+                assert np.all(np.abs(Pf - c["Pf"]) <= payoff_tol(p, c["Pf"])), (c["idx"], arith)
+                assert np.all(np.abs(Pc - c["Pc"]) <= payoff_tol(p, c["Pc"])), (c["idx"], arith)
+        n += 1
+    assert n > 100

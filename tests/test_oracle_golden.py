@@ -3,7 +3,8 @@ import numpy as np
 import pytest
 
 from oracle import np_oracle as O
-from tests.helpers import CLASS_CODES, anti_cases, gbm_cases, merton_cases, oracle_params, regen_Z
+from tests.helpers import (CLASS_CODES, anti_cases, gbm_cases, merton_cases, milstein_gbm_cases,
+                           milstein_merton_cases, oracle_params, regen_Z)
 
 
 def test_np_oracle_gbm_bit_exact(golden):
@@ -119,3 +120,28 @@ def test_oracles_antithetic_bit_exact(golden, c_oracle):
     with pytest.raises(Exception, match="odd coarseness factor"):
         O.anti_level_payoffs(O.Params(), O.EURO, 2, 3, n=4)
     assert "odd coarseness factor" in str(g["odd_M_message"])
+
+
+def test_oracles_milstein(golden, c_oracle):
+    """The notebook's Milstein time-steppers bound over the reference's sde (ExampleUsages.ipynb cells 1, 6)."""
+    g = golden["payoffs_milstein"]
+    n = 0
+    for c in milstein_gbm_cases(g):
+        model, pay = CLASS_CODES[c["cname"]]
+        p = oracle_params(c["cname"], c["kw_name"], scheme="milstein")
+        Z = regen_Z(c)
+        Pf, Pc = O.level_payoffs(p, model, pay, c["l"], c["M"], Z=Z.copy())
+        assert np.array_equal(Pf, c["Pf"]) and np.array_equal(np.asarray(Pc, dtype=float) * np.ones(c["n"]), c["Pc"])
+        Pf, Pc = c_oracle.gbm_replay(p, pay, c["l"], c["M"], Z)
+        assert np.array_equal(Pf, c["Pf"]) and np.array_equal(Pc, c["Pc"]), c["idx"]
+        n += 1
+    for c in milstein_merton_cases(g):
+        model, pay = CLASS_CODES[c["cname"]]
+        p = oracle_params(c["cname"], c["kw_name"], scheme="milstein")
+        Pf, Pc = O.level_payoffs(p, model, pay, c["l"], c["M"], n=c["n"], draws=O.ReplayDraws(c["packed"]))
+        assert np.array_equal(Pf, c["Pf"]), c["idx"]
+        Pf, Pc = c_oracle.merton_replay(p, pay, c["l"], c["M"], c["packed"])
+        np.testing.assert_allclose(Pf, c["Pf"], rtol=0, atol=2e-13 * p.X0)
+        np.testing.assert_allclose(Pc, c["Pc"], rtol=0, atol=2e-13 * p.X0)
+        n += 1
+    assert n > 100
