@@ -6,6 +6,7 @@
 #include "mlmcb_kernels.cuh"
 
 #include <math.h>
+#include <mutex>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -259,6 +260,7 @@ struct HostSide {
 };
 constexpr int kMaxSweep = 64;
 HostSide g_host[64];
+std::mutex g_host_mu[64];          // the staging buffers of a device serve one _host call at a time
 
 int host_side(int dev, HostSide** out) {
     HostSide& h = g_host[dev];
@@ -311,6 +313,8 @@ int mlmcb_level_sums_host(const mlmcb_params* p, int model, int payoff, int l, i
     if (!h_out7) return fail(MLMCB_EINVAL, "h_out7 is NULL");
     DeviceGuard g(device);
     if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    if (device < 0 || device >= 64) return fail(MLMCB_EINVAL, "device %d out of range", device);
+    std::lock_guard<std::mutex> lock(g_host_mu[device]);
     HostSide* h;
     if (int rc = host_side(device, &h)) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -330,6 +334,8 @@ int mlmcb_level_sweep_host(const mlmcb_params* p, int model, int payoff, int M, 
     if (n_levels < 0 || n_levels > kMaxSweep) return fail(MLMCB_EINVAL, "n_levels=%d out of range (max %d)", n_levels, kMaxSweep);
     DeviceGuard g(device);
     if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    if (device < 0 || device >= 64) return fail(MLMCB_EINVAL, "device %d out of range", device);
+    std::lock_guard<std::mutex> lock(g_host_mu[device]);
     HostSide* h;
     if (int rc = host_side(device, &h)) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
