@@ -57,8 +57,8 @@ def write_sass_mix():
         import sass_mix
         hdr = open(os.path.join(CSRC, "mlmcb_kernels.cuh")).read()
         unroll = int(re.search(r"#define MLMCB_UNROLL (\d+)", hdr).group(1))
-        out = {k: sass_mix.hot_loop_mix(LIB, pat, 4 * unroll) for k, pat in
-               (("f32bm", "level_kernel<double, 0, 0, 4, 0>"), ("f64bm", "level_kernel<double, 0, 0, 4, 1>"))}
+        out = {k: sass_mix.hot_loop_mix(LIB, pat, 4 * (unroll if k == "f32bm" else 1)) for k, pat in
+               (("f32bm", "level_kernel<double, 0, 0, 4, 0, 0>"), ("f64bm", "level_kernel<double, 0, 0, 4, 1, 0>"))}
         json.dump(out, open(os.path.join(CSRC, "sass_mix.json"), "w"), indent=1)
     except Exception as e:  # cuobjdump missing: not fatal
         sys.stderr.write(f"sass_mix skipped: {e}\n")

@@ -29,6 +29,12 @@
 #ifndef MLMCB_MINBLOCKS
 #define MLMCB_MINBLOCKS 8           // GBM/f32bm kernels: cap at 64 registers -> 8 blocks of 128 threads per SM
 #endif
+#ifndef MLMCB_F64BM_LIBDEVICE
+#define MLMCB_F64BM_LIBDEVICE 0     // 1: the first-cut canonical sampler on CUDA's log/sqrt/sincospi
+#endif
+#ifndef MLMCB_MINBLOCKS_F64
+#define MLMCB_MINBLOCKS_F64 1
+#endif
 #ifndef MLMCB_PHILOX_ROUNDS
 #define MLMCB_PHILOX_ROUNDS 10      // experiments only; the shipped library is Philox4x32-10
 #endif
@@ -46,7 +52,6 @@ enum { SCH_EM = 0, SCH_MILSTEIN = 1 };
 enum { PAY_EURO = 0, PAY_ASIAN = 1, PAY_LOOKBACK = 2, PAY_DIGITAL = 3 };
 
 constexpr int kThreads = 128;
-constexpr int kUnroll = MLMCB_UNROLL;
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 
@@ -69,6 +74,8 @@ struct LevelConsts {
     // Milstein scheme (ExampleUsages.ipynb cell 1: + 0.5*X*sig**2*(dW**2-dt))
     double sig2, half_sig2, a_fm, a_cm, c_mil;
     float poly_q4, poly_c4;         // leading sin/cos coefficients as uniform operands (no per-block MOV)
+    // fp64 sampler constants, read straight from the constant bank by DFMA (no 64-bit immediates exist)
+    double dq[9], dc[9], lg[7], ln2_hi, ln2_lo;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -216,12 +223,88 @@ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {   // (0,1), 53
     return ((double)v + 0.5) * 0x1p-53;
 }
 
-__device__ __forceinline__ void bm_pair_f64(uint32_t a, uint32_t b, uint32_t c, uint32_t d, double& z0, double& z1) {
+// ---- canonical fp64 Box-Muller, hand-scheduled for B200's dispatch costs -------------------
+// All transcendental work is FP64-pipe instructions (1 dispatch cycle each) seeded by one MUFU
+// each; integer work is kept to the few bit operations that build the uniforms and split the
+// exponent.  Accuracy: |error| < 4e-16 absolute on each normal (tests/test_gpu_philox.py checks
+// the stream against a float64 recomputation from the same Philox words).
+
+// (0,1) uniform from 52 random bits (low 20 of `hi`, all of `lo`) plus a half-ulp offset.
+__device__ __forceinline__ double u52(uint32_t hi, uint32_t lo) {
+    return __hiloint2double((int)((hi & 0x000FFFFFu) | 0x3FF00000u), (int)lo) - (1.0 - 0x1p-53);
+}
+__device__ __forceinline__ double rcp64_seed(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));        // MUFU.RCP64H, ~2^-22
+    return y;
+}
+__device__ __forceinline__ double rsqrt64_seed(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));      // MUFU.RSQ64H, ~2^-22
+    return y;
+}
+// -2*ln(u) for a normal double u in (0,1): fdlibm's log (Sun, e_log.c) with the division done
+// by a reciprocal seed and two Newton steps.  Relative error < 2e-16.
+__device__ __forceinline__ double neg2_log(const LevelConsts& C, double u) {
+    const int ix = __double2hiint(u) + 0x00095F62;               // 0x3ff00000 - 0x3fe6a09e
+    const int k = (ix >> 20) - 0x3ff;
+    const double m = __hiloint2double((ix & 0x000fffff) + 0x3fe6a09e, __double2loint(u));   // [sqrt(1/2), sqrt(2))
+    const double f = m - 1.0, g = m + 1.0;
+    double y = rcp64_seed(g);
+    y = fma(y, fma(-g, y, 1.0), y);
+    y = fma(y, fma(-g, y, 1.0), y);
+    const double s = f * y;                                      // y is 1/g to ~1 ulp: no refinement needed
+    const double z = s * s;
+    double R = fma(z, C.lg[6], C.lg[5]);
+    R = fma(R, z, C.lg[4]);
+    R = fma(R, z, C.lg[3]);
+    R = fma(R, z, C.lg[2]);
+    R = fma(R, z, C.lg[1]);
+    R = fma(R, z, C.lg[0]);
+    R *= z;
+    const double hfsq = 0.5 * f * f, dk = (double)k;
+    // ln u = k*ln2_hi - ((hfsq - (s*(hfsq+R) + k*ln2_lo)) - f)
+    const double lg = fma(dk, C.ln2_hi, f - (hfsq - fma(s, hfsq + R, dk * C.ln2_lo)));
+    return -2.0 * lg;
+}
+// sqrt(s), s in [2e-16, 74]: reciprocal-root seed (2^-22), one coupled Newton (Goldschmidt) step
+// (2^-44) and one residual correction g + (s - g*g)*h, which squares the error again.  <= 1 ulp.
+__device__ __forceinline__ double sqrt_pos(double s) {
+    const double y = rsqrt64_seed(s);
+    double g = s * y, h = 0.5 * y;
+    const double r = fma(-g, h, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    return fma(fma(-g, g, s), h, g);
+}
+
+// sin(pi h)/h and cos(pi h) on |h| <= 1/2 as degree-8 polynomials in h^2 (tools/gen_trig_poly.py,
+// max abs error 3e-17 / 1e-16 including coefficient rounding)
+__device__ __forceinline__ void sincos_half(const LevelConsts& C, double h, double& sn_over_h, double& cs) {
+    const double T = h * h;
+    double q = fma(T, C.dq[8], C.dq[7]), c = fma(T, C.dc[8], C.dc[7]);
+#pragma unroll
+    for (int i = 6; i >= 0; --i) { q = fma(q, T, C.dq[i]); c = fma(c, T, C.dc[i]); }
+    sn_over_h = q; cs = c;
+}
+
+// One Philox block (a,b,c,d) -> two N(0,1): radius from u52(a,b), angle pi*h with h = u52-like
+// from (c,d) shifted to [-1/2,1/2), half-plane from the top bit of c.
+__device__ __forceinline__ void bm_pair_f64(const LevelConsts& C, uint32_t a, uint32_t b, uint32_t c, uint32_t d, double& z0, double& z1) {
+#if MLMCB_F64BM_LIBDEVICE
     double rad = sqrt(-2.0 * log(u53(a, b)));
     double sn, cs;
     sincospi(2.0 * u53(c, d), &sn, &cs);
     z0 = rad * cs;
     z1 = rad * sn;
+#else
+    double rad = sqrt_pos(neg2_log(C, u52(a, b)));
+    rad = __hiloint2double(__double2hiint(rad) | (int)(c & 0x80000000u), __double2loint(rad));
+    const double h = __hiloint2double((int)((c & 0x000FFFFFu) | 0x3FF00000u), (int)d) - 1.5;
+    double q, cs;
+    sincos_half(C, h, q, cs);
+    z0 = rad * cs;
+    z1 = (rad * h) * q;
+#endif
 }
 
 template <typename R> __device__ __forceinline__ R fma_(R a, R b, R c);
@@ -234,6 +317,7 @@ template <> __device__ __forceinline__ float min_<float>(float a, float b) { ret
 // Four grid-step normals for (path, block b) = steps 4b+1 .. 4b+4.
 template <typename R, int SAMP>
 struct PhiloxSource {
+    static constexpr int kUnroll = SAMP == SAMP_F32BM ? MLMCB_UNROLL : 1;   // blocks in flight per thread
     const LevelConsts& C;
     ull pid;
     __device__ __forceinline__ void load4(uint32_t b, R z[4]) const {
@@ -244,8 +328,8 @@ struct PhiloxSource {
         } else {
             U4 r = philox_at(C, pid, STREAM_GRID, 2 * b), s = philox_at(C, pid, STREAM_GRID, 2 * b + 1);
             double d0, d1, d2, d3;
-            bm_pair_f64(r.x, r.y, r.z, r.w, d0, d1);
-            bm_pair_f64(s.x, s.y, s.z, s.w, d2, d3);
+            bm_pair_f64(C, r.x, r.y, r.z, r.w, d0, d1);
+            bm_pair_f64(C, s.x, s.y, s.z, s.w, d2, d3);
             z[0] = (R)d0; z[1] = (R)d1; z[2] = (R)d2; z[3] = (R)d3;
         }
     }
@@ -253,6 +337,7 @@ struct PhiloxSource {
 
 // Replayed normals, step-major Z[step*n + path] (MLMC_RSCAM.py:343 call order).
 struct ReplaySource {
+    static constexpr int kUnroll = 1;
     const double* Z;
     ull n, i, nsteps;
     __device__ __forceinline__ void load4(uint32_t b, double z[4]) const {
@@ -399,7 +484,7 @@ __device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source
     }
 
     const uint32_t nblk = (uint32_t)(C.nsteps >> 2);
-#pragma unroll kUnroll
+#pragma unroll Source::kUnroll
     for (uint32_t b = 0; b < nblk; ++b) {
         R z[4];
         src.load4(b, z);
@@ -734,15 +819,15 @@ template <typename R, int SAMP>
 __device__ __forceinline__ void jump_draws(const LevelConsts& C, ull pid, uint32_t jk, double& gap, R& zq, R& zw) {
     if (SAMP == SAMP_F32BM) {
         U4 r = philox_at(C, pid, STREAM_JUMP, jk);
-        gap = -log(u53(r.x, r.y)) * C.inv_lam;
+        gap = neg2_log(C, u52(r.x, r.y)) * (0.5 * C.inv_lam);        // Exp(lam) inter-arrival time :454/:474
         float a, b;
         bm_pair_f32(C.poly_q4, C.poly_c4, r.z, r.w, a, b);
         zq = (R)a; zw = (R)b;
     } else {
         U4 r = philox_at(C, pid, STREAM_JUMP, 2 * jk), s = philox_at(C, pid, STREAM_JUMP, 2 * jk + 1);
-        gap = -log(u53(r.x, r.y)) * C.inv_lam;
+        gap = neg2_log(C, u52(r.x, r.y)) * (0.5 * C.inv_lam);        // Exp(lam) inter-arrival time :454/:474
         double a, b;
-        bm_pair_f64(s.x, s.y, s.z, s.w, a, b);
+        bm_pair_f64(C, s.x, s.y, s.z, s.w, a, b);
         zq = (R)a; zw = (R)b;
     }
 }
@@ -890,7 +975,7 @@ __device__ __forceinline__ void emit(const LevelConsts& C, ull i, double vf, dou
 }
 
 template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH>
-__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? 1 : (MODEL == 0 ? MLMCB_MINBLOCKS : 6))
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64 : (MODEL == 0 ? MLMCB_MINBLOCKS : 6))
 level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
              double* out7, double* Pf_out, double* Pc_out) {
     Sums7 acc;
