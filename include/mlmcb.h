@@ -33,10 +33,13 @@ typedef struct mlmcb_params {
     double beta;
     double disc;
     double J_bar;
+    double boundary_c;   /* MLMCB_AMERICAN: exercise boundary b(t) = max(K*(1 - c*sqrt(T-t)), 0) */
 } mlmcb_params;
 
 enum { MLMCB_GBM = 0, MLMCB_MERTON = 1 };                                   /* model   */
-enum { MLMCB_EURO = 0, MLMCB_ASIAN = 1, MLMCB_LOOKBACK = 2, MLMCB_DIGITAL = 3 };  /* payoff */
+enum { MLMCB_EURO = 0, MLMCB_ASIAN = 1, MLMCB_LOOKBACK = 2, MLMCB_DIGITAL = 3,       /* payoff */
+       MLMCB_AMERICAN = 4 /* American put, Amer_GBM.path :1511-1615 + Amer_payoff :138-158: GBM only, M == 2
+                             (:1524), the demo notebook's boundary family (ExampleUsages.ipynb cell 1) */ };
 
 /* flags for the Philox-mode level function */
 enum {

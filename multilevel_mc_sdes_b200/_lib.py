@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MLMCB_LIB") or os.path.join(_HERE, "csrc", "libmlmcb.so")   # MLMCB_LIB: kernel experiments
 
 GBM, MERTON = 0, 1
-EURO, ASIAN, LOOKBACK, DIGITAL = 0, 1, 2, 3
+EURO, ASIAN, LOOKBACK, DIGITAL, AMERICAN = 0, 1, 2, 3, 4
 SAMPLER_F32BM, SAMPLER_F64BM = 0, 1
 FP32_PATHS = 0x10
 ANTITHETIC = 0x20
@@ -19,7 +19,8 @@ OK, EINVAL, ECUDA, ENOTIMPL = 0, -1, -2, -3
 class Params(C.Structure):
     """struct mlmcb_params (include/mlmcb.h)."""
     _fields_ = [(k, C.c_double) for k in
-                ("X0", "K", "T", "r", "sig", "drift", "lam", "jumpmean", "jumpstd", "beta", "disc", "J_bar")]
+                ("X0", "K", "T", "r", "sig", "drift", "lam", "jumpmean", "jumpstd", "beta", "disc", "J_bar",
+                 "boundary_c")]
 
 
 class MlmcbError(RuntimeError):

@@ -77,7 +77,11 @@ int make_consts(const mlmcb_params* p, int model, int payoff, int l, int M, ull 
                 ull path_offset, LevelConsts* C) {
     if (!p) return fail(MLMCB_EINVAL, "params is NULL");
     if (model != MLMCB_GBM && model != MLMCB_MERTON) return fail(MLMCB_EINVAL, "unknown model %d", model);
-    if (payoff < 0 || payoff > 3) return fail(MLMCB_EINVAL, "unknown payoff %d", payoff);
+    if (payoff < 0 || payoff > 4) return fail(MLMCB_EINVAL, "unknown payoff %d", payoff);
+    if (payoff == MLMCB_AMERICAN) {
+        if (model != MLMCB_GBM) return fail(MLMCB_ENOTIMPL, "the American put is implemented for GBM only (Amer_GBM)");
+        if (M != 2) return fail(MLMCB_EINVAL, "M must be equal to 2 for American Option pricer. Please use M=2.");   // :1525
+    }
     if (l < 0 || l > 255) return fail(MLMCB_EINVAL, "level %d out of range", l);
     if (M < 2) return fail(MLMCB_EINVAL, "coarseness factor M=%d must be >= 2", M);
     if (path_offset + n_paths >= (1ull << 48)) return fail(MLMCB_EINVAL, "path ids must stay below 2^48");
@@ -124,11 +128,13 @@ int make_consts(const mlmcb_params* p, int model, int payoff, int l, int M, ull 
                                  1.479819860511658591e-01};
     memcpy(C->dq, dq, sizeof dq); memcpy(C->dc, dc, sizeof dc); memcpy(C->lg, lg, sizeof lg);
     C->ln2_hi = 6.93147180369123816490e-01; C->ln2_lo = 1.90821492927058770002e-10;
+    C->r = p->r; C->boundary_c = p->boundary_c;
     C->sig2 = pow(p->sig, 2.0);                                                      // self.sig**2
     C->half_sig2 = 0.5 * C->sig2;
     C->c_mil = C->half_sig2 * C->dt;
     C->a_fm = (C->mu - C->half_sig2) * C->dt;
     C->a_cm = (C->mu - C->half_sig2) * C->Mdt;
+    C->amer_cneg = -2.0 / (C->sig2 * C->dt);
     return 0;
 }
 
@@ -240,6 +246,37 @@ LevelKernel pick_anti_kernel(int payoff, int M, int flags) {
     return samp == MLMCB_SAMPLER_F64BM ? pick_anti_fn<double, SAMP_F64BM>(fn, mt) : pick_anti_fn<double, SAMP_F32BM>(fn, mt);
 }
 
+// American put: tabulate the per-step scalars, then run the path kernel (Philox or replay).
+constexpr ull kAmerMaxSteps = 1ull << 22;
+
+int amer_table(const LevelConsts& C, cudaStream_t st, AmerRow** tab) {
+    if (C.nsteps > kAmerMaxSteps) return fail(MLMCB_EINVAL, "American put: M**l above 2^22 fine steps is not supported");
+    CU(cudaMallocAsync((void**)tab, (size_t)(C.nsteps + 1) * sizeof(AmerRow), st));
+    const int threads = 128;
+    const int blocks = (int)((C.nsteps + 1 + threads - 1) / threads);
+    amer_table_kernel<<<blocks, threads, 0, st>>>(C, *tab);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int amer_level_sums(const LevelConsts& C, int flags, int device, cudaStream_t st, double* d_out7, double* d_Pf,
+                    double* d_Pc) {
+    if (flags & (MLMCB_FP32_PATHS | MLMCB_ANTITHETIC | MLMCB_MILSTEIN))
+        return fail(MLMCB_ENOTIMPL, "the American put is built for fp64 Euler-Maruyama paths without the antithetic estimator");
+    typedef void (*K)(const LevelConsts, const AmerRow*, double*, unsigned*, double*, double*, double*);
+    K k = (flags & MLMCB_SAMPLER_MASK) == MLMCB_SAMPLER_F64BM ? amer_level_kernel<SAMP_F64BM> : amer_level_kernel<SAMP_F32BM>;
+    int grid = 1;
+    if (int rc = geometry(k, device, C.n_paths, &grid, nullptr)) return rc;
+    AmerRow* tab = nullptr;
+    if (int rc = amer_table(C, st, &tab)) return rc;
+    Workspace w;
+    if (int rc = ws_alloc(grid, st, &w)) return rc;
+    k<<<grid, kThreads, 0, st>>>(C, tab, w.partials, w.ticket, d_out7, d_Pf, d_Pc);
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(tab, st));
+    return ws_free(&w, st);
+}
+
 int level_sums_impl(const mlmcb_params* p, int model, int payoff, int l, int M, ull n_paths, ull seed,
                     ull path_offset, int flags, int device, cudaStream_t st, double* d_out7, double* d_Pf,
                     double* d_Pc) {
@@ -251,6 +288,7 @@ int level_sums_impl(const mlmcb_params* p, int model, int payoff, int l, int M, 
         if (int rc = check_anti(model, payoff, M)) return rc;
     }
     if (n_paths == 0) { CU(cudaMemsetAsync(d_out7, 0, 7 * sizeof(double), st)); return 0; }
+    if (payoff == MLMCB_AMERICAN) return amer_level_sums(C, flags, device, st, d_out7, d_Pf, d_Pc);
     LevelKernel k = (flags & MLMCB_ANTITHETIC) ? pick_anti_kernel(payoff, M, flags) : pick_kernel(model, payoff, M, flags);
     int grid = 1;
     if (int rc = geometry(k, device, n_paths, &grid, nullptr)) return rc;
@@ -392,6 +430,23 @@ int mlmcb_replay_gbm(const mlmcb_params* p, int payoff, int l, int M, uint64_t n
     LevelConsts C;
     if (int rc = make_consts(p, MLMCB_GBM, payoff, l, M, n_paths, 0, 0, &C)) return rc;
     if (n_paths == 0) return 0;
+    if (payoff == MLMCB_AMERICAN) {
+        if (anti || mil) return fail(MLMCB_ENOTIMPL, "the American put is built for Euler-Maruyama without the antithetic estimator");
+        AmerRow* tab = nullptr;
+        if (int rc = amer_table(C, st, &tab)) return rc;
+        int grid = (int)((n_paths + kThreads - 1) / kThreads);
+        if (grid > 65535) grid = 65535;
+        Workspace w;
+        if (int rc = ws_alloc(grid + 1, st, &w)) return rc;
+        double* out = d_out7 ? d_out7 : w.partials;
+        if (arith == MLMCB_ARITH_EXACT)
+            replay_amer_kernel<AR_EXACT><<<grid, kThreads, 0, st>>>(C, tab, d_Z, w.partials + 8, w.ticket, out, d_Pf, d_Pc);
+        else
+            replay_amer_kernel<AR_FAST><<<grid, kThreads, 0, st>>>(C, tab, d_Z, w.partials + 8, w.ticket, out, d_Pf, d_Pc);
+        CU(cudaGetLastError());
+        CU(cudaFreeAsync(tab, st));
+        return ws_free(&w, st);
+    }
     typedef void (*K)(const LevelConsts, const double*, double*, unsigned*, double*, double*, double*);
     static const K table[3][2] = {
         {replay_gbm_kernel<FN_FINAL, AR_FAST, 0>, replay_gbm_kernel<FN_FINAL, AR_EXACT, 0>},
@@ -482,8 +537,12 @@ int mlmcb_launch_geometry(int model, int payoff, int M, int flags, int device, i
     if (flags & MLMCB_ANTITHETIC) {
         if (int rc = check_anti(model, payoff, M)) return rc;
     }
-    LevelKernel k = (flags & MLMCB_ANTITHETIC) ? pick_anti_kernel(payoff, M, flags) : pick_kernel(model, payoff, M, flags);
-    if (int rc = geometry(k, device, ~0ull >> 16, &grid, &mb)) return rc;
+    if (payoff == MLMCB_AMERICAN) {
+        if (int rc = geometry(amer_level_kernel<SAMP_F32BM>, device, ~0ull >> 16, &grid, &mb)) return rc;
+    } else {
+        LevelKernel k = (flags & MLMCB_ANTITHETIC) ? pick_anti_kernel(payoff, M, flags) : pick_kernel(model, payoff, M, flags);
+        if (int rc = geometry(k, device, ~0ull >> 16, &grid, &mb)) return rc;
+    }
     if (threads_per_block) *threads_per_block = kThreads;
     if (max_blocks) *max_blocks = mb;
     return 0;

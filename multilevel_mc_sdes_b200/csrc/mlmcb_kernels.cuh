@@ -49,7 +49,7 @@ enum { FN_FINAL = 0, FN_AVG = 1, FN_MIN = 2 };
 enum { AR_FAST = 0, AR_EXACT = 1 };
 enum { SAMP_F32BM = 0, SAMP_F64BM = 1 };
 enum { SCH_EM = 0, SCH_MILSTEIN = 1 };
-enum { PAY_EURO = 0, PAY_ASIAN = 1, PAY_LOOKBACK = 2, PAY_DIGITAL = 3 };
+enum { PAY_EURO = 0, PAY_ASIAN = 1, PAY_LOOKBACK = 2, PAY_DIGITAL = 3, PAY_AMERICAN = 4 };
 
 constexpr int kThreads = 128;
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
@@ -71,6 +71,7 @@ struct LevelConsts {
     // Merton
     double lam, inv_lam, jm, js;
     double inv_blk_dt;              // 1/(4*dt): jump time -> block index
+    double r, boundary_c, amer_cneg;  // American put: rate, boundary constant, -2/(sig^2 dt); discounting inside the path, exercise boundary constant
     // Milstein scheme (ExampleUsages.ipynb cell 1: + 0.5*X*sig**2*(dW**2-dt))
     double sig2, half_sig2, a_fm, a_cm, c_mil;
     float poly_q4, poly_c4;         // leading sin/cos coefficients as uniform operands (no per-block MOV)
@@ -960,6 +961,188 @@ __device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid,
         w.slow_block(4ull * nfull, rem, z[0], z[1], z[2], z[3]);
     }
     w.st.outputs(C, vf, vc, gf, gc);
+}
+
+// ------------------------------------------------------------------------------------------
+// American put under GBM: Amer_GBM.path :1511-1615 + Amer_payoff :138-158 (M == 2 only, :1524),
+// with the demo notebook's exercise boundary b(t) = max(K*(1-c*sqrt(T-t)), 0) (cell 1, `exb`).
+// Everything that depends only on the step index - barrier values, exercise values, discount
+// factors - is the same for every path, so a small set-up kernel tabulates it once per launch
+// (one 64-byte row per fine step, evaluated in the reference's operation order); the path kernel
+// then reads one row per step (same address across the warp -> broadcast) and keeps the three
+// state components of the fine and of the coarse path in registers.
+// The reference's `halfdWc=dWc` (:1577) aliases the array that `dWc += dWf` (:1549) updates in
+// place, so at the coarse step halfdWc IS dWc; the mid-point (:1585) is reproduced as such.
+// ------------------------------------------------------------------------------------------
+struct AmerRow {
+    double bR;        // b(j*dt): right barrier of fine step j, left barrier of step j+1      :1561
+    double mkF, eF;   // max(K - b(tfMid), 0) and exp(-r*tfMid), tfMid = (j-1)*dt + dt/2     :1558-1569
+    double mkC, eC;   // j even: max(K - b(tcMid), 0), exp(-r*tcMid), tcMid = (j-M)*dt + M*dt/2   :1590-1605
+    double mb1;       // j even: 0.5*(b(j*dt) + b((j-M)*dt))                                   :1599
+    double pad0, pad1;
+};
+
+__device__ __forceinline__ double amer_eb(const LevelConsts& C, double t) {
+    return fmax(__dmul_rn(C.K, __dsub_rn(1.0, __dmul_rn(C.boundary_c, __dsqrt_rn(__dsub_rn(C.T, t))))), 0.0);
+}
+
+__global__ void amer_table_kernel(const __grid_constant__ LevelConsts C, AmerRow* tab) {
+    const ull j = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > C.nsteps) return;
+    AmerRow row = {0, 0, 0, 0, 0, 0, 0, 0};
+    const double tj = __dmul_rn((double)j, C.dt);
+    row.bR = amer_eb(C, tj);
+    if (j >= 1) {
+        const double t_ = __dmul_rn((double)(j - 1), C.dt), tm = __dadd_rn(t_, __ddiv_rn(C.dt, 2.0));
+        row.mkF = fmax(__dsub_rn(C.K, amer_eb(C, tm)), 0.0);
+        row.eF = exp(__dmul_rn(-C.r, tm));
+        if (j % 2 == 0) {
+            const double tc = __dmul_rn((double)(j - 2), C.dt), tcm = __dadd_rn(tc, __ddiv_rn(C.Mdt, 2.0));
+            row.mkC = fmax(__dsub_rn(C.K, amer_eb(C, tcm)), 0.0);
+            row.eC = exp(__dmul_rn(-C.r, tcm));
+            row.mb1 = __dmul_rn(0.5, __dadd_rn(row.bR, amer_eb(C, tc)));
+        }
+    }
+    tab[j] = row;
+}
+
+template <int AR>
+struct AmerState {
+    double f0, f1, f2, c0, c1, c2, dWc, lbF, lbC;
+
+    __device__ __forceinline__ void init(const LevelConsts& C, const AmerRow* tab) {
+        f0 = c0 = C.X0; f1 = c1 = 1.0; f2 = c2 = 0.0; dWc = 0.0;
+        lbF = lbC = __ldg(&tab[0].bR);
+    }
+    // probability of touching the barrier inside a step (Brownian-bridge formula) :1566 / :1600
+    __device__ __forceinline__ static double touch(const LevelConsts& C, double A, double B, double Xl) {
+        if (AR == AR_EXACT)
+            return exp(__ddiv_rn(__dmul_rn(__dmul_rn(-2.0, A), B), __dmul_rn(__dmul_rn(C.sig2, C.dt), __dmul_rn(Xl, Xl))));
+        return exp((C.amer_cneg * A) * B / (Xl * Xl));
+    }
+    __device__ __forceinline__ static double inc(const LevelConsts& C, double X, double h, double dW, double a, double b) {
+        if (AR == AR_EXACT) return __dadd_rn(__dmul_rn(__dmul_rn(C.mu, X), h), __dmul_rn(__dmul_rn(C.sig, X), dW));
+        return X * fma(b, dW, a);          // here dW is the normal (or the sum of two), b = sig*sqrt(dt)
+    }
+    // fine step j with normal z; row = tab[j]
+    __device__ __forceinline__ void fine(const LevelConsts& C, const AmerRow& row, double z) {
+        double Xl = f0, Xr, dWf;
+        if (AR == AR_EXACT) {
+            dWf = __dmul_rn(C.sqrt_dt, z);                              // :1548
+            dWc = __dadd_rn(dWc, dWf);
+            Xr = __dadd_rn(Xl, inc(C, Xl, C.dt, dWf, 0, 0));            // :1554
+        } else {
+            dWc += z;                                                    // in units of sqrt(dt)
+            Xr = fma(Xl, fma(C.b_f, z, C.a_f), Xl);
+        }
+        const double A = fmax(Xl - lbF, 0.0), B = fmax(Xr - row.bR, 0.0);
+        const double P1 = touch(C, A, B, Xl);
+        if (AR == AR_EXACT) {
+            f2 = __dadd_rn(f2, __dmul_rn(__dmul_rn(__dmul_rn(f1, P1), row.mkF), row.eF));      // :1569
+            f1 = __dmul_rn(f1, __dsub_rn(1.0, P1));                      // :1571
+        } else {
+            f2 = fma(f1 * P1, row.mkF * row.eF, f2);
+            f1 = fma(-f1, P1, f1);
+        }
+        f0 = Xr;
+        lbF = row.bR;
+    }
+    // coarse step ending at even j; row = tab[j]
+    __device__ __forceinline__ void coarse(const LevelConsts& C, const AmerRow& row) {
+        double Xl = c0, Xr, Xmid;
+        if (AR == AR_EXACT) {
+            Xr = __dadd_rn(Xl, inc(C, Xl, C.Mdt, dWc, 0, 0));            // :1584
+            Xmid = __dadd_rn(__dadd_rn(Xl, __dmul_rn(0.5, __dsub_rn(Xr, Xl))),
+                             __dmul_rn(__dmul_rn(C.sig, Xl), __dsub_rn(dWc, __dmul_rn(0.5, dWc))));    // :1585
+        } else {
+            Xr = fma(Xl, fma(C.b_f, dWc, C.a_c), Xl);
+            Xmid = fma(C.b_f * Xl, 0.5 * dWc, fma(0.5, Xr - Xl, Xl));
+        }
+        const double A = fmax(Xl - lbC, 0.0), Bm = fmax(Xmid - row.mb1, 0.0), B = fmax(Xr - row.bR, 0.0);
+        const double P11 = touch(C, A, Bm, Xl), P12 = touch(C, Bm, B, Xl);   // :1600-1601
+        if (AR == AR_EXACT) {
+            const double P1 = __dsub_rn(1.0, __dmul_rn(__dsub_rn(1.0, P11), __dsub_rn(1.0, P12)));   // :1603
+            c2 = __dadd_rn(c2, __dmul_rn(__dmul_rn(__dmul_rn(c1, P1), row.mkC), row.eC));         // :1605
+            c1 = __dmul_rn(c1, __dsub_rn(1.0, P1));
+        } else {
+            const double keep = (1.0 - P11) * (1.0 - P12);
+            c2 = fma(c1 * (1.0 - keep), row.mkC * row.eC, c2);
+            c1 *= keep;
+        }
+        c0 = Xr;
+        lbC = row.bR;
+        dWc = 0.0;
+    }
+    // Amer_payoff :153-157
+    __device__ __forceinline__ void payoffs(const LevelConsts& C, double& Pf, double& Pc) const {
+        Pf = __dadd_rn(f2, __dmul_rn(__dmul_rn(f1, fmax(__dsub_rn(C.K, f0), 0.0)), C.disc));
+        Pc = C.is_l0 ? 0.0 : __dadd_rn(c2, __dmul_rn(__dmul_rn(c1, fmax(__dsub_rn(C.K, c0), 0.0)), C.disc));
+    }
+};
+
+__device__ __forceinline__ AmerRow load_row(const AmerRow* tab, ull j) {
+    const double2* p = reinterpret_cast<const double2*>(tab + j);
+    const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    AmerRow r = {a.x, a.y, b.x, b.y, c.x, c.y, 0.0, 0.0};
+    return r;
+}
+
+template <int SAMP>
+__global__ void __launch_bounds__(kThreads)
+amer_level_kernel(const __grid_constant__ LevelConsts C, const AmerRow* tab, double* partials, unsigned* ticket,
+                  double* out7, double* Pf_out, double* Pc_out) {
+    Sums7 acc;
+    acc.clear();
+    const ull stride = (ull)gridDim.x * blockDim.x;
+    for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
+        PhiloxSource<double, SAMP> src{C, C.path_offset + i};
+        AmerState<AR_FAST> st;
+        st.init(C, tab);
+        const uint32_t nblk = (uint32_t)((C.nsteps + 3) >> 2);
+        for (uint32_t b = 0; b < nblk; ++b) {
+            double z[4];
+            src.load4(b, z);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const ull j = 4ull * b + k + 1;
+                if (j <= C.nsteps) {
+                    const AmerRow row = load_row(tab, j);
+                    st.fine(C, row, z[k]);
+                    if (k & 1) st.coarse(C, row);
+                }
+            }
+        }
+        double Pf, Pc;
+        st.payoffs(C, Pf, Pc);
+        acc.add(Pf, Pc, C.is_l0);
+        if (Pf_out) Pf_out[i] = Pf;
+        if (Pc_out) Pc_out[i] = Pc;
+    }
+    grid_finish(acc, partials, ticket, out7);
+}
+
+template <int AR>
+__global__ void __launch_bounds__(kThreads)
+replay_amer_kernel(const __grid_constant__ LevelConsts C, const AmerRow* tab, const double* Z, double* partials,
+                   unsigned* ticket, double* out7, double* Pf_out, double* Pc_out) {
+    Sums7 acc;
+    acc.clear();
+    const ull stride = (ull)gridDim.x * blockDim.x;
+    for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
+        AmerState<AR> st;
+        st.init(C, tab);
+        for (ull j = 1; j <= C.nsteps; ++j) {
+            const AmerRow row = load_row(tab, j);
+            st.fine(C, row, Z[(j - 1) * C.n_paths + i]);
+            if ((j & 1) == 0) st.coarse(C, row);
+        }
+        double Pf, Pc;
+        st.payoffs(C, Pf, Pc);
+        acc.add(Pf, Pc, C.is_l0);
+        if (Pf_out) Pf_out[i] = Pf;
+        if (Pc_out) Pc_out[i] = Pc;
+    }
+    grid_finish(acc, partials, ticket, out7);
 }
 
 // ------------------------------------------------------------------------------------------

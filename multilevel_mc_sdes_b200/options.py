@@ -24,7 +24,7 @@ import sys
 import numpy as np
 
 from . import _lib
-from ._lib import GBM, MERTON, EURO, ASIAN, LOOKBACK, DIGITAL
+from ._lib import GBM, MERTON, EURO, ASIAN, LOOKBACK, DIGITAL, AMERICAN
 
 _SAMPLERS = {"f32bm": _lib.SAMPLER_F32BM, "f64bm": _lib.SAMPLER_F64BM}
 
@@ -170,6 +170,7 @@ class Option:
         p.beta = float(getattr(self, "beta", 0.5826))
         p.disc = float(np.exp(-self.r * self.T))                # numpy's value, as the reference :80
         p.J_bar = float(getattr(self, "J_bar", 0.0))
+        p.boundary_c = float(getattr(self, "boundary_c", 0.0))
         return p
 
     def _flags(self):
@@ -410,6 +411,33 @@ class Digital_GBM(GBM_Option):
         D2 = ((np.log(self.X0 / self.K) + (self.r + 0.5 * self.sig ** 2) * self.T) / (self.sig * np.sqrt(self.T))
               - self.sig * np.sqrt(self.T))
         return self.K * np.exp(-self.r * self.T) * _norm_cdf(D2)
+
+
+def sqrt_boundary(c=0.8):
+    """The exercise-boundary family of the demo notebook (ExampleUsages.ipynb cell 1, `exb`):
+    b(self, t) = max(K*(1 - c*sqrt(T - t)), 0).  The returned callable has the reference's
+    `exerciseBoundary(self, t)` signature and carries `c` so Amer_GBM can run it on the GPU."""
+    def boundary(self, t):
+        return np.maximum(self.K * (1 - c * np.sqrt(self.T - t)), 0)
+    boundary.mlmcb_c = float(c)
+    return boundary
+
+
+class Amer_GBM(GBM_Option):
+    """American put under GBM (reference Amer_GBM :1483-1632, Amer_payoff :138-158): barrier-crossing
+    probabilities between grid points, M must be 2 (:1524).  `exerciseBoundary` is `sqrt_boundary(c)`
+    or just the number c; an arbitrary Python callable cannot be evaluated inside the kernel and is
+    rejected (NotImplementedError) rather than silently run on the host."""
+    _payoff_kind = AMERICAN
+
+    def __init__(self, exerciseBoundary=0.8, **kwargs):
+        super().__init__(**kwargs)
+        c = getattr(exerciseBoundary, "mlmcb_c", exerciseBoundary)
+        if callable(c):
+            raise NotImplementedError(
+                "Amer_GBM on the GPU supports the boundary family K*(1-c*sqrt(T-t)): pass sqrt_boundary(c) or c")
+        self.boundary_c = float(c)
+        self.exerciseBoundary = exerciseBoundary if callable(exerciseBoundary) else sqrt_boundary(self.boundary_c)
 
 
 class Euro_Merton(Merton_Option):

@@ -28,10 +28,11 @@ typedef struct {
     double disc;                             /* np.exp(-r*T) as evaluated by the caller :80 */
     double J_bar;                            /* np.exp(jumpmean+0.5*jumpstd**2)-1 :1291     */
     double milstein;                         /* != 0: the notebook's milstein_GBM / milstein_Merton increments */
+    double boundary_c;                       /* American put: exercise boundary K*(1-c*sqrt(T-t)) (notebook exb) */
 } orc_params;
 
 enum { ORC_GBM = 0, ORC_MERTON = 1 };
-enum { ORC_EURO = 0, ORC_ASIAN = 1, ORC_LOOKBACK = 2, ORC_DIGITAL = 3 };
+enum { ORC_EURO = 0, ORC_ASIAN = 1, ORC_LOOKBACK = 2, ORC_DIGITAL = 3, ORC_AMERICAN = 4 };
 
 static int64_t ipow(int M, int l) { int64_t n = 1; for (int i = 0; i < l; ++i) n *= M; return n; }
 
@@ -121,6 +122,51 @@ static void gbm_one(const orc_params *p, int payoff, int l, int M, int64_t nstep
     double cf = 1 - p->beta * sig * sqrt(dt), cc = 1 - p->beta * sig * sqrt(M * dt);   /* :105 :110 */
     *Pf = payoff_of(p, payoff, vf, Mf, cf);
     *Pc = (l == 0) ? vc : payoff_of(p, payoff, vc, Mc, cc);        /* l==0: raw coarse output :82 */
+}
+
+/* ---- one coupled American-put path: Amer_GBM.path :1511-1615 + Amer_payoff :138-158 (M == 2) ---- *
+ * `halfdWc` aliases `dWc` in the reference (:1577 binds the array that :1549 updates in place), so  *
+ * the coarse mid-point uses dWc - 0.5*dWc.                                                          */
+static inline double amer_eb(const orc_params *p, double t) {          /* notebook cell 1: exb */
+    double v = p->K * (1 - p->boundary_c * sqrt(p->T - t));
+    return v > 0 ? v : 0;
+}
+static inline double pos(double v) { return v > 0 ? v : 0; }
+static void amer_one(const orc_params *p, int l, int M, int64_t nsteps, const double *Z, int64_t zstride,
+                     orc_rng *g, double *Pf, double *Pc) {
+    const double T = p->T, X0 = p->X0, mu = p->r + p->drift, sig = p->sig, K = p->K, r = p->r;
+    const double dt = T / (double)nsteps, sqrt_dt = sqrt(dt), sig2 = pow(sig, 2.0);
+    double f0 = X0, f1 = 1.0, f2 = 0.0, c0 = X0, c1 = 1.0, c2 = 0.0, dWc = 0.0;
+    for (int64_t j = 1; j <= nsteps; ++j) {
+        double t_ = (double)(j - 1) * dt;
+        double z = Z ? Z[(j - 1) * zstride] : rng_normal(g);
+        double dWf = sqrt_dt * z;                                                  /* :1548 */
+        dWc += dWf;
+        double Xl = f0, Xr = Xl + gbm_inc(mu, sig, Xl, dt, dWf);                   /* :1554 */
+        double lb = amer_eb(p, t_), tfMid = t_ + dt / 2, rb = amer_eb(p, (double)j * dt), mb = amer_eb(p, tfMid);
+        double P1 = exp(-2 * pos(Xl - lb) * pos(Xr - rb) / (sig2 * dt * (Xl * Xl)));       /* :1566 */
+        f2 += f1 * P1 * pos(K - mb) * exp(-r * tfMid);                             /* :1569 */
+        f1 *= (1.0 - P1);
+        f0 = Xr;
+        if (j % M == 0) {
+            t_ = (double)(j - M) * dt;
+            Xl = c0; Xr = Xl + gbm_inc(mu, sig, Xl, M * dt, dWc);                  /* :1584 */
+            double Xmid = Xl + 0.5 * (Xr - Xl) + sig * Xl * (dWc - 0.5 * dWc);     /* :1585 with the alias */
+            lb = amer_eb(p, t_);
+            double tcMid = t_ + M * dt / 2;
+            rb = amer_eb(p, (double)j * dt);
+            double mb2 = amer_eb(p, tcMid), mb1 = 0.5 * (rb + lb);
+            double P11 = exp(-2 * pos(Xl - lb) * pos(Xmid - mb1) / (dt * sig2 * (Xl * Xl)));     /* :1600 */
+            double P12 = exp(-2 * pos(Xmid - mb1) * pos(Xr - rb) / (dt * sig2 * (Xl * Xl)));     /* :1601 */
+            double Pc1 = (1.0 - (1.0 - P11) * (1.0 - P12));
+            c2 += c1 * Pc1 * pos(K - mb2) * exp(-r * tcMid);                       /* :1605 */
+            c1 *= (1 - Pc1);
+            c0 = Xr;
+            dWc = 0.0;
+        }
+    }
+    *Pf = f2 + f1 * pos(K - f0) * p->disc;                                         /* :153 */
+    *Pc = (l == 0) ? 0.0 : c2 + c1 * pos(K - c0) * p->disc;                        /* :155 / :157 */
 }
 
 /* ---- one antithetic GBM triple: diffusion_anti_path :162-217, _avg :219-290, anti_EA_payoff :292-317 -- *
@@ -235,6 +281,11 @@ int orc_gbm_replay(const orc_params *p, int payoff, int l, int M, int64_t n,
                    double *Pf, double *Pc) {
     int64_t nsteps = ipow(M, l);
     set_scheme(p);
+    if (payoff == ORC_AMERICAN) {
+        if (M != 2) return -1;
+        for (int64_t i = 0; i < n; ++i) amer_one(p, l, M, nsteps, Z + i, n, NULL, Pf + i, Pc + i);
+        return 0;
+    }
     for (int64_t i = 0; i < n; ++i) gbm_one(p, payoff, l, M, nsteps, Z + i, n, NULL, Pf + i, Pc + i);
     return 0;
 }
@@ -277,7 +328,8 @@ static void *orc_worker(void *arg) {
     for (int64_t i = jb->lo; i < jb->hi; ++i) {
         orc_rng g; rng_seed(&g, jb->seed, (uint64_t)i + ((uint64_t)jb->l << 48));
         double Pf, Pc;
-        if (jb->anti) gbm_anti_one(jb->p, jb->payoff, jb->l, jb->M, jb->nsteps, NULL, 0, &g, &Pf, &Pc);
+        if (jb->payoff == ORC_AMERICAN) amer_one(jb->p, jb->l, jb->M, jb->nsteps, NULL, 0, &g, &Pf, &Pc);
+        else if (jb->anti) gbm_anti_one(jb->p, jb->payoff, jb->l, jb->M, jb->nsteps, NULL, 0, &g, &Pf, &Pc);
         else if (jb->model == ORC_GBM) gbm_one(jb->p, jb->payoff, jb->l, jb->M, jb->nsteps, NULL, 0, &g, &Pf, &Pc);
         else {
             jd_src s = { NULL, NULL, NULL, 0, 0, 0, &g, 1.0 / jb->p->lam };

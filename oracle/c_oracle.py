@@ -12,7 +12,7 @@ _SO = os.path.join(_HERE, "libmlmc_oracle.so")
 class OrcParams(C.Structure):
     _fields_ = [(k, C.c_double) for k in
                 ("X0", "K", "T", "r", "sig", "drift", "lam", "jumpmean", "jumpstd", "beta", "disc", "J_bar",
-                 "milstein")]
+                 "milstein", "boundary_c")]
 
 
 def build(force=False):
@@ -52,7 +52,7 @@ def to_params(p):
                      float(getattr(p, "jumpmean", 0.0)), float(getattr(p, "jumpstd", 0.0)),
                      float(getattr(p, "beta", 0.5826)), float(np.exp(-p.r * p.T)),
                      float(np.exp(getattr(p, "jumpmean", 0.0) + 0.5 * getattr(p, "jumpstd", 0.0) ** 2) - 1),
-                     1.0 if getattr(p, "scheme", "em") == "milstein" else 0.0)
+                     1.0 if getattr(p, "scheme", "em") == "milstein" else 0.0, float(getattr(p, "boundary_c", 0.8)))
 
 
 def _dp(a):

@@ -280,6 +280,36 @@ def milstein_cases(ref):
     return out
 
 
+def amer_cases(ref):
+    """Amer_GBM (:1483-1632) with the demo notebook's exercise boundary `exb` (cell 1):
+    np.maximum(self.K*(1-0.8*np.sqrt(self.T-t)),0); c = 0.8 and one other value."""
+    out = {}
+    idx = 0
+    for c in (0.8, 0.5):
+        def exb(self, t, c=c):
+            return np.maximum(self.K * (1 - c * np.sqrt(self.T - t)), 0)
+        for kw_name, kw in (("default", {}), ("alt2", ALT_GBM2)):
+            for l in (0, 1, 2, 3, 4, 6):
+                n = 96 if l <= 4 else 32
+                seed = 9500 + idx
+                opt = ref.Amer_GBM(exerciseBoundary=exb, **kw)
+                np.random.seed(seed)
+                Pf, Pc = opt.payoff(n, l, 2)
+                out[f"c{idx}_meta"] = np.array(["Amer_GBM", kw_name, str(l), "2", str(n), str(seed), repr(c)])
+                out[f"c{idx}_Pf"] = np.asarray(Pf, dtype=np.float64)
+                out[f"c{idx}_Pc"] = np.asarray(Pc, dtype=np.float64) * np.ones(n)
+                idx += 1
+    opt = ref.Amer_GBM(exerciseBoundary=exb)
+    np.random.seed(9600)
+    out["looper_sums"] = opt.looper(700, 3, 2, False, 300)
+    try:
+        opt.looper(10, 2, 4, False)
+    except ValueError as e:
+        out["bad_M_message"] = np.array(str(e))
+    out["n_cases"] = np.array(idx)
+    return out
+
+
 def looper_cases(ref):
     out = {}
     idx = 0
@@ -357,7 +387,7 @@ def main():
     ref = load_reference()
     os.makedirs(OUT, exist_ok=True)
     for name, fn in (("payoffs_gbm", gbm_cases), ("payoffs_merton", merton_cases), ("payoffs_anti", anti_cases),
-                     ("payoffs_milstein", milstein_cases),
+                     ("payoffs_milstein", milstein_cases), ("payoffs_amer", amer_cases),
                      ("looper", looper_cases),
                      ("mlmc_trace", mlmc_traces), ("closed_forms", closed_forms)):
         d = fn(ref)

@@ -21,7 +21,7 @@ Randomness is abstracted behind a *draw source* so the same restatement serves t
 import numpy as np
 
 GBM, MERTON = 0, 1
-EURO, ASIAN, LOOKBACK, DIGITAL = 0, 1, 2, 3
+EURO, ASIAN, LOOKBACK, DIGITAL, AMERICAN = 0, 1, 2, 3, 4
 MODEL_NAMES = {GBM: "GBM", MERTON: "Merton"}
 PAYOFF_NAMES = {EURO: "Euro", ASIAN: "Asian", LOOKBACK: "Lookback", DIGITAL: "Digital"}
 
@@ -31,8 +31,9 @@ class Params:
     GBM_Option :1330-1347, Merton_Option :1273-1296, Lookback beta :1443/:1691)."""
 
     def __init__(self, X0=100, K=100, T=1, r=0.05, sig=0.2, drift=0, lam=1, jumpmean=0.1,
-                 jumpstd=0.2, beta=0.5826, scheme="em"):
+                 jumpstd=0.2, beta=0.5826, scheme="em", boundary_c=0.8):
         self.scheme = scheme                                        # "em" | "milstein" (notebook cell 1)
+        self.boundary_c = boundary_c                                # exercise boundary K*(1-c*sqrt(T-t)) (notebook `exb`)
         self.X0, self.K, self.T, self.r, self.sig, self.drift = X0, K, T, r, sig, drift
         self.lam, self.jumpmean, self.jumpstd, self.beta = lam, jumpmean, jumpstd, beta
         self.mu = r + drift                                         # :1347
@@ -277,6 +278,85 @@ def anti_level_payoffs(p, payoff, l, M, n=None, Z=None):
     return 0.5 * (Pf + Pa), Pc
 
 
+# ----------------------------------------------------------------------------- American put (GBM)
+def exercise_boundary(p, t):
+    """The demo notebook's `exb` (ExampleUsages.ipynb cell 1): max(K*(1-0.8*sqrt(T-t)), 0), with the
+    0.8 exposed as p.boundary_c.  It is the callback `Amer_GBM(exerciseBoundary=...)` is given."""
+    return np.maximum(p.K * (1 - p.boundary_c * np.sqrt(p.T - t)), 0)
+
+
+def amer_paths(p, l, M, Z=None, n=None):
+    """Amer_GBM.path :1511-1615.  Returns (Xf, Xc), each (n,3): price, probability of not having
+    crossed, accumulated exercise value.  Keeps the reference's aliasing at :1577: `halfdWc=dWc`
+    binds the SAME array that `dWc += dWf` (:1549) then updates in place, so at the coarse step
+    halfdWc is dWc (and `halfdWc - 0.5*dWc` is 0.5*dWc)."""
+    if M != 2:
+        raise ValueError("M must be equal to 2 for American Option pricer. Please use M=2.")     # :1525
+    T, X0, sig, K, r = p.T, p.X0, p.sig, p.K, p.r
+    eb = lambda t: exercise_boundary(p, t)
+    Nsteps = M ** l
+    dt = T / Nsteps
+    sqrt_dt = np.sqrt(dt)
+    if Z is not None:
+        n = Z.shape[1]
+    dWc = np.zeros(n)
+    Xf = np.zeros((n, 3))
+    Xf[:, 0] = X0 * np.ones(n)
+    Xf[:, 1] = np.ones(n)
+    Xf[:, 2] = np.zeros(n)
+    Xc = Xf.copy()
+    halfdWc = dWc
+    for j in range(1, Nsteps + 1):
+        t_ = (j - 1) * dt
+        z = Z[j - 1] if Z is not None else np.random.randn(n)
+        dWf = sqrt_dt * z                                           # :1548
+        dWc += dWf                                                  # :1549 (in place)
+        Xleft = Xf[:, 0]
+        Xright = Xleft + gbm_increment(p, Xleft, dt, dWf)           # :1554
+        leftBarrier = eb(t_)
+        tfMid = t_ + dt / 2
+        rightBarrier = eb(j * dt)
+        midBarrier = eb(tfMid)
+        Prob1 = np.exp(-2 * np.maximum(Xleft - leftBarrier, 0) * np.maximum(Xright - rightBarrier, 0)
+                       / ((sig ** 2) * dt * Xleft ** 2))             # :1566
+        Xf[:, 2] += Xf[:, 1] * Prob1 * np.maximum(K - midBarrier, 0) * np.exp(-r * (tfMid))    # :1569
+        Xf[:, 1] *= (1.0 - Prob1)                                   # :1571
+        Xf[:, 0] = Xright                                           # :1573
+        if j % M == M / 2:
+            halfdWc = dWc                                           # :1577 (alias, see docstring)
+        if j % M == 0:
+            t_ = (j - M) * dt
+            Xleft = Xc[:, 0]
+            Xright = Xleft + gbm_increment(p, Xleft, M * dt, dWc)   # :1584
+            Xmid = Xleft + 0.5 * (Xright - Xleft) + sig * Xleft * (halfdWc - 0.5 * dWc)     # :1585
+            leftBarrier = eb(t_)
+            tcMid = t_ + M * dt / 2
+            rightBarrier = eb(j * dt)
+            midBarrier2 = eb(tcMid)
+            midBarrier1 = 0.5 * (rightBarrier + leftBarrier)
+            Prob11 = np.exp(-2 * np.maximum(Xleft - leftBarrier, 0) * np.maximum(Xmid - midBarrier1, 0)
+                            / (dt * (sig ** 2) * (Xleft ** 2)))     # :1600
+            Prob12 = np.exp(-2 * np.maximum(Xmid - midBarrier1, 0) * np.maximum(Xright - rightBarrier, 0)
+                            / (dt * (sig ** 2) * (Xleft ** 2)))     # :1601
+            Prob1 = (1.0 - (1.0 - Prob11) * (1.0 - Prob12))         # :1603
+            Xc[:, 2] += Xc[:, 1] * Prob1 * np.maximum(K - midBarrier2, 0) * np.exp(-r * tcMid)   # :1605
+            Xc[:, 1] *= (1 - Prob1)                                 # :1607
+            Xc[:, 0] = Xright
+            dWc = np.zeros(n)                                       # :1612
+    return Xf, Xc
+
+
+def amer_level_payoffs(p, l, M, n=None, Z=None):
+    """Amer_payoff :138-158 over Amer_GBM.path; at l==0 the second item is 0 (:155)."""
+    K, T, r = p.K, p.T, p.r
+    Xf, Xc = amer_paths(p, l, M, Z=Z, n=n)
+    Pf = Xf[:, 2] + Xf[:, 1] * np.maximum(K - Xf[:, 0], 0) * np.exp(-r * T)
+    if l == 0:
+        return Pf, 0
+    Pc = Xc[:, 2] + Xc[:, 1] * np.maximum(K - Xc[:, 0], 0) * np.exp(-r * T)
+    return Pf, Pc
+
+
 # ----------------------------------------------------------------------------- Merton coupled paths
 def merton_paths(p, functional, l, M, n, draws=None):
     """JD_path :428-492 / JD_path_avg :494-571 / JD_path_min :573-651 (jump-adapted EM).
@@ -412,7 +492,9 @@ def apply_payoff(p, payoff, l, M, path_out):
 
 
 def level_payoffs(p, model, payoff, l, M, n=None, Z=None, draws=None):
-    """`Option.payoff(N_loop,l,M)` for one of the 8 products -> (Pf, Pc)."""
+    """`Option.payoff(N_loop,l,M)` for one of the 8 products (+ American put) -> (Pf, Pc)."""
+    if payoff == AMERICAN:
+        return amer_level_payoffs(p, l, M, n=n, Z=Z)
     fn = functional_of(payoff)
     if model == GBM:
         out = gbm_paths(p, fn, l, M, Z=Z, n=n)
@@ -426,7 +508,7 @@ def seven_sums(Pf, Pc, l):
     """One chunk of Option.looper :946-955."""
     sumPf = np.sum(Pf)
     sumPf2 = np.sum(Pf ** 2)
-    if l == 0:
+    if l == 0:                       # Pc is ignored here (an array of X0, or the scalar 0 of Amer_payoff)
         return np.array([sumPf, sumPf2, sumPf, sumPf2, 0, 0, 0])
     dP = Pf - Pc
     return np.array([np.sum(dP), np.sum(dP ** 2), sumPf, sumPf2,

@@ -82,3 +82,10 @@ def milstein_merton_cases(g):
                       E=g[f"m{i}_zE"], offE=g[f"m{i}_offE"])
         yield dict(idx=i, cname=cname, kw_name=kw_name, l=int(l), M=int(M), n=int(n), seed=int(seed),
                    Pf=g[f"m{i}_Pf"], Pc=g[f"m{i}_Pc"], packed=packed)
+
+
+def amer_cases(g):
+    for i in range(int(g["n_cases"])):
+        cname, kw_name, l, M, n, seed, c = [str(x) for x in g[f"c{i}_meta"]]
+        yield dict(idx=i, cname=cname, kw_name=kw_name, l=int(l), M=int(M), n=int(n), seed=int(seed), c=float(c),
+                   Pf=g[f"c{i}_Pf"], Pc=g[f"c{i}_Pc"], Z=None)

@@ -243,3 +243,27 @@ def test_f64bm_stream_matches_float64_recomputation(cuda_lib):
             got = (z[2 * call, p], z[2 * call + 1, p])
             worst = max(worst, abs(got[0] - want[0]), abs(got[1] - want[1]))
     assert worst < 1e-14, worst
+
+
+def test_american_put_level_moments_and_price(cuda_lib, c_oracle):
+    n_gpu, n_cpu = 4_000_000, 300_000
+    for l in (0, 1, 3, 5):
+        ref = c_oracle.level_sums(O.Params(), O.GBM, O.AMERICAN, l, 2, n_cpu, seed=40 + l, nthreads=8)
+        for sampler in ("f32bm", "f64bm"):
+            s = mm.Amer_GBM(seed=8, sampler=sampler).looper(n_gpu, l, 2, False)
+            m_d, v_d, m_f, v_f = _moments(s, n_gpu, l)
+            rm_d, rv_d, rm_f, rv_f = _moments(ref, n_cpu, l)
+            se = lambda v: np.sqrt(v / n_gpu + v / n_cpu)
+            assert abs(m_d - rm_d) < 4 * se(max(v_d, rv_d)) + 1e-15, (l, sampler)
+            assert abs(m_f - rm_f) < 4 * se(max(v_f, rv_f)), (l, sampler)
+            if l > 0:
+                assert abs(v_d - rv_d) < 4 * rv_d * np.sqrt(300 / n_cpu)
+    # the early-exercise premium: American put above the European put (BS put = call - S + K e^{-rT} = 5.5735)
+    opt = mm.Amer_GBM(verbose=False, alpha_0=1, beta_0=1)
+    sums, N = opt.mlmc(0.01, M=2)
+    price = float(np.sum(sums[0] / N))
+    assert 5.6 < price < 6.2, price          # reference boundary c=0.8 is sub-optimal; true value 6.09
+    with pytest.raises(ValueError, match="M must be equal to 2"):
+        opt.looper(100, 2, 4, False)
+    with pytest.raises(NotImplementedError):
+        mm.Amer_GBM(scheme="milstein").looper(100, 2, 2, False)

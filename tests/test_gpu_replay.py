@@ -8,7 +8,7 @@ import pytest
 
 import multilevel_mc_sdes_b200 as mm
 from oracle import np_oracle as O
-from tests.helpers import milstein_gbm_cases, milstein_merton_cases
+from tests.helpers import amer_cases, milstein_gbm_cases, milstein_merton_cases
 from tests.helpers import CLASS_CODES, anti_cases, case_kwargs, gbm_cases, merton_cases, oracle_params, payoff_tol, regen_Z
 
 pytestmark = pytest.mark.gpu
@@ -174,3 +174,26 @@ def test_milstein_replay(golden, cuda_lib):
                 assert np.all(np.abs(Pc - c["Pc"]) <= payoff_tol(p, c["Pc"])), (c["idx"], arith)
         n += 1
     assert n > 100
+
+
+def test_american_put_replay(golden, cuda_lib, c_oracle):
+    """Amer_GBM: both arithmetic policies within 1e-12*max(|P|, K e^{-rT}) of the reference (the
+    per-step exp() makes bit-exactness impossible across libms); l = 9 against the C restatement."""
+    n = 0
+    for c in amer_cases(golden["payoffs_amer"]):
+        kw = case_kwargs("Euro_GBM", c["kw_name"])
+        p = O.Params(boundary_c=c["c"], **kw)
+        opt = mm.Amer_GBM(exerciseBoundary=c["c"], **kw)
+        Z = regen_Z(c)
+        for arith in ("exact", "fast"):
+            Pf, Pc = opt.payoff_replay(Z, c["l"], 2, arith=arith)
+            assert np.all(np.abs(Pf - c["Pf"]) <= payoff_tol(p, c["Pf"])), (c["idx"], arith, np.abs(Pf - c["Pf"]).max())
+            assert np.all(np.abs(Pc - c["Pc"]) <= payoff_tol(p, c["Pc"])), (c["idx"], arith, np.abs(Pc - c["Pc"]).max())
+        n += 1
+    assert n >= 24
+    Z = np.random.RandomState(5).randn(2 ** 9, 80)
+    rf, rc = c_oracle.gbm_replay(O.Params(), O.AMERICAN, 9, 2, Z)
+    Pf, Pc = mm.Amer_GBM().payoff_replay(Z, 9, 2, arith="exact")
+    assert np.all(np.abs(Pf - rf) <= payoff_tol(O.Params(), rf)) and np.all(np.abs(Pc - rc) <= payoff_tol(O.Params(), rc))
+    with pytest.raises(ValueError, match="M must be equal to 2"):
+        mm.Amer_GBM().payoff_replay(np.zeros((16, 4)), 2, 4)

@@ -149,6 +149,15 @@ def test_option_surface_and_errors():
     assert np.array_equal(o.sde(x, 0.01, 0.0, np.array([0.1, -0.1])), o.mu * x * 0.01 + o.sig * x * np.array([0.1, -0.1]))
 
 
+def test_amer_gbm_surface():
+    a = mm.Amer_GBM(exerciseBoundary=mm.sqrt_boundary(0.7), K=95)
+    assert a.boundary_c == 0.7 and a._params().boundary_c == 0.7
+    assert a.exerciseBoundary(a, 0.5) == max(95 * (1 - 0.7 * np.sqrt(0.5)), 0)
+    assert mm.Amer_GBM().boundary_c == 0.8 and mm.Amer_GBM(0.6).boundary_c == 0.6
+    with pytest.raises(NotImplementedError):
+        mm.Amer_GBM(exerciseBoundary=lambda self, t: 90.0)       # arbitrary callbacks cannot enter the kernel
+
+
 def test_path_ids_advance_per_level(monkeypatch):
     """Every looper call must consume fresh path ids."""
     seen, flags_seen = [], []

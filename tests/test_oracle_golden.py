@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import np_oracle as O
+from tests.helpers import amer_cases, case_kwargs
 from tests.helpers import (CLASS_CODES, anti_cases, gbm_cases, merton_cases, milstein_gbm_cases,
                            milstein_merton_cases, oracle_params, regen_Z)
 
@@ -145,3 +146,24 @@ def test_oracles_milstein(golden, c_oracle):
         np.testing.assert_allclose(Pc, c["Pc"], rtol=0, atol=2e-13 * p.X0)
         n += 1
     assert n > 100
+
+
+def test_oracles_american_put(golden, c_oracle):
+    """Amer_GBM.path :1511-1615 + Amer_payoff :138-158 with the notebook's exercise boundary."""
+    g = golden["payoffs_amer"]
+    n = 0
+    for c in amer_cases(g):
+        p = O.Params(boundary_c=c["c"], **case_kwargs("Euro_GBM", c["kw_name"]))
+        Z = regen_Z(c)
+        Pf, Pc = O.level_payoffs(p, O.GBM, O.AMERICAN, c["l"], 2, Z=Z.copy())
+        assert np.array_equal(Pf, c["Pf"]) and np.array_equal(np.asarray(Pc) * np.ones(c["n"]), c["Pc"])
+        Pf, Pc = c_oracle.gbm_replay(p, O.AMERICAN, c["l"], 2, Z)          # libm exp vs numpy exp: last-bit
+        np.testing.assert_allclose(Pf, c["Pf"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(Pc, c["Pc"], rtol=0, atol=1e-12)
+        n += 1
+    assert n >= 24
+    np.random.seed(9600)
+    assert np.array_equal(O.looper(O.Params(boundary_c=0.5), O.GBM, O.AMERICAN, 700, 3, 2, Npl=300), g["looper_sums"])
+    with pytest.raises(ValueError, match="M must be equal to 2"):
+        O.level_payoffs(O.Params(), O.GBM, O.AMERICAN, 2, 4, n=4)
+    assert "M must be equal to 2" in str(g["bad_M_message"])
