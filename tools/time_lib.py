@@ -23,9 +23,9 @@ ap.add_argument("--batch", type=float, default=float(1 << 25))
 ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 lib = _lib.load()
-cls = {(0, 0): mm.Euro_GBM, (0, 1): mm.Asian_GBM, (0, 2): mm.Lookback_GBM, (0, 3): mm.Digital_GBM,
+cls = {(0, 4): mm.Amer_GBM, (0, 0): mm.Euro_GBM, (0, 1): mm.Asian_GBM, (0, 2): mm.Lookback_GBM, (0, 3): mm.Digital_GBM,
        (1, 0): mm.Euro_Merton, (1, 1): mm.Asian_Merton, (1, 2): mm.Lookback_Merton, (1, 3): mm.Digital_Merton}[(a.model, a.payoff)]
-opt = cls(X0=125, K=105, r=0.02, sig=0.5) if a.model == 0 else cls()
+opt = cls(X0=125, K=105, r=0.02, sig=0.5) if (a.model == 0 and a.payoff != 4) else cls()
 p = opt._params()
 out = torch.zeros(7, dtype=torch.float64, device="cuda")
 n = int(a.batch)
