@@ -79,6 +79,16 @@ int mlmcb_level_sums(const mlmcb_params* p, int model, int payoff, int l, int M,
                      int device, void* cuda_stream,
                      double* d_out7, double* d_Pf, double* d_Pc);
 
+/* The path functions themselves (Option.path / anti_path :320-651, :162-290, :1511-1615): same
+ * simulation, and additionally the per-path quantities the reference path function returns, as rows
+ * of d_raw[rows][n_paths]:  plain products 4 rows (fine value, fine minimum, coarse value, coarse
+ * minimum; value = terminal price or average; minima only for lookbacks), MLMCB_ANTITHETIC 3 rows
+ * (fine, antithetic, coarse), MLMCB_AMERICAN 6 rows (Xf[:,0..2], Xc[:,0..2]).  mlmcb_path_rows tells. */
+int mlmcb_path_rows(int payoff, int flags);
+int mlmcb_level_paths(const mlmcb_params* p, int model, int payoff, int l, int M,
+                      uint64_t n_paths, uint64_t seed, uint64_t path_offset, int flags,
+                      int device, void* cuda_stream, double* d_out7, double* d_raw);
+
 /* Same, result delivered to HOST memory (h_out7[7]); launch + 56-byte D2H + stream sync.
  * This is the call `Option.looper` makes. */
 int mlmcb_level_sums_host(const mlmcb_params* p, int model, int payoff, int l, int M,

@@ -35,6 +35,9 @@ _vp = C.c_void_p
 SIGNATURES = {
     "mlmcb_level_sums": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, _u64, _u64, _u64,
                                    C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "mlmcb_path_rows": (C.c_int, [C.c_int, C.c_int]),
+    "mlmcb_level_paths": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, _u64, _u64, _u64,
+                                    C.c_int, C.c_int, _vp, _vp, _vp]),
     "mlmcb_level_sums_host": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, _u64, _u64, _u64,
                                         C.c_int, C.c_int, _vp, _dp]),
     "mlmcb_level_sweep_host": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int,

@@ -279,11 +279,12 @@ int amer_level_sums(const LevelConsts& C, int flags, int device, cudaStream_t st
 
 int level_sums_impl(const mlmcb_params* p, int model, int payoff, int l, int M, ull n_paths, ull seed,
                     ull path_offset, int flags, int device, cudaStream_t st, double* d_out7, double* d_Pf,
-                    double* d_Pc) {
+                    double* d_Pc, double* d_raw = nullptr) {
     if (!d_out7) return fail(MLMCB_EINVAL, "d_out7 is NULL");
     if (int rc = check_flags(flags)) return rc;
     LevelConsts C;
     if (int rc = make_consts(p, model, payoff, l, M, n_paths, seed, path_offset, &C)) return rc;
+    C.raw = d_raw;
     if (flags & MLMCB_ANTITHETIC) {
         if (int rc = check_anti(model, payoff, M)) return rc;
     }
@@ -354,6 +355,21 @@ int mlmcb_level_sums(const mlmcb_params* p, int model, int payoff, int l, int M,
     if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
     return level_sums_impl(p, model, payoff, l, M, n_paths, seed, path_offset, flags, device,
                            (cudaStream_t)cuda_stream, d_out7, d_Pf, d_Pc);
+}
+
+int mlmcb_path_rows(int payoff, int flags) {
+    if (payoff == MLMCB_AMERICAN) return 6;
+    return (flags & MLMCB_ANTITHETIC) ? 3 : 4;
+}
+
+int mlmcb_level_paths(const mlmcb_params* p, int model, int payoff, int l, int M, uint64_t n_paths,
+                      uint64_t seed, uint64_t path_offset, int flags, int device, void* cuda_stream,
+                      double* d_out7, double* d_raw) {
+    if (!d_raw) return fail(MLMCB_EINVAL, "d_raw is NULL");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    return level_sums_impl(p, model, payoff, l, M, n_paths, seed, path_offset, flags, device,
+                           (cudaStream_t)cuda_stream, d_out7, nullptr, nullptr, d_raw);
 }
 
 int mlmcb_level_sums_host(const mlmcb_params* p, int model, int payoff, int l, int M, uint64_t n_paths,

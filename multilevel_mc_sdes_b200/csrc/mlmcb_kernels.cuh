@@ -71,6 +71,7 @@ struct LevelConsts {
     // Merton
     double lam, inv_lam, jm, js;
     double inv_blk_dt;              // 1/(4*dt): jump time -> block index
+    double* raw;                    // optional [rows][n_paths] path-function outputs (Option.path), else NULL
     double r, boundary_c, amer_cneg;  // American put: rate, boundary constant, -2/(sig^2 dt); discounting inside the path, exercise boundary constant
     // Milstein scheme (ExampleUsages.ipynb cell 1: + 0.5*X*sig**2*(dW**2-dt))
     double sig2, half_sig2, a_fm, a_cm, c_mil;
@@ -703,6 +704,7 @@ __device__ __forceinline__ void emit_anti(const LevelConsts& C, ull i, double vf
     acc.add(Pf, Pc, C.is_l0);
     if (Pf_out) Pf_out[i] = Pf;
     if (Pc_out) Pc_out[i] = Pc;
+    if (C.raw) { C.raw[i] = vf; C.raw[C.n_paths + i] = va; C.raw[2 * C.n_paths + i] = vc; }   // anti_path :217/:290
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1114,6 +1116,11 @@ amer_level_kernel(const __grid_constant__ LevelConsts C, const AmerRow* tab, dou
         }
         double Pf, Pc;
         st.payoffs(C, Pf, Pc);
+        if (C.raw) {      // Amer_GBM.path returns Xf[:,0..2], Xc[:,0..2] (:1615)
+            const ull n = C.n_paths;
+            C.raw[i] = st.f0; C.raw[n + i] = st.f1; C.raw[2 * n + i] = st.f2;
+            C.raw[3 * n + i] = st.c0; C.raw[4 * n + i] = st.c1; C.raw[5 * n + i] = st.c2;
+        }
         acc.add(Pf, Pc, C.is_l0);
         if (Pf_out) Pf_out[i] = Pf;
         if (Pc_out) Pc_out[i] = Pc;
@@ -1138,6 +1145,11 @@ replay_amer_kernel(const __grid_constant__ LevelConsts C, const AmerRow* tab, co
         }
         double Pf, Pc;
         st.payoffs(C, Pf, Pc);
+        if (C.raw) {      // Amer_GBM.path returns Xf[:,0..2], Xc[:,0..2] (:1615)
+            const ull n = C.n_paths;
+            C.raw[i] = st.f0; C.raw[n + i] = st.f1; C.raw[2 * n + i] = st.f2;
+            C.raw[3 * n + i] = st.c0; C.raw[4 * n + i] = st.c1; C.raw[5 * n + i] = st.c2;
+        }
         acc.add(Pf, Pc, C.is_l0);
         if (Pf_out) Pf_out[i] = Pf;
         if (Pc_out) Pc_out[i] = Pc;
@@ -1155,6 +1167,9 @@ __device__ __forceinline__ void emit(const LevelConsts& C, ull i, double vf, dou
     acc.add(Pf, Pc, C.is_l0);
     if (Pf_out) Pf_out[i] = Pf;
     if (Pc_out) Pc_out[i] = Pc;
+    if (C.raw) {      // what the reference path function returns: (Xf,Xc) | (Af/T,Ac/T) | (Xf,Mf,Xc,Mc)
+        C.raw[i] = vf; C.raw[C.n_paths + i] = gf; C.raw[2 * C.n_paths + i] = vc; C.raw[3 * C.n_paths + i] = gc;
+    }
 }
 
 template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH>

@@ -137,10 +137,39 @@ class Option:
         return self._payoff_arrays(N_loop, l, M, _lib.ANTITHETIC)
 
     def path(self, N_loop, l, M):
-        raise NotImplementedError("Option instance has no implemented path method")
+        """What the bound reference path function returns for N_loop fresh coupled paths:
+        (Xf,Xc) final values :349, (Af/T,Ac/T) :386 for Asian, (Xf,Mf,Xc,Mc) :426 for lookbacks,
+        (Xf,Xc) each (N,3) for the American put :1615."""
+        if self._model is None or self._payoff_kind is None:
+            raise NotImplementedError("Option instance has no implemented path method")        # :859
+        raw = self._raw_paths(N_loop, l, M, 0)
+        if self._payoff_kind == AMERICAN:
+            return raw[0:3].T.copy(), raw[3:6].T.copy()
+        if self._payoff_kind == LOOKBACK:
+            return raw[0], raw[1], raw[2], raw[3]
+        return raw[0], raw[2]
 
     def anti_path(self, N_loop, l, M):
-        raise NotImplementedError("Option instance has no implemented anti_path method")
+        """(Xf,Xa,Xc) :217 or (Af/T,Aa/T,Ac/T) :290; at l==0 the antithetic item equals the fine one."""
+        if not self._has_anti:
+            raise NotImplementedError("Option instance has no implemented anti_path method")    # :874
+        raw = self._raw_paths(N_loop, l, M, _lib.ANTITHETIC)
+        return raw[0], raw[1], raw[2]
+
+    def _raw_paths(self, N_loop, l, M, extra_flags):
+        import torch
+        n = int(N_loop)
+        start = self._take_ids(l, n)
+        flags = self._flags() | extra_flags
+        rows = _lib.load().mlmcb_path_rows(self._payoff_kind, flags)
+        dev = torch.device("cuda", self.device)
+        raw = torch.empty((rows, n), dtype=torch.float64, device=dev)
+        out7 = torch.empty(7, dtype=torch.float64, device=dev)
+        p = self._params()
+        _lib.check(_lib.load().mlmcb_level_paths(
+            C.byref(p), self._model, self._payoff_kind, int(l), int(M), n, self.seed, start, flags,
+            self.device, _stream_handle(self.device), out7.data_ptr(), raw.data_ptr()))
+        return raw.cpu().numpy()
 
     def sde(self, X, dt, t_, dW, dJ=0):
         raise NotImplementedError("Option instance has no implemented sde method")

@@ -267,3 +267,28 @@ def test_american_put_level_moments_and_price(cuda_lib, c_oracle):
         opt.looper(100, 2, 4, False)
     with pytest.raises(NotImplementedError):
         mm.Amer_GBM(scheme="milstein").looper(100, 2, 2, False)
+
+
+def test_path_functions_return_reference_shapes(cuda_lib):
+    """Option.path / anti_path: the per-path quantities behind the payoffs (same ids -> same paths)."""
+    disc = np.exp(-0.05)
+    o = mm.Euro_GBM(seed=4)
+    Xf, Xc = o.path(5000, 3, 4)
+    o2 = mm.Euro_GBM(seed=4)
+    Pf, Pc = o2.payoff(5000, 3, 4)
+    assert np.array_equal(Pf, disc * np.maximum(0, Xf - 100)) and np.array_equal(Pc, disc * np.maximum(0, Xc - 100))
+    Xf, Mf, Xc, Mc = mm.Lookback_GBM(seed=4).path(5000, 3, 4)
+    assert np.all(Mf <= Xf) and np.all(Mc <= Xc) and np.all(Mf <= 100) and Xf.shape == (5000,)
+    Af, Ac = mm.Asian_Merton(seed=4).path(2000, 2, 2)
+    assert Af.shape == (2000,) and np.all(Af > 0) and np.all(Ac > 0)
+    Xf, Xa, Xc = mm.Euro_GBM(seed=4).anti_path(3000, 3, 4)
+    assert not np.array_equal(Xf, Xa) and abs(np.mean(Xf) - np.mean(Xa)) < 1.0
+    Xf, Xa, Xc = mm.Asian_GBM(seed=4).anti_path(3000, 0, 4)
+    assert np.array_equal(Xf, Xa)                                     # l==0: "just ignore Xa=Xf" (:215)
+    F, Cc = mm.Amer_GBM(seed=4).path(4000, 4, 2)
+    assert F.shape == (4000, 3) and Cc.shape == (4000, 3)
+    assert np.all((F[:, 1] >= 0) & (F[:, 1] <= 1)) and np.all(F[:, 2] >= 0)
+    with pytest.raises(NotImplementedError):
+        mm.Option().path(10, 1, 2)
+    with pytest.raises(NotImplementedError):
+        mm.Digital_Merton().anti_path(10, 1, 2)
