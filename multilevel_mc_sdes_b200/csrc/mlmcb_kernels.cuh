@@ -885,6 +885,55 @@ struct MjdWalker {
     }
 };
 
+// One jump-free 4-step block of the Merton path (= a GBM block with drift r - lam*J_bar).
+// G accumulates the trapezoid integral (FN_AVG) or the running minimum (FN_MIN).
+template <typename R, int FN, int MT, int SCH>
+__device__ __forceinline__ void mjd_fast_block(const LevelConsts& C, const StepCoef<R, SCH>& co, const R z[4],
+                                               R& Xf, R& Xc, R& Gf, R& Gc) {
+    if (FN == FN_AVG) {
+        R acc = (R)0.5 * Xf, accc = (R)0.5 * Xc, sz = (R)0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            R t_ = co.t(z[k]);
+            Xf = fma_<R>(Xf, t_, Xf);
+            sz += z[k];
+            acc += (k == 3) ? (R)0.5 * Xf : Xf;
+            if ((MT == 4 && k == 3) || (MT == 2 && (k & 1))) {
+                R tc_ = co.tc(sz);
+                Xc = fma_<R>(Xc, tc_, Xc);
+                sz = (R)0;
+                if (MT == 4) accc = fma_<R>((R)0.5, Xc, accc);
+                else accc += (k == 3) ? (R)0.5 * Xc : Xc;
+            }
+        }
+        Gf = fma_<R>((R)C.dt, acc, Gf);
+        Gc = fma_<R>((R)C.Mdt, accc, Gc);
+    } else if (MT == 4) {
+        const R s4 = (z[0] + z[1]) + (z[2] + z[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            R t_ = co.t(z[k]);
+            Xf = fma_<R>(Xf, t_, Xf);
+            if (FN == FN_MIN) Gf = min_<R>(Gf, Xf);
+        }
+        R tc_ = co.tc(s4);
+        Xc = fma_<R>(Xc, tc_, Xc);
+        if (FN == FN_MIN) Gc = min_<R>(Gc, Xc);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k += 2) {
+            R t0 = co.t(z[k]), t1 = co.t(z[k + 1]);
+            Xf = fma_<R>(Xf, t0, Xf);
+            if (FN == FN_MIN) Gf = min_<R>(Gf, Xf);
+            Xf = fma_<R>(Xf, t1, Xf);
+            if (FN == FN_MIN) Gf = min_<R>(Gf, Xf);
+            R tc_ = co.tc(z[k] + z[k + 1]);
+            Xc = fma_<R>(Xc, tc_, Xc);
+            if (FN == FN_MIN) Gc = min_<R>(Gc, Xc);
+        }
+    }
+}
+
 template <typename R, int FN, int MT, int SAMP, int SCH>
 __device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid,
                                                 double& vf, double& vc, double& gf, double& gc) {
@@ -894,64 +943,37 @@ __device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid,
     const StepCoef<R, SCH> co(C);
     const uint32_t nfull = (uint32_t)(C.nsteps >> 2);
     // jb = first block that may hold this path's next jump.  The block loop stays uniform across
-    // the warp (all lanes at the same b): lanes with b < jb take the GBM-like block, the others
-    // the jump-adapted one, and the warp reconverges at the end of every block.
+    // the warp (all lanes at the same b).  The lanes agree (one REDUX) on how many blocks ahead are
+    // jump-free for every one of them and run those in a tight loop identical to the GBM one; the
+    // block where some lane jumps is executed once with both paths (divergent), then they agree again.
     uint32_t jb = MT != 0 ? w.jump_block(nfull) : 0;
     R Xf = w.st.Sf, Xc = w.st.Sc, Gf = w.st.Gf, Gc = w.st.Gc;
-    for (uint32_t b = 0; b < nfull; ++b) {
-        R z[4];
-        src.load4(b, z);
-        if (b < jb) {
-            if (FN == FN_AVG) {
-                R acc = (R)0.5 * Xf, accc = (R)0.5 * Xc, sz = (R)0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    R t_ = co.t(z[k]);
-                    Xf = fma_<R>(Xf, t_, Xf);
-                    sz += z[k];
-                    acc += (k == 3) ? (R)0.5 * Xf : Xf;
-                    if ((MT == 4 && k == 3) || (MT == 2 && (k & 1))) {
-                        R tc_ = co.tc(sz);
-                        Xc = fma_<R>(Xc, tc_, Xc);
-                        sz = (R)0;
-                        if (MT == 4) accc = fma_<R>((R)0.5, Xc, accc);
-                        else accc += (k == 3) ? (R)0.5 * Xc : Xc;
-                    }
-                }
-                Gf = fma_<R>((R)C.dt, acc, Gf);
-                Gc = fma_<R>((R)C.Mdt, accc, Gc);
-            } else if (MT == 4) {
-                const R s4 = (z[0] + z[1]) + (z[2] + z[3]);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    R t_ = co.t(z[k]);
-                    Xf = fma_<R>(Xf, t_, Xf);
-                    if (FN == FN_MIN) Gf = min_<R>(Gf, Xf);
-                }
-                R tc_ = co.tc(s4);
-                Xc = fma_<R>(Xc, tc_, Xc);
-                if (FN == FN_MIN) Gc = min_<R>(Gc, Xc);
+    uint32_t b = 0;
+    while (b < nfull) {
+        const unsigned lanes = __activemask();
+        const uint32_t run = __reduce_min_sync(lanes, jb > b ? jb - b : 0u);
+        const uint32_t stop = b + run;
+#pragma unroll 1
+        for (; b < stop; ++b) {
+            R z[4];
+            src.load4(b, z);
+            mjd_fast_block<R, FN, MT, SCH>(C, co, z, Xf, Xc, Gf, Gc);
+        }
+        if (b < nfull) {
+            R z[4];
+            src.load4(b, z);
+            if (b < jb) {
+                mjd_fast_block<R, FN, MT, SCH>(C, co, z, Xf, Xc, Gf, Gc);
             } else {
-#pragma unroll
-                for (int k = 0; k < 4; k += 2) {
-                    R t0 = co.t(z[k]), t1 = co.t(z[k + 1]);
-                    Xf = fma_<R>(Xf, t0, Xf);
-                    if (FN == FN_MIN) Gf = min_<R>(Gf, Xf);
-                    Xf = fma_<R>(Xf, t1, Xf);
-                    if (FN == FN_MIN) Gf = min_<R>(Gf, Xf);
-                    R tc_ = co.tc(z[k] + z[k + 1]);
-                    Xc = fma_<R>(Xc, tc_, Xc);
-                    if (FN == FN_MIN) Gc = min_<R>(Gc, Xc);
-                }
+                // the block that holds a jump (or every block when M is generic): state is clean at
+                // the block start, so the walker restarts its clocks there
+                w.st.Sf = Xf; w.st.Sc = Xc; w.st.Gf = Gf; w.st.Gc = Gc;
+                if (MT != 0) w.st.tf = w.st.tc = (double)(4ull * b) * C.dt;
+                w.slow_block(4ull * b, 4, z[0], z[1], z[2], z[3]);
+                Xf = w.st.Sf; Xc = w.st.Sc; Gf = w.st.Gf; Gc = w.st.Gc;
+                if (MT != 0) jb = w.jump_block(nfull);
             }
-        } else {
-            // the block that holds a jump (or every block when M is generic): state is clean at
-            // the block start, so the walker restarts its clocks there
-            w.st.Sf = Xf; w.st.Sc = Xc; w.st.Gf = Gf; w.st.Gc = Gc;
-            if (MT != 0) w.st.tf = w.st.tc = (double)(4ull * b) * C.dt;
-            w.slow_block(4ull * b, 4, z[0], z[1], z[2], z[3]);
-            Xf = w.st.Sf; Xc = w.st.Sc; Gf = w.st.Gf; Gc = w.st.Gc;
-            if (MT != 0) jb = w.jump_block(nfull);
+            ++b;
         }
     }
     w.st.Sf = Xf; w.st.Sc = Xc; w.st.Gf = Gf; w.st.Gc = Gc;
