@@ -81,7 +81,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    per_core = 10000                     # one step = one reference-sized chunk (Npl=1e4, :919) per core, ~1 s
+    per_core = int(os.environ.get("MLMCB_BENCH_REF_PATHS", 10000))   # one step = one reference-sized chunk (Npl=1e4, :919) per core, ~1 s
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
