@@ -1039,14 +1039,25 @@ struct AmerState {
         lbF = lbC = __ldg(&tab[0].bR);
     }
     // probability of touching the barrier inside a step (Brownian-bridge formula) :1566 / :1600
-    __device__ __forceinline__ static double touch(const LevelConsts& C, double A, double B, double Xl) {
-        if (AR == AR_EXACT)
-            return exp(__ddiv_rn(__dmul_rn(__dmul_rn(-2.0, A), B), __dmul_rn(__dmul_rn(C.sig2, C.dt), __dmul_rn(Xl, Xl))));
-        return exp((C.amer_cneg * A) * B / (Xl * Xl));
+    __device__ __forceinline__ static double touch_exact(const LevelConsts& C, double A, double B, double Xl) {
+        return exp(__ddiv_rn(__dmul_rn(__dmul_rn(-2.0, A), B), __dmul_rn(__dmul_rn(C.sig2, C.dt), __dmul_rn(Xl, Xl))));
     }
-    __device__ __forceinline__ static double inc(const LevelConsts& C, double X, double h, double dW, double a, double b) {
-        if (AR == AR_EXACT) return __dadd_rn(__dmul_rn(__dmul_rn(C.mu, X), h), __dmul_rn(__dmul_rn(C.sig, X), dW));
-        return X * fma(b, dW, a);          // here dW is the normal (or the sum of two), b = sig*sqrt(dt)
+    // production form: the exponent with a precomputed w = -2/(sig^2 dt Xl^2); far from the barrier
+    // the exponent is below -750 for every lane of the warp (exp underflows to exactly 0), and the
+    // whole warp skips the exp.
+    __device__ __forceinline__ static double inv_scale(const LevelConsts& C, double Xl) {
+        const double g = Xl * Xl;
+        double y = rcp64_seed(g);
+        y = fma(y, fma(-g, y, 1.0), y);
+        y = fma(y, fma(-g, y, 1.0), y);
+        return C.amer_cneg * y;
+    }
+    __device__ __forceinline__ static double exp_or_zero(double arg) {
+        if (__all_sync(__activemask(), arg < -750.0)) return 0.0;
+        return exp(arg);
+    }
+    __device__ __forceinline__ static double inc_exact(const LevelConsts& C, double X, double h, double dW) {
+        return __dadd_rn(__dmul_rn(__dmul_rn(C.mu, X), h), __dmul_rn(__dmul_rn(C.sig, X), dW));
     }
     // fine step j with normal z; row = tab[j]
     __device__ __forceinline__ void fine(const LevelConsts& C, const AmerRow& row, double z) {
@@ -1054,13 +1065,13 @@ struct AmerState {
         if (AR == AR_EXACT) {
             dWf = __dmul_rn(C.sqrt_dt, z);                              // :1548
             dWc = __dadd_rn(dWc, dWf);
-            Xr = __dadd_rn(Xl, inc(C, Xl, C.dt, dWf, 0, 0));            // :1554
+            Xr = __dadd_rn(Xl, inc_exact(C, Xl, C.dt, dWf));            // :1554
         } else {
             dWc += z;                                                    // in units of sqrt(dt)
             Xr = fma(Xl, fma(C.b_f, z, C.a_f), Xl);
         }
         const double A = fmax(Xl - lbF, 0.0), B = fmax(Xr - row.bR, 0.0);
-        const double P1 = touch(C, A, B, Xl);
+        const double P1 = AR == AR_EXACT ? touch_exact(C, A, B, Xl) : exp_or_zero(inv_scale(C, Xl) * A * B);
         if (AR == AR_EXACT) {
             f2 = __dadd_rn(f2, __dmul_rn(__dmul_rn(__dmul_rn(f1, P1), row.mkF), row.eF));      // :1569
             f1 = __dmul_rn(f1, __dsub_rn(1.0, P1));                      // :1571
@@ -1075,7 +1086,7 @@ struct AmerState {
     __device__ __forceinline__ void coarse(const LevelConsts& C, const AmerRow& row) {
         double Xl = c0, Xr, Xmid;
         if (AR == AR_EXACT) {
-            Xr = __dadd_rn(Xl, inc(C, Xl, C.Mdt, dWc, 0, 0));            // :1584
+            Xr = __dadd_rn(Xl, inc_exact(C, Xl, C.Mdt, dWc));            // :1584
             Xmid = __dadd_rn(__dadd_rn(Xl, __dmul_rn(0.5, __dsub_rn(Xr, Xl))),
                              __dmul_rn(__dmul_rn(C.sig, Xl), __dsub_rn(dWc, __dmul_rn(0.5, dWc))));    // :1585
         } else {
@@ -1083,7 +1094,13 @@ struct AmerState {
             Xmid = fma(C.b_f * Xl, 0.5 * dWc, fma(0.5, Xr - Xl, Xl));
         }
         const double A = fmax(Xl - lbC, 0.0), Bm = fmax(Xmid - row.mb1, 0.0), B = fmax(Xr - row.bR, 0.0);
-        const double P11 = touch(C, A, Bm, Xl), P12 = touch(C, Bm, B, Xl);   // :1600-1601
+        double P11, P12;                                                 // :1600-1601
+        if (AR == AR_EXACT) {
+            P11 = touch_exact(C, A, Bm, Xl); P12 = touch_exact(C, Bm, B, Xl);
+        } else {
+            const double w = inv_scale(C, Xl) * Bm;
+            P11 = exp_or_zero(w * A); P12 = exp_or_zero(w * B);
+        }
         if (AR == AR_EXACT) {
             const double P1 = __dsub_rn(1.0, __dmul_rn(__dsub_rn(1.0, P11), __dsub_rn(1.0, P12)));   // :1603
             c2 = __dadd_rn(c2, __dmul_rn(__dmul_rn(__dmul_rn(c1, P1), row.mkC), row.eC));         // :1605
