@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""High-accuracy end-to-end check of both samplers: Euro_GBM mlmc at small eps against BS()."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import multilevel_mc_sdes_b200 as mm  # noqa: E402
+
+rep = {}
+for sampler in ("f32bm", "f64bm"):
+    for eps in ((2e-3, 5e-4, 1e-4, 5e-5) if sampler == "f32bm" else (5e-4, 1e-4)):
+        errs, secs, tot = [], [], []
+        for seed in range(4):
+            o = mm.Euro_GBM(verbose=False, seed=seed, sampler=sampler, alpha_0=1, beta_0=1)
+            t0 = time.perf_counter()
+            sums, N = o.mlmc(eps, M=4)
+            secs.append(time.perf_counter() - t0)
+            errs.append(float(np.sum(sums[0] / N) - o.BS()))
+            tot.append(float(N.sum()))
+        rep[f"{sampler}_eps{eps:g}"] = {"errors": errs, "rms_over_eps": float(np.sqrt(np.mean(np.square(errs))) / eps),
+                                        "mean_err_over_eps": float(np.mean(errs) / eps), "seconds": secs, "samples": tot}
+print(json.dumps(rep, indent=1))
