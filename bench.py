@@ -252,7 +252,8 @@ def run_b200(args):
     try:
         mix = json.load(open(os.path.join(ROOT, "multilevel_mc_sdes_b200", "csrc", "sass_mix.json")))[sampler]
         f_sm = (clocks.get("sm_mhz") or 1965.0) * 1e6
-        slots_per_s = 148 * 4 * f_sm                              # dispatch cycles/s over all SMSPs
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        slots_per_s = n_sm * 4 * f_sm                             # dispatch cycles/s over all SMSPs
         warp_steps_per_s = steps_per_s_gpu / 32.0
         cyc = slots_per_s / warp_steps_per_s
         issue = {

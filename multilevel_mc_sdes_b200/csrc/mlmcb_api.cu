@@ -44,9 +44,11 @@ struct DeviceGuard {
 
 struct DeviceInfo { int sms = 0; bool pool_ready = false; };
 DeviceInfo g_dev[64];
+std::mutex g_dev_mu;               // first-use initialisation of g_dev / g_host entries
 
 int device_info(int dev, DeviceInfo** out) {
     if (dev < 0 || dev >= 64) return fail(MLMCB_EINVAL, "device %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_dev_mu);
     DeviceInfo& d = g_dev[dev];
     if (!d.sms) {
         int sms = 0;
