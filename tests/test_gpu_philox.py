@@ -292,3 +292,23 @@ def test_path_functions_return_reference_shapes(cuda_lib):
         mm.Option().path(10, 1, 2)
     with pytest.raises(NotImplementedError):
         mm.Digital_Merton().anti_path(10, 1, 2)
+
+
+def test_maximum_sizes(cuda_lib):
+    """Path ids beyond 2^32 (the id is 48 bits wide), more paths per launch than 2^32, and the longest
+    supported path (2^20 fine steps)."""
+    opt = mm.Euro_GBM(seed=3)
+    n = 5_000_000_000                                               # > 2^32 paths in one launch, l = 0
+    s = level_sums(opt, n, 0, 2)
+    bs_l0_tol = 4 * np.sqrt((s[1] / n - (s[0] / n) ** 2) / n)
+    ref = level_sums(opt, 50_000_000, 0, 2, offset=(1 << 40))      # ids around 2^40: same distribution
+    assert abs(s[0] / n - ref[0] / 5e7) < bs_l0_tol + 4 * np.sqrt((ref[1] / 5e7 - (ref[0] / 5e7) ** 2) / 5e7)
+    a = level_sums(opt, 1000, 2, 2, offset=(1 << 32) - 500, per_path=True)[1]
+    b = level_sums(opt, 500, 2, 2, offset=(1 << 32), per_path=True)[1]
+    assert np.array_equal(a[500:], b)                                # ids straddling 2^32 are consistent
+    with pytest.raises(ValueError):
+        level_sums(opt, 10, 2, 2, offset=(1 << 48))                  # ids must stay below 2^48
+    long = level_sums(mm.Asian_GBM(seed=1), 20_000, 20, 2)           # 1 048 576 fine steps per path
+    assert np.isfinite(long).all() and long[3] > 0
+    with pytest.raises(ValueError):
+        level_sums(opt, 10, 34, 2)                                   # 2^34 steps: above the 2^33 cap
