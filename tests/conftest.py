@@ -14,6 +14,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """The CUDA library and the C oracle are build products (git-ignored): make sure they exist and
+    are current before any test imports them (nvcc cross-compiles sm_100a without a GPU)."""
+    from multilevel_mc_sdes_b200 import build as b
+    if b.is_stale():
+        b.build()
+    from oracle import c_oracle
+    c_oracle.build()
+
+
 @pytest.fixture(scope="session")
 def golden():
     return {n: np.load(os.path.join(GOLDEN, n + ".npz"), allow_pickle=False)
