@@ -17,11 +17,21 @@ def pytest_configure(config):
 def pytest_sessionstart(session):
     """The CUDA library and the C oracle are build products (git-ignored): make sure they exist and
     are current before any test imports them (nvcc cross-compiles sm_100a without a GPU)."""
+    import warnings
     from multilevel_mc_sdes_b200 import build as b
-    if b.is_stale():
+    if not os.path.exists(b.LIB):
         b.build()
+    elif b.is_stale():
+        try:            # file times may not survive a copy of the tree: a present library is still usable
+            b.build()
+        except Exception as e:  # noqa: BLE001
+            warnings.warn(f"libmlmcb.so looks older than its sources and could not be rebuilt: {e}")
     from oracle import c_oracle
-    c_oracle.build()
+    try:
+        c_oracle.build()
+    except Exception:  # noqa: BLE001
+        if not os.path.exists(os.path.join(ROOT, "oracle", "libmlmc_oracle.so")):
+            raise
 
 
 @pytest.fixture(scope="session")
