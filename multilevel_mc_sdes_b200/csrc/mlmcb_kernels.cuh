@@ -184,36 +184,6 @@ __device__ __forceinline__ void bm_quad_f32(const LevelConsts& C, U4 w, float z[
     q = __ffma2_rn(q, T, f2(MLMCB_Q0)); c = __ffma2_rn(c, T, f2(MLMCB_C0));
     float2 zc = __fmul2_rn(rad, c), zs = __fmul2_rn(__fmul2_rn(rad, h), q);
     z[0] = zc.x; z[1] = zs.x; z[2] = zc.y; z[3] = zs.y;
-#elif MLMCB_PACKED_F32 == 2
-    // only the two Horner chains packed (8 FFMA2): balances fmaheavy against the issue slots
-    float ua = fmaf(__uint2float_rn(w.x), 0x1p-32f, 0x1p-33f), ub = fmaf(__uint2float_rn(w.z), 0x1p-32f, 0x1p-33f);
-    float ra = sqrt_approx(lg2_approx(ua) * MLMCB_NEG2LN2), rb = sqrt_approx(lg2_approx(ub) * MLMCB_NEG2LN2);
-    ra = __uint_as_float(__float_as_uint(ra) ^ (w.x << 31));
-    rb = __uint_as_float(__float_as_uint(rb) ^ (w.z << 31));
-    float ha = __int2float_rn((int)w.y) * 0x1p-32f, hb = __int2float_rn((int)w.w) * 0x1p-32f;
-    float2 T = make_float2(ha * ha, hb * hb);
-    float2 q = __ffma2_rn(T, f2(MLMCB_Q4), f2(MLMCB_Q3)), c = __ffma2_rn(T, f2(MLMCB_C4), f2(MLMCB_C3));
-    q = __ffma2_rn(q, T, f2(MLMCB_Q2)); c = __ffma2_rn(c, T, f2(MLMCB_C2));
-    q = __ffma2_rn(q, T, f2(MLMCB_Q1)); c = __ffma2_rn(c, T, f2(MLMCB_C1));
-    q = __ffma2_rn(q, T, f2(MLMCB_Q0)); c = __ffma2_rn(c, T, f2(MLMCB_C0));
-    z[0] = ra * c.x; z[1] = (ra * ha) * q.x; z[2] = rb * c.y; z[3] = (rb * hb) * q.y;
-#elif MLMCB_PACKED_F32 == 3
-    // one Horner chain packed per pair: (q,c) of the same pair ride together (4 FFMA2 per pair)
-    float ua = fmaf(__uint2float_rn(w.x), 0x1p-32f, 0x1p-33f), ub = fmaf(__uint2float_rn(w.z), 0x1p-32f, 0x1p-33f);
-    float ra = sqrt_approx(lg2_approx(ua) * MLMCB_NEG2LN2), rb = sqrt_approx(lg2_approx(ub) * MLMCB_NEG2LN2);
-    ra = __uint_as_float(__float_as_uint(ra) ^ (w.x << 31));
-    rb = __uint_as_float(__float_as_uint(rb) ^ (w.z << 31));
-    float ha = __int2float_rn((int)w.y) * 0x1p-32f, hb = __int2float_rn((int)w.w) * 0x1p-32f;
-    float Ta = ha * ha, Tb = hb * hb;
-    float2 pa = __ffma2_rn(f2(Ta), make_float2(MLMCB_Q4, MLMCB_C4), make_float2(MLMCB_Q3, MLMCB_C3));
-    pa = __ffma2_rn(pa, f2(Ta), make_float2(MLMCB_Q2, MLMCB_C2));
-    pa = __ffma2_rn(pa, f2(Ta), make_float2(MLMCB_Q1, MLMCB_C1));
-    pa = __ffma2_rn(pa, f2(Ta), make_float2(MLMCB_Q0, MLMCB_C0));
-    float qb = fmaf(Tb, MLMCB_Q4, MLMCB_Q3), cb = fmaf(Tb, MLMCB_C4, MLMCB_C3);
-    qb = fmaf(qb, Tb, MLMCB_Q2); cb = fmaf(cb, Tb, MLMCB_C2);
-    qb = fmaf(qb, Tb, MLMCB_Q1); cb = fmaf(cb, Tb, MLMCB_C1);
-    qb = fmaf(qb, Tb, MLMCB_Q0); cb = fmaf(cb, Tb, MLMCB_C0);
-    z[0] = ra * pa.y; z[1] = (ra * ha) * pa.x; z[2] = rb * cb; z[3] = (rb * hb) * qb;
 #else
     bm_pair_f32(C.poly_q4, C.poly_c4, w.x, w.y, z[0], z[1]);
     bm_pair_f32(C.poly_q4, C.poly_c4, w.z, w.w, z[2], z[3]);
