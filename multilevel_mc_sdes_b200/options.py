@@ -387,6 +387,10 @@ class Merton_Option(Option):
         self.J_bar = np.exp(jumpmean + 0.5 * jumpstd ** 2) - 1   # :1291
         self.jumpstd = jumpstd
         self.jumpmean = jumpmean
+        # kept for attribute parity with the reference (:1294-1295); the kernels draw their own
+        # exponential gaps and jump sizes from Philox and never call these
+        self.jumptime = np.random.exponential
+        self.jumpsize = lambda: jumpmean + jumpstd * np.random.standard_normal()
         self.sig = sig
 
     def sde(self, X, dt, t_, dW, dJ=0):
@@ -394,6 +398,30 @@ class Merton_Option(Option):
         if self.scheme == "milstein":                           # notebook cell 1, milstein_Merton
             dx_ = dx_ + 0.5 * X * (self.sig ** 2) * (dW ** 2 - dt)
         return dx_ + (dx_ + X) * dJ
+
+
+class _HostOnlyOption(Option):
+    """Reference classes whose SDE / path / payoff are arbitrary user Python callables
+    (JumpDiffusion_Option :1044-1120, Diffusion_Option :1122-1209, MyOption :1211-1244).  A Python
+    lambda cannot run inside a CUDA kernel, so these stay with the reference's host path; the names
+    exist here only to fail with a clear message instead of an AttributeError."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError(
+            f"{type(self).__name__} takes user-supplied Python callables and is outside the GPU hot path; "
+            "use the reference implementation for it (see DESIGN.md, out of scope)")
+
+
+class JumpDiffusion_Option(_HostOnlyOption):
+    pass
+
+
+class Diffusion_Option(_HostOnlyOption):
+    pass
+
+
+class MyOption(_HostOnlyOption):
+    pass
 
 
 class Euro_GBM(GBM_Option):

@@ -149,6 +149,20 @@ def test_option_surface_and_errors():
     assert np.array_equal(o.sde(x, 0.01, 0.0, np.array([0.1, -0.1])), o.mu * x * 0.01 + o.sig * x * np.array([0.1, -0.1]))
 
 
+def test_reference_class_names_are_all_present():
+    """Every class the reference module defines exists here (MLMC_RSCAM.py:13-16); the user-lambda
+    ones refuse to construct instead of silently running something else."""
+    for name in ("Option", "JumpDiffusion_Option", "Diffusion_Option", "Merton_Option", "GBM_Option", "MyOption",
+                 "Euro_GBM", "Euro_Merton", "Lookback_GBM", "Lookback_Merton", "Asian_GBM", "Asian_Merton",
+                 "Digital_GBM", "Digital_Merton", "Amer_GBM"):
+        assert hasattr(mm, name), name
+    for cls in (mm.JumpDiffusion_Option, mm.Diffusion_Option, mm.MyOption):
+        with pytest.raises(NotImplementedError):
+            cls(sig=lambda x, t: 0.2)
+    m = mm.Euro_Merton()
+    assert callable(m.jumptime) and callable(m.jumpsize)
+
+
 def test_amer_gbm_surface():
     a = mm.Amer_GBM(exerciseBoundary=mm.sqrt_boundary(0.7), K=95)
     assert a.boundary_c == 0.7 and a._params().boundary_c == 0.7
