@@ -406,8 +406,7 @@ int mlmcb_level_sweep_host(const mlmcb_params* p, int model, int payoff, int M, 
     HostSide* h;
     if (int rc = host_side(device, &h)) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    // fork: side streams wait for whatever precedes on the caller's stream
-    CU(cudaEventRecord(h->fork, st));
+    // fork: side streams wait for whatever precedes on the caller's stream (and the zero-fill)
     CU(cudaMemsetAsync(h->dev, 0, (size_t)n_levels * 8 * sizeof(double), st));
     CU(cudaEventRecord(h->fork, st));
     bool used[8] = {};
@@ -417,8 +416,10 @@ int mlmcb_level_sweep_host(const mlmcb_params* p, int model, int payoff, int M, 
         cudaStream_t s = h->side[slot & 7];
         if (!used[slot & 7]) { CU(cudaStreamWaitEvent(s, h->fork, 0)); used[slot & 7] = true; }
         if (int rc = level_sums_impl(p, model, payoff, levels[i], M, n_paths[i], seed, path_offsets[i], flags,
-                                     device, s, h->dev + (size_t)i * 8, nullptr, nullptr))
+                                     device, s, h->dev + (size_t)i * 8, nullptr, nullptr)) {
+            cudaDeviceSynchronize();      // launches already issued on side streams must not outlive the call
             return rc;
+        }
         ++slot;
     }
     for (int s = 0; s < 8; ++s) {
