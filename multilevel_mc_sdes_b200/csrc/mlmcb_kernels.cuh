@@ -51,7 +51,10 @@ enum { SAMP_F32BM = 0, SAMP_F64BM = 1 };
 enum { SCH_EM = 0, SCH_MILSTEIN = 1 };
 enum { PAY_EURO = 0, PAY_ASIAN = 1, PAY_LOOKBACK = 2, PAY_DIGITAL = 3, PAY_AMERICAN = 4 };
 
-constexpr int kThreads = 128;
+#ifndef MLMCB_THREADS
+#define MLMCB_THREADS 128
+#endif
+constexpr int kThreads = MLMCB_THREADS;
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 
