@@ -312,3 +312,26 @@ def test_maximum_sizes(cuda_lib):
     assert np.isfinite(long).all() and long[3] > 0
     with pytest.raises(ValueError):
         level_sums(opt, 10, 34, 2)                                   # 2^34 steps: above the 2^33 cap
+
+
+def test_concurrent_host_calls_from_threads(cuda_lib):
+    """The _host entry points are serialised per device and the workspace is stream-ordered: calls from
+    several Python threads give the same sums as the same calls made one after the other."""
+    import threading
+    specs = [(mm.Euro_GBM, 3, 4), (mm.Asian_GBM, 2, 2), (mm.Lookback_Merton, 3, 2), (mm.Digital_GBM, 4, 2),
+             (mm.Amer_GBM, 3, 2), (mm.Euro_Merton, 1, 2)]
+    want = [cls(seed=9).looper(200_003, l, M, False) for cls, l, M in specs]
+    got = [None] * len(specs)
+
+    def work(i):
+        cls, l, M = specs[i]
+        for _ in range(3):
+            got[i] = cls(seed=9).looper(200_003, l, M, False)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(specs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
