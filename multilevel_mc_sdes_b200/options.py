@@ -265,6 +265,27 @@ class Option:
         for signature compatibility (the GPU needs no chunking)."""
         return self._sweep([(int(Nl), int(l))], M, anti=(anti == True))[0]  # noqa: E712 (reference spelling :941)
 
+    def looper_async(self, Nl, l, M, anti=False, out=None):
+        """Device-side variant of `looper`: launches on torch's current stream and returns the seven sums
+        as a CUDA float64 tensor without synchronising (no D2H copy).  With `distributed=True` this rank
+        simulates its slice only and the caller owns the all-reduce."""
+        self._check_product()
+        if anti and not self._has_anti:
+            raise NotImplementedError("Option instance has no implemented anti_payoff method")
+        import torch
+        n = int(Nl)
+        start = self._take_ids(l, n)
+        n_loc, start_loc = self._shard(n, start)
+        dev = torch.device("cuda", self.device)
+        if out is None:
+            out = torch.empty(7, dtype=torch.float64, device=dev)
+        p = self._params()
+        _lib.check(_lib.load().mlmcb_level_sums(
+            C.byref(p), self._model, self._payoff_kind, int(l), int(M), n_loc, self.seed, start_loc,
+            self._flags() | (_lib.ANTITHETIC if anti else 0), self.device, _stream_handle(self.device),
+            out.data_ptr(), None, None))
+        return out
+
     def _sweep(self, requests, M, anti=False):
         """requests: [(Nl, l), ...] -> list of 7-vectors.  All launches of one sweep run
         concurrently on the device; one D2H copy brings every row back."""

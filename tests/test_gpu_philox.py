@@ -335,3 +335,11 @@ def test_concurrent_host_calls_from_threads(cuda_lib):
         t.join()
     for a, b in zip(want, got):
         assert np.array_equal(a, b)
+
+
+def test_looper_async_matches_looper(cuda_lib):
+    import torch
+    a = mm.Asian_GBM(seed=12).looper(300_000, 3, 4, False)
+    t = mm.Asian_GBM(seed=12).looper_async(300_000, 3, 4)
+    assert t.is_cuda and t.dtype == torch.float64
+    assert np.array_equal(t.cpu().numpy(), a)
