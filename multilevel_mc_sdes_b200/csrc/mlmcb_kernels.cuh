@@ -115,7 +115,7 @@ __device__ __forceinline__ U4 philox10(const LevelConsts& C, uint32_t c0, uint32
 // everything else fixed along a path, both multiplies of round 1 and one multiply each of rounds
 // 2 and 3 are loop-invariant and hoisted by the compiler: 16 instead of 20 IMAD.WIDE per block
 // for the same Philox4x32-10 output.
-enum { STREAM_GRID = 0, STREAM_JUMP = 1 };
+enum { STREAM_GRID = 0, STREAM_JUMP = 1, STREAM_PACK = 2 };
 
 __device__ __forceinline__ U4 philox_at(const LevelConsts& C, ull pid, uint32_t kind, uint32_t blk) {
     return philox10(C, kind, blk, (uint32_t)pid, ((uint32_t)(pid >> 32) & 0xFFFFu) | C.ctr3_tag);
@@ -295,18 +295,32 @@ struct PhiloxSource {
     static constexpr int kUnroll = SAMP == SAMP_F32BM ? MLMCB_UNROLL : 1;   // blocks in flight per thread
     const LevelConsts& C;
     ull pid;
-    __device__ __forceinline__ void load4(uint32_t b, R z[4]) const {
+    __device__ __forceinline__ void load4(uint32_t b, R z[4]) const { load4_stream(STREAM_GRID, b, z); }
+    __device__ __forceinline__ void load4_stream(uint32_t kind, uint32_t b, R z[4]) const {
         if (SAMP == SAMP_F32BM) {
             float f[4];
-            bm_quad_f32(C, philox_at(C, pid, STREAM_GRID, b), f);
+            bm_quad_f32(C, philox_at(C, pid, kind, b), f);
             z[0] = (R)f[0]; z[1] = (R)f[1]; z[2] = (R)f[2]; z[3] = (R)f[3];
         } else {
-            U4 r = philox_at(C, pid, STREAM_GRID, 2 * b), s = philox_at(C, pid, STREAM_GRID, 2 * b + 1);
+            U4 r = philox_at(C, pid, kind, 2 * b), s = philox_at(C, pid, kind, 2 * b + 1);
             double d0, d1, d2, d3;
             bm_pair_f64(C, r.x, r.y, r.z, r.w, d0, d1);
             bm_pair_f64(C, s.x, s.y, s.z, s.w, d2, d3);
             z[0] = (R)d0; z[1] = (R)d1; z[2] = (R)d2; z[3] = (R)d3;
         }
+    }
+};
+
+// Normals of a path that shares a Philox block with its neighbours (coarsest levels): z[base..].
+template <typename R>
+struct PackedSource {
+    static constexpr int kUnroll = 1;
+    R z[4];
+    int base;
+    __device__ __forceinline__ void load4(uint32_t, R out[4]) const {   // two steps per path: base is 0 or 2
+        out[0] = base == 0 ? z[0] : z[2];
+        out[1] = base == 0 ? z[1] : z[3];
+        out[2] = out[3] = (R)0;
     }
 };
 
@@ -1191,6 +1205,68 @@ level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* 
     Sums7 acc;
     acc.clear();
     const ull stride = (ull)gridDim.x * blockDim.x;
+    if (MODEL == 0 && C.nsteps <= 2) {
+        // The coarsest levels (1 or 2 fine steps per path) are where MLMC puts most of its samples and
+        // a path needs fewer normals than one Philox block holds: 4 (or 2) consecutive global path ids
+        // share one block (stream STREAM_PACK, counter = id / paths-per-block), each taking its own
+        // normals.  Still a pure function of (seed, level, global path id).
+        const int per = C.nsteps == 1 ? 4 : 2;
+        const ull first = C.path_offset / per, last = (C.path_offset + C.n_paths - 1) / per;
+        const ull lo = C.path_offset, hi = C.path_offset + C.n_paths;
+        if (C.nsteps == 1) {
+            // l == 0: one Euler step, no coarse path (:341), sums row [Pf, Pf^2, Pf, Pf^2, 0, 0, 0] (:949)
+            const StepCoef<R, SCH> co(C);
+            const R X0 = (R)C.X0;
+            const double h0 = 0.5 * C.X0, vc0 = FN == FN_AVG ? 0.0 : C.X0, gc0 = FN == FN_MIN ? C.X0 : 0.0;
+            double s0 = 0.0, s1 = 0.0;
+            for (ull c = first + (ull)blockIdx.x * blockDim.x + threadIdx.x; c <= last; c += stride) {
+                R z[4];
+                PhiloxSource<R, SAMP>{C, c}.load4_stream(STREAM_PACK, 0, z);
+                const ull p0 = c << 2;
+                const bool inner = p0 >= lo && p0 + 4 <= hi;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const R Xf = fma_<R>(X0, co.t(z[k]), X0);
+                    double vf = (double)Xf, gf = 0.0;
+                    if (FN == FN_AVG) vf = C.avg_wf * ((double)Xf + fma(-0.5, (double)Xf, h0));      // :369-386
+                    if (FN == FN_MIN) gf = (double)min_<R>(X0, Xf);                                    // :420
+                    const double Pf = payoff_fine(C, vf, gf);
+                    if (inner || (p0 + k >= lo && p0 + k < hi)) {
+                        s0 += Pf;
+                        s1 = fma(Pf, Pf, s1);
+                        if (Pf_out || Pc_out || C.raw) {
+                            const ull i = p0 + k - lo;
+                            if (Pf_out) Pf_out[i] = Pf;
+                            if (Pc_out) Pc_out[i] = vc0;                                               // raw coarse output :82
+                            if (C.raw) {
+                                C.raw[i] = vf; C.raw[C.n_paths + i] = gf;
+                                C.raw[2 * C.n_paths + i] = vc0; C.raw[3 * C.n_paths + i] = gc0;
+                            }
+                        }
+                    }
+                }
+            }
+            acc.s[0] = acc.s[2] = s0;
+            acc.s[1] = acc.s[3] = s1;
+        } else {
+            for (ull c = first + (ull)blockIdx.x * blockDim.x + threadIdx.x; c <= last; c += stride) {
+                PhiloxSource<R, SAMP> quad{C, c};
+                PackedSource<R> src;
+                quad.load4_stream(STREAM_PACK, 0, src.z);
+#pragma unroll 1
+                for (int k = 0; k < 2; ++k) {
+                    const ull pid = c * 2 + k;
+                    if (pid < lo || pid >= hi) continue;
+                    src.base = 2 * k;
+                    double vf, vc, gf, gc;
+                    gbm_path_fast<R, FN, 0, SCH>(C, src, vf, vc, gf, gc);
+                    emit(C, pid - lo, vf, vc, gf, gc, acc, Pf_out, Pc_out);
+                }
+            }
+        }
+        grid_finish(acc, partials, ticket, out7);
+        return;
+    }
     for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
         const ull pid = C.path_offset + i;
         double vf, vc, gf, gc;

@@ -343,3 +343,24 @@ def test_looper_async_matches_looper(cuda_lib):
     t = mm.Asian_GBM(seed=12).looper_async(300_000, 3, 4)
     assert t.is_cuda and t.dtype == torch.float64
     assert np.array_equal(t.cpu().numpy(), a)
+
+
+def test_packed_low_levels_are_id_addressed(cuda_lib, c_oracle):
+    """l = 0 (and M=2, l=1) share one Philox block between 4 (2) neighbouring path ids: the per-path
+    values must not depend on how a range is cut (odd offsets, odd lengths), only on the global id."""
+    for cls, l, M in ((mm.Euro_GBM, 0, 2), (mm.Asian_GBM, 0, 4), (mm.Lookback_GBM, 1, 2), (mm.Digital_GBM, 0, 3),
+                      (mm.Euro_GBM, 1, 2)):
+        opt = cls(seed=21)
+        _, Pf, Pc = level_sums(opt, 10_007, l, M, offset=3, per_path=True)
+        _, Pa, _ = level_sums(opt, 4_001, l, M, offset=3, per_path=True)
+        _, Pb, Pcb = level_sums(opt, 6_006, l, M, offset=4_004, per_path=True)
+        assert np.array_equal(np.concatenate([Pa, Pb]), Pf)
+        assert np.array_equal(Pcb, Pc[4_001:])
+        s = level_sums(opt, 10_007, l, M, offset=3)
+        np.testing.assert_allclose(s, O.seven_sums(Pf, Pc, l), rtol=1e-12)
+        assert len(np.unique(Pf[Pf > 0])) > 0.4 * np.count_nonzero(Pf > 0) or cls is mm.Digital_GBM   # distinct draws
+    # neighbours inside one block are independent draws
+    _, Pf, _ = level_sums(mm.Lookback_GBM(seed=2), 400_000, 0, 2, per_path=True)
+    q = Pf.reshape(-1, 4)
+    c = np.corrcoef(q.T)
+    assert np.all(np.abs(c[np.triu_indices(4, 1)]) < 4 / np.sqrt(len(q)))
