@@ -282,6 +282,19 @@ def run_b200(args):
         "algorithmic_hbm_bytes_per_launch": 56,
     }
 
+    # the second half of BASELINE.json's metric: mlmc(eps) wall time (N=1 only; ~0.3 s of GPU time)
+    mlmc_wall = None
+    if world == 1:
+        mlmc_wall = {}
+        for name, o, eps, kw in (("asian_gbm_eps1e-4_M4", mm.Asian_GBM(verbose=False, device=local), 1e-4, dict(M=4)),
+                                 ("readme_euro_gbm_eps0.01", mm.Euro_GBM(verbose=False, device=local, **OPT_KW), 0.01, {})):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sums_m, N_m = o.mlmc(eps, **kw)
+            mlmc_wall[name] = {"seconds": time.perf_counter() - t0, "price": float(np.sum(sums_m[0] / N_m)),
+                               "levels": len(N_m), "samples": float(N_m.sum())}
+        mlmc_wall["readme_euro_gbm_eps0.01"]["BS"] = 35.17419437739385
+
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
@@ -304,7 +317,7 @@ def run_b200(args):
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(_lib.Params),
                 "d2h_bytes_per_step": 56, "ms_per_step": 1e3 * dt / args.steps},
         "gpu_launches": args.steps,
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "mlmc_wall": mlmc_wall,
         "check": {"mean_Pf_last_step": price_f, "path_steps_per_s": value * nsteps_path},
     }
     print(json.dumps(line))
