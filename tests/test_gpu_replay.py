@@ -197,3 +197,38 @@ def test_american_put_replay(golden, cuda_lib, c_oracle):
     assert np.all(np.abs(Pf - rf) <= payoff_tol(O.Params(), rf)) and np.all(np.abs(Pc - rc) <= payoff_tol(O.Params(), rc))
     with pytest.raises(ValueError, match="M must be equal to 2"):
         mm.Amer_GBM().payoff_replay(np.zeros((16, 4)), 2, 4)
+
+
+def test_randomised_parameters_bit_exact_against_c_oracle(cuda_lib, c_oracle):
+    """40 seeded random parameter sets / shapes (odd path counts, M in 2..6, every GBM product, plain,
+    Milstein and antithetic): the reference-order policy must equal the pinned C restatement bit for bit,
+    the production policy within 1e-12*max(|P|, K e^{-rT})."""
+    rs = np.random.RandomState(20261020)
+    n_checked = 0
+    for case in range(40):
+        kw = dict(X0=float(rs.uniform(50, 150)), K=float(rs.uniform(60, 140)), T=float(rs.choice([0.25, 0.5, 1.0, 2.0, 3.0])),
+                  r=float(rs.uniform(0.0, 0.08)), sig=float(rs.uniform(0.05, 0.6)), drift=float(rs.choice([0.0, 0.01, -0.02])))
+        M = int(rs.choice([2, 3, 4, 5, 6]))
+        l = int(rs.randint(0, 5 if M <= 3 else 4))
+        n = int(rs.choice([1, 7, 33, 129, 257]))
+        Z = rs.randn(M ** l, n)
+        variant = case % 3
+        for cname, pay in (("Euro_GBM", O.EURO), ("Asian_GBM", O.ASIAN), ("Lookback_GBM", O.LOOKBACK), ("Digital_GBM", O.DIGITAL)):
+            if variant == 2 and (pay not in (O.EURO, O.ASIAN) or M % 2):
+                continue
+            scheme = "milstein" if variant == 1 else "em"
+            p = O.Params(scheme=scheme, **kw)
+            opt = getattr(mm, cname)(scheme=scheme, **kw)
+            if variant == 2:
+                rf, rc = c_oracle.gbm_anti_replay(p, pay, l, M, Z)
+                Pf, Pc = opt.payoff_replay(Z, l, M, arith="exact", anti=True)
+                Qf, Qc = opt.payoff_replay(Z, l, M, arith="fast", anti=True)
+            else:
+                rf, rc = c_oracle.gbm_replay(p, pay, l, M, Z)
+                Pf, Pc = opt.payoff_replay(Z, l, M, arith="exact")
+                Qf, Qc = opt.payoff_replay(Z, l, M, arith="fast")
+            assert np.array_equal(Pf, rf) and np.array_equal(Pc, rc), (case, cname, kw, M, l, n)
+            if pay != O.DIGITAL:
+                assert np.all(np.abs(Qf - rf) <= payoff_tol(p, rf)) and np.all(np.abs(Qc - rc) <= payoff_tol(p, rc)), (case, cname)
+            n_checked += 1
+    assert n_checked > 90
