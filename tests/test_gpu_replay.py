@@ -232,3 +232,29 @@ def test_randomised_parameters_bit_exact_against_c_oracle(cuda_lib, c_oracle):
                 assert np.all(np.abs(Qf - rf) <= payoff_tol(p, rf)) and np.all(np.abs(Qc - rc) <= payoff_tol(p, rc)), (case, cname)
             n_checked += 1
     assert n_checked > 90
+
+
+def test_randomised_merton_parameters_against_numpy_oracle(cuda_lib):
+    """Seeded random Merton parameter sets (jump intensity up to 6 per year, both schemes): the CUDA path
+    replays the draws recorded from the pinned numpy restatement within the north-star tolerance."""
+    rs = np.random.RandomState(424242)
+    n_checked = 0
+    for case in range(16):
+        kw = dict(X0=float(rs.uniform(60, 140)), K=float(rs.uniform(70, 130)), T=float(rs.choice([0.5, 1.0, 2.0])),
+                  r=float(rs.uniform(0.0, 0.06)), sig=float(rs.uniform(0.1, 0.5)), lam=float(rs.choice([0.5, 1.0, 3.0, 6.0])),
+                  jumpmean=float(rs.uniform(-0.2, 0.2)), jumpstd=float(rs.uniform(0.05, 0.4)))
+        M = int(rs.choice([2, 3, 4]))
+        l = int(rs.randint(0, 4))
+        scheme = "milstein" if case % 2 else "em"
+        for cname, pay in (("Euro_Merton", O.EURO), ("Asian_Merton", O.ASIAN), ("Lookback_Merton", O.LOOKBACK)):
+            p = O.Params(scheme=scheme, **kw)
+            rec = O.RecordingDraws()
+            np.random.seed(1000 + case)
+            rf, rc = O.level_payoffs(p, O.MERTON, pay, l, M, n=33, draws=rec)
+            opt = getattr(mm, cname)(scheme=scheme, **kw)
+            for arith in ("exact", "fast"):
+                Pf, Pc = opt.payoff_replay(rec.packed(), l, M, arith=arith)
+                assert np.all(np.abs(Pf - rf) <= payoff_tol(p, rf)), (case, cname, arith, np.abs(Pf - rf).max())
+                assert np.all(np.abs(Pc - np.asarray(rc, dtype=float)) <= payoff_tol(p, np.asarray(rc, dtype=float))), (case, cname, arith)
+            n_checked += 1
+    assert n_checked == 48
