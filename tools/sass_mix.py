@@ -51,17 +51,21 @@ def hot_loop_mix(lib, pat, steps_per_iter=4):
         if pat not in name:
             continue
         body = ks[mangled]
-        best = None
+        # candidate loops = [target, backward branch]; the hot loop is the INNERMOST one (no other
+        # backward branch inside) that carries the most Philox multiplies (IMAD.WIDE)
+        spans = []
         for addr, ins in body:
             m = re.search(r"BRA(?:\.U)?\s+(?:\S+,\s+)?(0x[0-9a-f]+)", ins)
-            if not m or int(m.group(1), 16) > addr:
+            if m and int(m.group(1), 16) <= addr:
+                spans.append((int(m.group(1), 16), addr))
+        best, best_key = None, None
+        for lo, hi in spans:
+            if any((l2, h2) != (lo, hi) and lo <= l2 and h2 <= hi for l2, h2 in spans):
                 continue
-            lo = int(m.group(1), 16)
-            ops = [re.sub(r"^@!?U?P\d+\s+", "", i).split()[0] for a, i in body if lo <= a <= addr]
-            if not any(o.startswith("DFMA") or o.startswith("FFMA") for o in ops):
-                continue
-            if best is None or len(ops) < len(best):
-                best = ops
+            ops = [re.sub(r"^@!?U?P\d+\s+", "", i).split()[0] for a, i in body if lo <= a <= hi]
+            key = (sum(1 for o in ops if o.startswith("IMAD.WIDE")), len(ops))
+            if key[0] and (best_key is None or key > best_key):
+                best, best_key = ops, key
         if best is None:
             return None
         cls = collections.Counter()
