@@ -52,7 +52,7 @@ def hot_loop_mix(lib, pat, steps_per_iter=4):
             continue
         body = ks[mangled]
         # candidate loops = [target, backward branch]; the hot loop is the INNERMOST one (no other
-        # backward branch inside) that carries the most Philox multiplies (IMAD.WIDE)
+        # backward branch inside, no global stores) that carries the most Philox multiplies (IMAD.WIDE)
         spans = []
         for addr, ins in body:
             m = re.search(r"BRA(?:\.U)?\s+(?:\S+,\s+)?(0x[0-9a-f]+)", ins)
@@ -63,6 +63,8 @@ def hot_loop_mix(lib, pat, steps_per_iter=4):
             if any((l2, h2) != (lo, hi) and lo <= l2 and h2 <= hi for l2, h2 in spans):
                 continue
             ops = [re.sub(r"^@!?U?P\d+\s+", "", i).split()[0] for a, i in body if lo <= a <= hi]
+            if any(o.startswith("STG") for o in ops):
+                continue              # the coarsest-level loop writes optional per-path outputs; the step loop stores nothing
             key = (sum(1 for o in ops if o.startswith("IMAD.WIDE")), len(ops))
             if key[0] and (best_key is None or key > best_key):
                 best, best_key = ops, key
