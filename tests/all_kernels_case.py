@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Small end-to-end case for compute-sanitizer (memcheck): every kernel family once, tiny sizes."""
+"""Small end-to-end script (run by hand on a GPU box, also the intended target of a memcheck run):
+every kernel family once at small, non-multiple-of-block sizes.  Lives under tests/ because it uses the
+oracle's draw recorder."""
 import os
 import sys
 

@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Run the BASELINE.json configurations on one B200 and print a JSON report.
 
-    python tools/run_configs.py [--cpu] [--quick] > gpurun_out/configs.json
+    python tools/run_configs.py [--quick] > gpurun_out/configs.json
 
-#1 Euro_GBM(125,105,.02,.5).mlmc(0.01) vs BS()          (README example; --cpu also times the numpy port)
+#1 Euro_GBM(125,105,.02,.5).mlmc(0.01) vs BS()          (README example)
 #2 Asian_GBM().mlmc(1e-4, M=4), fp64, alpha_0=beta_0=None
 #3 Lookback_GBM() fixed-level sweep l=0..8, 1e8 samples/level, M=2 and M=4 (Giles_plot core :1775-1777)
 #4 Digital_Merton(beta_0=0.5).mlmc(1e-3, M=2)
@@ -36,7 +36,6 @@ def timed_mlmc(opt, eps, **kw):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--quick", action="store_true")
     a = ap.parse_args()
     rep = {"gpu": torch.cuda.get_device_name(0)}
@@ -75,15 +74,6 @@ def main():
     eps = 1e-2 if a.quick else 1e-3
     rep[f"cfg4_digital_merton_M2_eps{eps:g}"] = timed_mlmc(o, eps, M=2)
 
-    if a.cpu:
-        from oracle import np_oracle as O
-        p = O.Params(X0=125, K=105, r=0.02, sig=0.5)
-        np.random.seed(0)
-        t0 = time.perf_counter()
-        sums, N, al, be = mm.mlmc_driver(lambda reqs, M: [O.looper(p, O.GBM, O.EURO, n, l, M) for n, l in reqs],
-                                         0.01, 2, 1000, 1, 1)
-        rep["cfg1_numpy_port_1core"] = {"seconds": time.perf_counter() - t0, "price": float(np.sum(sums[0] / N)),
-                                        "L": len(N) - 1, "total_samples": float(N.sum())}
     print(json.dumps(rep, indent=1))
 
 
