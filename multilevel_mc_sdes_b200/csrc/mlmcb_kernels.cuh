@@ -32,6 +32,12 @@
 #ifndef MLMCB_F64BM_LIBDEVICE
 #define MLMCB_F64BM_LIBDEVICE 0     // 1: the first-cut canonical sampler on CUDA's log/sqrt/sincospi
 #endif
+#ifndef MLMCB_MINBLOCKS_MJD
+#define MLMCB_MINBLOCKS_MJD 6
+#endif
+#ifndef MLMCB_UNROLL_MJD
+#define MLMCB_UNROLL_MJD 2
+#endif
 #ifndef MLMCB_MINBLOCKS_F64
 #define MLMCB_MINBLOCKS_F64 1
 #endif
@@ -55,6 +61,7 @@ enum { PAY_EURO = 0, PAY_ASIAN = 1, PAY_LOOKBACK = 2, PAY_DIGITAL = 3, PAY_AMERI
 #define MLMCB_THREADS 128
 #endif
 constexpr int kThreads = MLMCB_THREADS;
+constexpr int kUnrollMjd = MLMCB_UNROLL_MJD;
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 
@@ -940,7 +947,7 @@ __device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid,
         const unsigned lanes = __activemask();
         const uint32_t run = __reduce_min_sync(lanes, jb > b ? jb - b : 0u);
         const uint32_t stop = b + run;
-#pragma unroll 1
+#pragma unroll kUnrollMjd
         for (; b < stop; ++b) {
             R z[4];
             src.load4(b, z);
@@ -1199,7 +1206,7 @@ __device__ __forceinline__ void emit(const LevelConsts& C, ull i, double vf, dou
 }
 
 template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH>
-__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64 : (MODEL == 0 ? MLMCB_MINBLOCKS : 6))
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64 : (MODEL == 0 ? MLMCB_MINBLOCKS : MLMCB_MINBLOCKS_MJD))
 level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
              double* out7, double* Pf_out, double* Pc_out) {
     Sums7 acc;
