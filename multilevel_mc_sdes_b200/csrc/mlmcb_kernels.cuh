@@ -744,7 +744,7 @@ struct JD {
     __device__ __forceinline__ void jump(const LevelConsts& C, double tau, R zw, R zq) {
         double dt = tau - tf;                                            // :458
         dtc += dt;                                                       // :459
-        R dWf = mul(zw, (R)sqrt(dt));                                    // :460
+        R dWf = mul(zw, (R)(AR == AR_EXACT ? sqrt(dt) : (dt > 0.0 ? sqrt_pos(dt) : 0.0)));   // :460
         dWc = add(dWc, dWf);                                             // :461
         R dJ;
         if (AR == AR_EXACT) dJ = (R)__dsub_rn(exp(__dadd_rn(C.jm, __dmul_rn(C.js, (double)zq))), 1.0);   // :462
@@ -773,7 +773,7 @@ struct JD {
     __device__ __forceinline__ void grid(const LevelConsts& C, double tn, R zw, bool whole = false) {
         const double dt = whole ? C.dt : tn - tf;                        // :477
         dtc += dt;                                                       // :478
-        R dWf = mul(zw, (R)(whole ? C.sqrt_dt : sqrt(dt)));              // :479
+        R dWf = mul(zw, (R)(whole ? C.sqrt_dt : (AR == AR_EXACT ? sqrt(dt) : (dt > 0.0 ? sqrt_pos(dt) : 0.0))));   // :479
         dWc = add(dWc, dWf);                                             // :480
         if (FN == FN_AVG) {                                              // :554-556
             Gf = add(Gf, half_area(Sf, dt));
