@@ -124,6 +124,12 @@ int mlmcb_replay_merton(const mlmcb_params* p, int payoff, int l, int M, uint64_
  * step < n_steps, for global path ids path_offset.. at level l.  For distribution tests.    */
 int mlmcb_sampler_probe(int sampler, uint64_t seed, int l, uint64_t path_offset, uint64_t n_paths,
                         uint64_t n_steps, int device, void* cuda_stream, double* d_out);
+/* The jump-stream records the Philox-mode Merton kernels use: d_out[3][n_records][n_paths] =
+ * inter-arrival times (scaled by 1/lam), jump-size normals, Brownian normals of the sub-step ending at
+ * each jump.  With mlmcb_sampler_probe this lets a test rebuild the exact draw streams of a Philox-mode
+ * call and push them through the replay entry point.                                                */
+int mlmcb_jump_probe(int sampler, uint64_t seed, int l, double lam, uint64_t path_offset, uint64_t n_paths,
+                     uint64_t n_records, int device, void* cuda_stream, double* d_out);
 /* Host-side Philox4x32-10 (same code the kernels use), for known-answer tests; no GPU needed. */
 void mlmcb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* Pipe micro-benchmarks used for the roofline denominators.  which: 0 DFMA, 1 DADD, 2 FFMA,

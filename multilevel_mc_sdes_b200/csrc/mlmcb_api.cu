@@ -547,6 +547,27 @@ int mlmcb_sampler_probe(int sampler, uint64_t seed, int l, uint64_t path_offset,
     return 0;
 }
 
+int mlmcb_jump_probe(int sampler, uint64_t seed, int l, double lam, uint64_t path_offset, uint64_t n_paths,
+                     uint64_t n_records, int device, void* cuda_stream, double* d_out) {
+    if (!d_out) return fail(MLMCB_EINVAL, "d_out is NULL");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    mlmcb_params p;
+    memset(&p, 0, sizeof p);
+    p.X0 = 1; p.K = 1; p.T = 1; p.sig = 1; p.lam = lam;
+    LevelConsts C;
+    if (int rc = make_consts(&p, MLMCB_MERTON, MLMCB_EURO, 0, 2, n_paths, seed, path_offset, &C)) return rc;
+    C.ctr3_tag = (uint32_t)l << 16;
+    if (n_paths == 0 || n_records == 0) return 0;
+    const int grid = (int)((n_paths + kThreads - 1) / kThreads);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (sampler == MLMCB_SAMPLER_F32BM) jump_probe_kernel<SAMP_F32BM><<<grid, kThreads, 0, st>>>(C, n_records, d_out);
+    else if (sampler == MLMCB_SAMPLER_F64BM) jump_probe_kernel<SAMP_F64BM><<<grid, kThreads, 0, st>>>(C, n_records, d_out);
+    else return fail(MLMCB_EINVAL, "unknown sampler %d", sampler);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int mlmcb_launch_geometry(int model, int payoff, int M, int flags, int device, int* threads_per_block,
                           int* max_blocks) {
     if (int rc = check_flags(flags)) return rc;

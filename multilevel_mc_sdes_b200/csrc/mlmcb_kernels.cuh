@@ -1377,6 +1377,21 @@ replay_mjd_kernel(const __grid_constant__ LevelConsts C, const double* zW, const
     grid_finish(acc, partials, ticket, out7);
 }
 
+// The jump-stream records of the Merton kernels: for record k of a path the inter-arrival time (already
+// divided by lam), the jump-size normal and the Brownian normal of the sub-step that ends at the jump.
+template <int SAMP>
+__global__ void jump_probe_kernel(const __grid_constant__ LevelConsts C, ull n_records, double* out) {
+    const ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_paths) return;
+    for (ull k = 0; k < n_records; ++k) {
+        double gap, zq, zw;
+        jump_draws<double, SAMP>(C, C.path_offset + i, (uint32_t)k, gap, zq, zw);
+        out[(0 * n_records + k) * C.n_paths + i] = gap;
+        out[(1 * n_records + k) * C.n_paths + i] = zq;
+        out[(2 * n_records + k) * C.n_paths + i] = zw;
+    }
+}
+
 template <int SAMP>
 __global__ void sampler_probe_kernel(const __grid_constant__ LevelConsts C, ull n_steps, double* out) {
     const ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x;

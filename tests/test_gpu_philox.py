@@ -364,3 +364,83 @@ def test_packed_low_levels_are_id_addressed(cuda_lib, c_oracle):
     q = Pf.reshape(-1, 4)
     c = np.corrcoef(q.T)
     assert np.all(np.abs(c[np.triu_indices(4, 1)]) < 4 / np.sqrt(len(q)))
+
+
+def _probe_normals(cuda_lib, sampler, seed, l, offset, n_paths, n_steps):
+    import torch
+    out = torch.empty(n_steps * n_paths, dtype=torch.float64, device="cuda")
+    _lib.check(cuda_lib.mlmcb_sampler_probe(sampler, seed, l, offset, n_paths, n_steps, 0, 0, out.data_ptr()))
+    torch.cuda.synchronize()
+    return out.cpu().numpy().reshape(n_steps, n_paths)
+
+
+@pytest.mark.parametrize("sampler", ["f32bm", "f64bm"])
+def test_philox_mode_equals_replay_of_its_own_draws_gbm(cuda_lib, sampler):
+    """Deterministic cross-check of the production kernels: the normals a Philox-mode call uses
+    (sampler probe) pushed through the replay entry point reproduce its per-path payoffs."""
+    code = _lib.SAMPLER_F32BM if sampler == "f32bm" else _lib.SAMPLER_F64BM
+    for cls, scheme in ((mm.Euro_GBM, "em"), (mm.Asian_GBM, "em"), (mm.Lookback_GBM, "em"), (mm.Digital_GBM, "em"),
+                        (mm.Asian_GBM, "milstein")):
+        if scheme == "milstein" and sampler == "f64bm":
+            continue                      # Milstein is built for the default sampler only
+        for l, M in ((2, 2), (3, 4), (2, 3), (5, 2)):
+            n, off, seed = 1000, 12345, 31
+            opt = cls(seed=seed, sampler=sampler, scheme=scheme)
+            opt._next_path[l] = off
+            Pf, Pc = opt.payoff(n, l, M)
+            Z = _probe_normals(cuda_lib, code, seed, l, off, n, M ** l)
+            Rf, Rc = cls(scheme=scheme).payoff_replay(Z, l, M, arith="fast")
+            np.testing.assert_allclose(Pf, Rf, rtol=1e-13, atol=1e-11)
+            np.testing.assert_allclose(Pc, Rc, rtol=1e-13, atol=1e-11)
+    # antithetic
+    opt = mm.Asian_GBM(seed=5, sampler=sampler)
+    opt._next_path[3] = 77
+    Pf, Pc = opt.anti_payoff(500, 3, 4)
+    Z = _probe_normals(cuda_lib, code, 5, 3, 77, 500, 64)
+    Rf, Rc = mm.Asian_GBM().payoff_replay(Z, 3, 4, arith="fast", anti=True)
+    np.testing.assert_allclose(Pf, Rf, rtol=1e-13, atol=1e-11)
+    np.testing.assert_allclose(Pc, Rc, rtol=1e-13, atol=1e-11)
+
+
+@pytest.mark.parametrize("lam", [1.0, 6.0])
+def test_philox_mode_equals_replay_of_its_own_draws_merton(cuda_lib, lam):
+    """The same for the jump-adapted kernels: grid normals from the sampler probe, jump records from the
+    jump probe, interleaved on the host in the order the reference consumes them (:454-479), replayed.
+    Exercises the jump-free run length agreement, the mixed blocks and the tail block of the production
+    kernel against the straightforward replay loop."""
+    import torch
+    for cls in (mm.Euro_Merton, mm.Asian_Merton, mm.Lookback_Merton):
+        for l, M in ((0, 2), (1, 2), (3, 2), (3, 4), (2, 3), (5, 2)):
+            n, off, seed, K = 600, 999, 17, 64
+            opt = cls(seed=seed, lam=lam)
+            opt._next_path[l] = off
+            Pf, Pc = opt.payoff(n, l, M)
+            nsteps = M ** l
+            # grid normals: the coarsest GBM-style packing does not apply to Merton; block-addressed stream
+            Z = _probe_normals(cuda_lib, _lib.SAMPLER_F32BM, seed, l, off, n, max(nsteps, 1))
+            rec = torch.empty(3 * K * n, dtype=torch.float64, device="cuda")
+            _lib.check(cuda_lib.mlmcb_jump_probe(_lib.SAMPLER_F32BM, seed, l, lam, off, n, K, 0, 0, rec.data_ptr()))
+            torch.cuda.synchronize()
+            rec = rec.cpu().numpy().reshape(3, K, n)
+            zW, zQ, E, oW, oQ, oE = [], [], [], [0], [0], [0]
+            T = 1.0
+            dt = T / nsteps
+            for i in range(n):
+                k = 0
+                tau = rec[0, 0, i]
+                E.append(rec[0, 0, i])
+                for j in range(1, nsteps + 1):
+                    tn = j * dt                     # the production kernel's grid time (double)j*dt
+                    while tau < tn:
+                        zW.append(rec[2, k, i]); zQ.append(rec[1, k, i])
+                        k += 1
+                        assert k < K
+                        E.append(rec[0, k, i])
+                        tau += rec[0, k, i]
+                    zW.append(Z[j - 1, i])
+                oW.append(len(zW)); oQ.append(len(zQ)); oE.append(len(E))
+            packed = dict(zW=np.array(zW), offW=np.array(oW, dtype=np.int64), zQ=np.array(zQ),
+                          offQ=np.array(oQ, dtype=np.int64), E=np.array(E), offE=np.array(oE, dtype=np.int64))
+            Rf, Rc = cls(lam=lam).payoff_replay(packed, l, M, arith="fast")
+            np.testing.assert_allclose(Pf, Rf, rtol=1e-12, atol=1e-10)
+            np.testing.assert_allclose(Pc, Rc, rtol=1e-12, atol=1e-10)
