@@ -444,3 +444,27 @@ def test_philox_mode_equals_replay_of_its_own_draws_merton(cuda_lib, lam):
             Rf, Rc = cls(lam=lam).payoff_replay(packed, l, M, arith="fast")
             np.testing.assert_allclose(Pf, Rf, rtol=1e-12, atol=1e-10)
             np.testing.assert_allclose(Pc, Rc, rtol=1e-12, atol=1e-10)
+
+
+def test_jump_stream_distributions(cuda_lib):
+    """Jump records: inter-arrival times ~ Exp(lam) (:1294), jump-size and sub-step normals ~ N(0,1),
+    mutually uncorrelated, and independent of the grid-step normals of the same path."""
+    import torch
+    from scipy import stats
+    lam, n, K = 2.5, 1 << 17, 8
+    for sampler in (_lib.SAMPLER_F32BM, _lib.SAMPLER_F64BM):
+        rec = torch.empty(3 * K * n, dtype=torch.float64, device="cuda")
+        _lib.check(cuda_lib.mlmcb_jump_probe(sampler, 7, 2, lam, 0, n, K, 0, 0, rec.data_ptr()))
+        torch.cuda.synchronize()
+        gap, zq, zw = rec.cpu().numpy().reshape(3, K * n)
+        N = gap.size
+        assert abs(gap.mean() * lam - 1) < 4 / np.sqrt(N)
+        assert abs(gap.var() * lam ** 2 - 1) < 4 * np.sqrt(8 / N)
+        assert stats.kstest(gap[:400000] * lam, "expon").pvalue > 1e-3
+        assert gap.min() > 0
+        for z in (zq, zw):
+            assert abs(z.mean()) < 4 / np.sqrt(N) and abs(z.var() - 1) < 4 * np.sqrt(2 / N)
+        for a, b in ((gap, zq), (gap, zw), (zq, zw)):
+            assert abs(np.corrcoef(a, b)[0, 1]) < 4 / np.sqrt(N)
+        grid = _probe_normals(cuda_lib, sampler, 7, 2, 0, n, K).reshape(-1)
+        assert abs(np.corrcoef(grid, zw)[0, 1]) < 4 / np.sqrt(N)
