@@ -124,6 +124,10 @@ int mlmcb_replay_merton(const mlmcb_params* p, int payoff, int l, int M, uint64_
  * step < n_steps, for global path ids path_offset.. at level l.  For distribution tests.    */
 int mlmcb_sampler_probe(int sampler, uint64_t seed, int l, uint64_t path_offset, uint64_t n_paths,
                         uint64_t n_steps, int device, void* cuda_stream, double* d_out);
+/* Same for the coarsest GBM levels (n_steps = 1 or 2 fine steps per path), where neighbouring path ids
+ * share one Philox block: d_out[step*n_paths + path].                                                 */
+int mlmcb_packed_probe(int sampler, uint64_t seed, int l, int n_steps, uint64_t path_offset, uint64_t n_paths,
+                       int device, void* cuda_stream, double* d_out);
 /* The jump-stream records the Philox-mode Merton kernels use: d_out[3][n_records][n_paths] =
  * inter-arrival times (scaled by 1/lam), jump-size normals, Brownian normals of the sub-step ending at
  * each jump.  With mlmcb_sampler_probe this lets a test rebuild the exact draw streams of a Philox-mode

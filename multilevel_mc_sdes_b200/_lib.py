@@ -48,6 +48,7 @@ SIGNATURES = {
     "mlmcb_replay_merton": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.c_int, _u64, _vp, _vp, _vp, _vp,
                                       _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "mlmcb_sampler_probe": (C.c_int, [C.c_int, _u64, C.c_int, _u64, _u64, _u64, C.c_int, _vp, _vp]),
+    "mlmcb_packed_probe": (C.c_int, [C.c_int, _u64, C.c_int, C.c_int, _u64, _u64, C.c_int, _vp, _vp]),
     "mlmcb_jump_probe": (C.c_int, [C.c_int, _u64, C.c_int, C.c_double, _u64, _u64, _u64, C.c_int, _vp, _vp]),
     "mlmcb_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "mlmcb_pipe_probe": (C.c_int, [C.c_int, C.c_int, _dp, C.POINTER(C.c_float)]),

@@ -547,6 +547,28 @@ int mlmcb_sampler_probe(int sampler, uint64_t seed, int l, uint64_t path_offset,
     return 0;
 }
 
+int mlmcb_packed_probe(int sampler, uint64_t seed, int l, int n_steps, uint64_t path_offset, uint64_t n_paths,
+                       int device, void* cuda_stream, double* d_out) {
+    if (!d_out) return fail(MLMCB_EINVAL, "d_out is NULL");
+    if (n_steps != 1 && n_steps != 2) return fail(MLMCB_EINVAL, "packed levels have 1 or 2 fine steps, not %d", n_steps);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    mlmcb_params p;
+    memset(&p, 0, sizeof p);
+    p.X0 = 1; p.K = 1; p.T = 1; p.sig = 1;
+    LevelConsts C;
+    if (int rc = make_consts(&p, MLMCB_GBM, MLMCB_EURO, 0, 2, n_paths, seed, path_offset, &C)) return rc;
+    C.ctr3_tag = (uint32_t)l << 16;
+    if (n_paths == 0) return 0;
+    const int grid = (int)((n_paths + kThreads - 1) / kThreads);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (sampler == MLMCB_SAMPLER_F32BM) packed_probe_kernel<SAMP_F32BM><<<grid, kThreads, 0, st>>>(C, n_steps, d_out);
+    else if (sampler == MLMCB_SAMPLER_F64BM) packed_probe_kernel<SAMP_F64BM><<<grid, kThreads, 0, st>>>(C, n_steps, d_out);
+    else return fail(MLMCB_EINVAL, "unknown sampler %d", sampler);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int mlmcb_jump_probe(int sampler, uint64_t seed, int l, double lam, uint64_t path_offset, uint64_t n_paths,
                      uint64_t n_records, int device, void* cuda_stream, double* d_out) {
     if (!d_out) return fail(MLMCB_EINVAL, "d_out is NULL");

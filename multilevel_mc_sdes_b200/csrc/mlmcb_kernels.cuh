@@ -1392,6 +1392,23 @@ __global__ void jump_probe_kernel(const __grid_constant__ LevelConsts C, ull n_r
     }
 }
 
+// The normals of the coarsest levels (1 or 2 fine steps per path), where 4 or 2 neighbouring global
+// path ids share one Philox block of the STREAM_PACK stream: out[step*n_paths + path].
+template <int SAMP>
+__global__ void packed_probe_kernel(const __grid_constant__ LevelConsts C, int nsteps, double* out) {
+    const ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_paths) return;
+    const int per = nsteps == 1 ? 4 : 2;
+    const ull pid = C.path_offset + i;
+    double z[4];
+    PhiloxSource<double, SAMP>{C, pid / per}.load4_stream(STREAM_PACK, 0, z);
+    const int base = (int)(pid % per) * nsteps;
+    for (int s = 0; s < nsteps; ++s) {
+        const int k = base + s;
+        out[(ull)s * C.n_paths + i] = k == 0 ? z[0] : k == 1 ? z[1] : k == 2 ? z[2] : z[3];
+    }
+}
+
 template <int SAMP>
 __global__ void sampler_probe_kernel(const __grid_constant__ LevelConsts C, ull n_steps, double* out) {
     const ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x;

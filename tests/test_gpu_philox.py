@@ -468,3 +468,25 @@ def test_jump_stream_distributions(cuda_lib):
             assert abs(np.corrcoef(a, b)[0, 1]) < 4 / np.sqrt(N)
         grid = _probe_normals(cuda_lib, sampler, 7, 2, 0, n, K).reshape(-1)
         assert abs(np.corrcoef(grid, zw)[0, 1]) < 4 / np.sqrt(N)
+
+
+@pytest.mark.parametrize("sampler", ["f32bm", "f64bm"])
+def test_packed_levels_equal_replay_of_their_own_draws(cuda_lib, sampler):
+    """l = 0 (hand-specialised loop, 4 ids per Philox block) and M=2, l=1 (2 ids per block): the normals
+    from the packed probe replayed through the parity-checked path give the same per-path payoffs."""
+    import torch
+    code = _lib.SAMPLER_F32BM if sampler == "f32bm" else _lib.SAMPLER_F64BM
+    for cls in (mm.Euro_GBM, mm.Asian_GBM, mm.Lookback_GBM, mm.Digital_GBM):
+        for l, M in ((0, 2), (0, 4), (0, 3), (1, 2)):
+            n, off, seed = 1003, 5, 9
+            nsteps = M ** l
+            opt = cls(seed=seed, sampler=sampler)
+            opt._next_path[l] = off
+            Pf, Pc = opt.payoff(n, l, M)
+            out = torch.empty(nsteps * n, dtype=torch.float64, device="cuda")
+            _lib.check(cuda_lib.mlmcb_packed_probe(code, seed, l, nsteps, off, n, 0, 0, out.data_ptr()))
+            torch.cuda.synchronize()
+            Z = out.cpu().numpy().reshape(nsteps, n)
+            Rf, Rc = cls().payoff_replay(Z, l, M, arith="fast")
+            np.testing.assert_allclose(Pf, Rf, rtol=1e-13, atol=1e-11)
+            np.testing.assert_allclose(Pc, Rc, rtol=1e-13, atol=1e-11)
