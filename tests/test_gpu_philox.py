@@ -392,6 +392,15 @@ def test_philox_mode_equals_replay_of_its_own_draws_gbm(cuda_lib, sampler):
             Rf, Rc = cls(scheme=scheme).payoff_replay(Z, l, M, arith="fast")
             np.testing.assert_allclose(Pf, Rf, rtol=1e-13, atol=1e-11)
             np.testing.assert_allclose(Pc, Rc, rtol=1e-13, atol=1e-11)
+    # American put (its own path kernel, same grid-step stream)
+    for l in (0, 1, 4, 7):
+        opt = mm.Amer_GBM(seed=6, sampler=sampler)
+        opt._next_path[l] = 41
+        Pf, Pc = opt.payoff(700, l, 2)
+        Z = _probe_normals(cuda_lib, code, 6, l, 41, 700, 2 ** l)
+        Rf, Rc = mm.Amer_GBM().payoff_replay(Z, l, 2, arith="fast")
+        np.testing.assert_allclose(Pf, Rf, rtol=1e-12, atol=1e-10)
+        np.testing.assert_allclose(Pc, Rc, rtol=1e-12, atol=1e-10)
     # antithetic
     opt = mm.Asian_GBM(seed=5, sampler=sampler)
     opt._next_path[3] = 77
