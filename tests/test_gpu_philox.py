@@ -499,3 +499,12 @@ def test_packed_levels_equal_replay_of_their_own_draws(cuda_lib, sampler):
             Rf, Rc = cls().payoff_replay(Z, l, M, arith="fast")
             np.testing.assert_allclose(Pf, Rf, rtol=1e-13, atol=1e-11)
             np.testing.assert_allclose(Pc, Rc, rtol=1e-13, atol=1e-11)
+
+
+def test_torch_custom_op(cuda_lib):
+    import torch
+    from multilevel_mc_sdes_b200 import torch_ops
+    opt = mm.Lookback_GBM(seed=3)
+    want = mm.Lookback_GBM(seed=3).looper(100_000, 3, 4, False)
+    got = torch.ops.mlmcb.level_sums(torch_ops.option_params(opt), opt._model, opt._payoff_kind, 3, 4, 100_000, 3, 0, 0, 0)
+    assert got.is_cuda and np.array_equal(got.cpu().numpy(), want)
