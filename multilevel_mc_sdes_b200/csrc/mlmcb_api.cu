@@ -6,9 +6,11 @@
 #include "mlmcb_kernels.cuh"
 
 #include <math.h>
+#include <map>
 #include <mutex>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 using namespace mlmcb;
@@ -75,6 +77,8 @@ int ipow_checked(int M, int l, ull* out) {
 
 // The per-launch constants.  Each reference-order scalar is one IEEE double operation per
 // Python operator, in Python's evaluation order (citations: /root/reference/MLMC_RSCAM.py).
+uint32_t run_blocks_for(ull nsteps);
+
 int make_consts(const mlmcb_params* p, int model, int payoff, int l, int M, ull n_paths, ull seed,
                 ull path_offset, LevelConsts* C) {
     if (!p) return fail(MLMCB_EINVAL, "params is NULL");
@@ -119,6 +123,7 @@ int make_consts(const mlmcb_params* p, int model, int payoff, int l, int M, ull 
     C->avg_wf = C->dt / C->T; C->avg_wc = C->Mdt / C->T;
     C->poly_q4 = MLMCB_Q4; C->poly_c4 = MLMCB_C4;
     C->inv_blk_dt = 1.0 / (4.0 * C->dt);
+    C->run_blocks = run_blocks_for(C->nsteps);
     // fp64 sampler: sin(pi h)/h and cos(pi h) in h^2 (tools/gen_trig_poly.py), fdlibm log coefficients
     static const double dq[9] = {0x1.921fb54442d18p+1, -0x1.4abbce625be52p+2, 0x1.466bc6775aa7dp+1, -0x1.32d2cce627c86p-1,
                                  0x1.5078348551854p-4, -0x1.e3074dfaf87afp-8, 0x1.e8f3675ee37ddp-12, -0x1.6f7acdb8f6580p-16,
@@ -145,8 +150,35 @@ int mt_of(int M) { return M == 2 ? 2 : M == 4 ? 4 : 0; }
 
 typedef void (*LevelKernel)(const LevelConsts, double*, unsigned*, double*, double*, double*);
 
+// Merton levels below this many fine steps run the event-driven kernel (mjd_flat_kernel), the rest the
+// block-uniform one; MLMCB_MJD_FLAT_BELOW / MLMCB_MJD_RUN_BLOCKS in the environment override (tuning).
+ull flat_below() {
+    static const ull v = [] {
+        const char* e = getenv("MLMCB_MJD_FLAT_BELOW");
+        return e ? strtoull(e, nullptr, 10) : (ull)MLMCB_MJD_FLAT_BELOW;
+    }();
+    return v;
+}
+uint32_t run_blocks_for(ull nsteps) {
+    static const long forced = [] {
+        const char* e = getenv("MLMCB_MJD_RUN_BLOCKS");
+        return e ? strtol(e, nullptr, 10) : 0L;
+    }();
+    if (forced > 0) return (uint32_t)forced;
+    // a lane waits about half a run per event, an event phase costs about as much as 20 fine steps
+    const double r = sqrt((double)nsteps * 20.0) / 4.0;
+    return r < 4.0 ? 4u : r > 4096.0 ? 4096u : (uint32_t)r;
+}
+
 template <typename R, int MODEL, int FN, int SAMP, int SCH>
-LevelKernel pick_mt(int mt) {
+LevelKernel pick_mt(int mt, bool flat) {
+    if (MODEL == 1 && flat) {
+        switch (mt) {
+        case 2: return mjd_flat_kernel<R, FN, 2, SAMP, SCH>;
+        case 4: return mjd_flat_kernel<R, FN, 4, SAMP, SCH>;
+        default: return mjd_flat_kernel<R, FN, 0, SAMP, SCH>;
+        }
+    }
     switch (mt) {
     case 2: return level_kernel<R, MODEL, FN, 2, SAMP, SCH>;
     case 4: return level_kernel<R, MODEL, FN, 4, SAMP, SCH>;
@@ -154,25 +186,26 @@ LevelKernel pick_mt(int mt) {
     }
 }
 template <typename R, int MODEL, int SAMP, int SCH>
-LevelKernel pick_fn(int fn, int mt) {
+LevelKernel pick_fn(int fn, int mt, bool flat) {
     switch (fn) {
-    case FN_AVG: return pick_mt<R, MODEL, FN_AVG, SAMP, SCH>(mt);
-    case FN_MIN: return pick_mt<R, MODEL, FN_MIN, SAMP, SCH>(mt);
-    default: return pick_mt<R, MODEL, FN_FINAL, SAMP, SCH>(mt);
+    case FN_AVG: return pick_mt<R, MODEL, FN_AVG, SAMP, SCH>(mt, flat);
+    case FN_MIN: return pick_mt<R, MODEL, FN_MIN, SAMP, SCH>(mt, flat);
+    default: return pick_mt<R, MODEL, FN_FINAL, SAMP, SCH>(mt, flat);
     }
 }
 template <typename R, int SAMP, int SCH = SCH_EM>
-LevelKernel pick_model(int model, int fn, int mt) {
-    return model == MLMCB_GBM ? pick_fn<R, 0, SAMP, SCH>(fn, mt) : pick_fn<R, 1, SAMP, SCH>(fn, mt);
+LevelKernel pick_model(int model, int fn, int mt, bool flat) {
+    return model == MLMCB_GBM ? pick_fn<R, 0, SAMP, SCH>(fn, mt, false) : pick_fn<R, 1, SAMP, SCH>(fn, mt, flat);
 }
-LevelKernel pick_kernel(int model, int payoff, int M, int flags) {
+LevelKernel pick_kernel(int model, int payoff, int M, int flags, ull nsteps) {
     const int fn = fn_of(payoff), mt = mt_of(M), samp = flags & MLMCB_SAMPLER_MASK;
-    if (flags & MLMCB_MILSTEIN) return pick_model<double, SAMP_F32BM, SCH_MILSTEIN>(model, fn, mt);
+    const bool flat = model == MLMCB_MERTON && nsteps < flat_below();
+    if (flags & MLMCB_MILSTEIN) return pick_model<double, SAMP_F32BM, SCH_MILSTEIN>(model, fn, mt, flat);
     if (flags & MLMCB_FP32_PATHS)
-        return samp == MLMCB_SAMPLER_F64BM ? pick_model<float, SAMP_F64BM>(model, fn, mt)
-                                           : pick_model<float, SAMP_F32BM>(model, fn, mt);
-    return samp == MLMCB_SAMPLER_F64BM ? pick_model<double, SAMP_F64BM>(model, fn, mt)
-                                       : pick_model<double, SAMP_F32BM>(model, fn, mt);
+        return samp == MLMCB_SAMPLER_F64BM ? pick_model<float, SAMP_F64BM>(model, fn, mt, flat)
+                                           : pick_model<float, SAMP_F32BM>(model, fn, mt, flat);
+    return samp == MLMCB_SAMPLER_F64BM ? pick_model<double, SAMP_F64BM>(model, fn, mt, flat)
+                                       : pick_model<double, SAMP_F32BM>(model, fn, mt, flat);
 }
 
 // Launch geometry: a grid-stride loop over paths.  The grid never exceeds the number of
@@ -183,8 +216,25 @@ int geometry(K kernel, int dev, ull n_paths, int* grid, int* max_blocks_out) {
     DeviceInfo* d;
     if (int rc = device_info(dev, &d)) return rc;
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
-    if (per_sm < 1) per_sm = 1;
+    {
+        // per (device, kernel), once: kernels that park jump records in shared memory ask for the
+        // large carve-out, so the occupancy computed here is the one the launch gets
+        static std::mutex mu;
+        static std::map<std::pair<int, const void*>, int> seen;
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = seen.find({dev, (const void*)kernel});
+        if (it == seen.end()) {
+            cudaFuncAttributes fa;
+            CU(cudaFuncGetAttributes(&fa, kernel));
+            if (fa.sharedSizeBytes > 4096)
+                CU(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
+            if (per_sm < 1) per_sm = 1;
+            seen[{dev, (const void*)kernel}] = per_sm;
+        } else {
+            per_sm = it->second;
+        }
+    }
     const ull max_threads = (ull)d->sms * per_sm * kThreads;
     const ull per_thread = (n_paths + max_threads - 1) / max_threads;
     const ull threads = per_thread ? (n_paths + per_thread - 1) / per_thread : 1;
@@ -292,7 +342,7 @@ int level_sums_impl(const mlmcb_params* p, int model, int payoff, int l, int M, 
     }
     if (n_paths == 0) { CU(cudaMemsetAsync(d_out7, 0, 7 * sizeof(double), st)); return 0; }
     if (payoff == MLMCB_AMERICAN) return amer_level_sums(C, flags, device, st, d_out7, d_Pf, d_Pc);
-    LevelKernel k = (flags & MLMCB_ANTITHETIC) ? pick_anti_kernel(payoff, M, flags) : pick_kernel(model, payoff, M, flags);
+    LevelKernel k = (flags & MLMCB_ANTITHETIC) ? pick_anti_kernel(payoff, M, flags) : pick_kernel(model, payoff, M, flags, C.nsteps);
     int grid = 1;
     if (int rc = geometry(k, device, n_paths, &grid, nullptr)) return rc;
     Workspace w;
@@ -602,7 +652,7 @@ int mlmcb_launch_geometry(int model, int payoff, int M, int flags, int device, i
     if (payoff == MLMCB_AMERICAN) {
         if (int rc = geometry(amer_level_kernel<SAMP_F32BM>, device, ~0ull >> 16, &grid, &mb)) return rc;
     } else {
-        LevelKernel k = (flags & MLMCB_ANTITHETIC) ? pick_anti_kernel(payoff, M, flags) : pick_kernel(model, payoff, M, flags);
+        LevelKernel k = (flags & MLMCB_ANTITHETIC) ? pick_anti_kernel(payoff, M, flags) : pick_kernel(model, payoff, M, flags, ~0ull);
         if (int rc = geometry(k, device, ~0ull >> 16, &grid, &mb)) return rc;
     }
     if (threads_per_block) *threads_per_block = kThreads;

@@ -35,6 +35,21 @@
 #ifndef MLMCB_MINBLOCKS_MJD
 #define MLMCB_MINBLOCKS_MJD 6
 #endif
+#ifndef MLMCB_MJD_UNROLLED
+#define MLMCB_MJD_UNROLLED 1
+#endif
+#ifndef MLMCB_MJD_LAZY_STEPS
+#define MLMCB_MJD_LAZY_STEPS 0
+#endif
+#ifndef MLMCB_MJD_FLAT_BELOW
+#define MLMCB_MJD_FLAT_BELOW 128    // Merton: levels with fewer fine steps run the event-driven kernel
+#endif
+#ifndef MLMCB_MINBLOCKS_FLAT
+#define MLMCB_MINBLOCKS_FLAT 5      // event-driven Merton kernel: 96 registers
+#endif
+#ifndef MLMCB_JUMP_RECS
+#define MLMCB_JUMP_RECS 4           // Merton: jump records produced up front per path (shared memory, 192 B per thread)
+#endif
 #ifndef MLMCB_UNROLL_MJD
 #define MLMCB_UNROLL_MJD 2
 #endif
@@ -81,6 +96,7 @@ struct LevelConsts {
     // Merton
     double lam, inv_lam, jm, js;
     double inv_blk_dt;              // 1/(4*dt): jump time -> block index
+    uint32_t run_blocks;            // event-driven Merton walk: iterations of the advance phase between event phases
     double* raw;                    // optional [rows][n_paths] path-function outputs (Option.path), else NULL
     double r, boundary_c, amer_cneg;  // American put: rate, boundary constant, -2/(sig^2 dt); discounting inside the path, exercise boundary constant
     // Milstein scheme (ExampleUsages.ipynb cell 1: + 0.5*X*sig**2*(dW**2-dt))
@@ -741,14 +757,23 @@ struct JD {
     }
 
     // one pass of the `while tau<tn` body :458-474 (the caller advances tau afterwards)
+    __device__ __forceinline__ static R jump_size(const LevelConsts& C, R zq) {                          // :462
+        if (AR == AR_EXACT) return (R)__dsub_rn(exp(__dadd_rn(C.jm, __dmul_rn(C.js, (double)zq))), 1.0);
+        return (R)(exp(fma(C.js, (double)zq, C.jm)) - 1.0);
+    }
     __device__ __forceinline__ void jump(const LevelConsts& C, double tau, R zw, R zq) {
+        jump_dJ(C, tau, zw, jump_size(C, zq));
+    }
+    __device__ __forceinline__ void jump_dJ(const LevelConsts& C, double tau, R zw, R dJ) {
         double dt = tau - tf;                                            // :458
-        dtc += dt;                                                       // :459
         R dWf = mul(zw, (R)(AR == AR_EXACT ? sqrt(dt) : (dt > 0.0 ? sqrt_pos(dt) : 0.0)));   // :460
+        jump_pre(C, dt, dWf, dJ);
+        tf = tau; tc = tau;                                              // :472-473
+    }
+    // the same with the step length and Brownian increment already formed (clocks untouched)
+    __device__ __forceinline__ void jump_pre(const LevelConsts& C, double dt, R dWf, R dJ) {
+        dtc += dt;                                                       // :459
         dWc = add(dWc, dWf);                                             // :461
-        R dJ;
-        if (AR == AR_EXACT) dJ = (R)__dsub_rn(exp(__dadd_rn(C.jm, __dmul_rn(C.js, (double)zq))), 1.0);   // :462
-        else dJ = (R)(exp(fma(C.js, (double)zq, C.jm)) - 1.0);
         if (FN == FN_AVG) {                                              // :532-540
             Gf = add(Gf, half_area(Sf, dt));
             Sf = add(Sf, dx(C, Sf, dt, dWf));
@@ -765,15 +790,19 @@ struct JD {
             Sc = add(Sc, add(d, mul(add(d, Sc), dJ)));
             if (FN == FN_MIN) { Gf = min_<R>(Gf, Sf); Gc = min_<R>(Gc, Sc); }   // :621-622
         }
-        dWc = (R)0; dtc = 0.0; tf = tau; tc = tau;                       // :470-473
+        dWc = (R)0; dtc = 0.0;                                           // :470-471
     }
 
     // the remainder step up to the grid time tn :477-482 (+ :637).  `whole` (production policy
     // only): no jump fell inside this fine step, so dt is the grid step and its root is known.
     __device__ __forceinline__ void grid(const LevelConsts& C, double tn, R zw, bool whole = false) {
         const double dt = whole ? C.dt : tn - tf;                        // :477
-        dtc += dt;                                                       // :478
         R dWf = mul(zw, (R)(whole ? C.sqrt_dt : (AR == AR_EXACT ? sqrt(dt) : (dt > 0.0 ? sqrt_pos(dt) : 0.0))));   // :479
+        grid_pre(C, dt, dWf);
+        tf = tn;                                                         // :482
+    }
+    __device__ __forceinline__ void grid_pre(const LevelConsts& C, double dt, R dWf) {
+        dtc += dt;                                                       // :478
         dWc = add(dWc, dWf);                                             // :480
         if (FN == FN_AVG) {                                              // :554-556
             Gf = add(Gf, half_area(Sf, dt));
@@ -783,7 +812,6 @@ struct JD {
             Sf = add(Sf, dx(C, Sf, dt, dWf));                            // :481
             if (FN == FN_MIN) Gf = min_<R>(Gf, Sf);                      // :637
         }
-        tf = tn;                                                         // :482
     }
 
     // coarse path catches up at a coarse grid time :483-487
@@ -831,51 +859,123 @@ __device__ __forceinline__ void jump_draws(const LevelConsts& C, ull pid, uint32
 
 // Merton coupled path, Philox mode.  A 4-step block with no jump inside is exactly a GBM block
 // with drift c = r - lam*J_bar; such blocks run in a tight loop identical to the GBM one, up to
-// the block that holds the next jump time (an integer compare per block).  A block that contains
-// a jump runs the general jump-adapted code above (rare: lam*T*4/nsteps per path), not unrolled.
+// the block that holds the next jump (an integer compare per block).  A block that contains a
+// jump runs the jump-adapted steps (rare: lam*T*4/nsteps per path).
+//
+// Jump records.  The lanes of a warp reach their jumps in different blocks, one lane at a time,
+// so whatever a jump costs inside the block is paid 32 times per warp.  Nearly all of it - the
+// Philox call, the fp64 log of the inter-arrival time, the Box-Muller pair, the fp64 exp of the
+// jump size, the square roots of the two partial steps either side of the jump, and the search
+// for the fine step the jump time falls into - does not depend on the path state.  So the first
+// kJumpRecs records of every path are produced at the path start with all lanes active and
+// parked in shared memory (one column per thread); the divergent block only applies them (a
+// dozen FMAs).  A path with more jumps than that (P = 1.9 % at lam*T = 1) produces the further
+// ones in place with the same code, reusing the slots.  Values are those of the reference's
+// control flow (:455-487): a jump belongs to the first step j with tau < j*dt, its partial step
+// starts at the previous jump if that fell in the same step, else at (j-1)*dt.
+constexpr int kJumpRecs = MLMCB_JUMP_RECS;          // power of two
+enum { REC_D1 = 0, REC_DW1, REC_DJ, REC_D2, REC_SQ2, REC_STEP, REC_FIELDS };
+
 template <typename R, int FN, int SAMP, int SCH>
 struct MjdWalker {
     const LevelConsts& C;
     ull pid;
+    double* rec;        // this thread's column of the block's record store: rec[(REC_FIELDS*slot + field)*kThreads]
     JD<R, FN, AR_FAST, SCH> st;
-    uint32_t jk;
-    double tau;
-    R zq, zwj;
+    uint32_t jk;        // index of the next jump of this path
+    uint32_t jp;        // records produced so far
+    double jnext;       // the fine step (1-based, integer-valued) that jump falls into; nsteps+1: after the end
+    double tlast;       // time and step of the newest record produced
+    double jlast;
     int cm;
 
+    __device__ __forceinline__ double& slot(uint32_t k, int field) const {
+        return rec[(REC_FIELDS * (k & (kJumpRecs - 1)) + field) * kThreads];
+    }
+    // the next record from the jump stream
+    __device__ __forceinline__ void produce() {
+        double gap;
+        R zq, zw;
+        jump_draws<R, SAMP>(C, pid, jp, gap, zq, zw);
+        const double t = tlast + gap;                                    // :454 / :474
+        const double nd = (double)C.nsteps;
+        double j = nd + 1.0;
+        if (t < nd * C.dt) {                                             // first j with t < j*dt  (:457)
+            j = floor(t * C.inv_blk_dt * 4.0) + 1.0;
+            j = fmin(j, nd);
+#pragma unroll 1
+            while (j > 1.0 && t < (j - 1.0) * C.dt) j -= 1.0;
+#pragma unroll 1
+            while (!(t < j * C.dt)) j += 1.0;
+        }
+        const double d1 = t - (j == jlast ? tlast : (j - 1.0) * C.dt);   // :458
+        const double d2 = j * C.dt - t;                                  // :477, if no further jump in step j
+        slot(jp, REC_D1) = d1;
+        slot(jp, REC_DW1) = (double)(zw * (R)(d1 > 0.0 ? sqrt_pos(d1) : 0.0));   // :460
+        slot(jp, REC_DJ) = (double)JD<R, FN, AR_FAST, SCH>::jump_size(C, zq);    // :462
+        slot(jp, REC_D2) = d2;
+        slot(jp, REC_SQ2) = d2 > 0.0 ? sqrt_pos(d2) : 0.0;               // :479
+        slot(jp, REC_STEP) = j;
+        tlast = t; jlast = j;
+        ++jp;
+    }
     __device__ __forceinline__ void start() {
         st.init(C);
-        jk = 0; cm = 0;
-        double gap;
-        jump_draws<R, SAMP>(C, pid, jk, gap, zq, zwj);
-        tau = gap;                                                       // :454
+        jk = jp = 0; cm = 0;
+        tlast = 0.0; jlast = 0.0;
+        // paths of a few steps reach their jumps together anyway: one record, the rest on demand
+        const uint32_t ahead = C.nsteps <= MLMCB_MJD_LAZY_STEPS ? 1u : (uint32_t)kJumpRecs;
+        const double nd = (double)C.nsteps;
+#pragma unroll 1
+        while (jp < ahead) {
+            produce();
+            if (__all_sync(__activemask(), jlast > nd)) break;           // nobody will look further
+        }
+        jnext = slot(0, REC_STEP);
     }
-    // steps j0+1 .. j0+cnt through the reference's control flow (:455-487)
-    __device__ __forceinline__ void slow_block(ull j0, int cnt, R z0, R z1, R z2, R z3) {
+    // fine step j, which holds the next jump: all its jumps, then the rest of the step  (:457-482)
+    __device__ __forceinline__ void jump_step(double j, R z) {
+        double d2, sq2;
+        do {
+            st.jump_pre(C, slot(jk, REC_D1), (R)slot(jk, REC_DW1), (R)slot(jk, REC_DJ));
+            d2 = slot(jk, REC_D2); sq2 = slot(jk, REC_SQ2);
+            ++jk;
+            if (jk == jp) produce();                                     // record jk-1 was the newest one
+            jnext = slot(jk, REC_STEP);
+        } while (jnext == j);
+        st.grid_pre(C, d2, z * (R)sq2);
+    }
+    __device__ __forceinline__ void whole_step(R z) { st.grid_pre(C, C.dt, z * (R)C.sqrt_dt); }
+
+    // steps j0+1 .. j0+cnt  (:455-487), any M
+    template <int MT>
+    __device__ __forceinline__ void steps(double j0, int cnt, R z0, R z1, R z2, R z3) {
 #pragma unroll 1
         for (int k = 0; k < cnt; ++k) {
-            const R zk = k == 0 ? z0 : k == 1 ? z1 : k == 2 ? z2 : z3;
-            const double tn = (double)(j0 + k + 1) * C.dt;               // :456
-            bool whole = true;
-            while (tau < tn) {                                           // :457
-                st.jump(C, tau, zwj, zq);
-                ++jk;
-                double gap;
-                jump_draws<R, SAMP>(C, pid, jk, gap, zq, zwj);
-                tau += gap;                                              // :474
-                whole = false;
-            }
-            st.grid(C, tn, zk, whole);
-            if (++cm == C.M) { cm = 0; st.coarse(C, tn); }               // :483
+            const R zk = (k & 2) ? ((k & 1) ? z3 : z2) : ((k & 1) ? z1 : z0);
+            const double j = j0 + (double)(k + 1);                       // :456
+            if (jnext == j) jump_step(j, zk);
+            else whole_step(zk);
+            if (MT == 2) { if (k & 1) st.coarse(C, 0.0); }
+            else if (MT == 4) { if (k == 3) st.coarse(C, 0.0); }
+            else if (++cm == C.M) { cm = 0; st.coarse(C, 0.0); }         // :483
         }
     }
-    // number of leading whole blocks [0, jb) that end at or before tau (no jump inside), <= cap
+    // steps j0+1 .. j0+4 with the coarse steps at their compile-time places (M = 2 or 4)
+    template <int MT>
+    __device__ __forceinline__ void jump_block4(double j0, const R z[4]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double j = j0 + (double)(k + 1);
+            if (jnext == j) jump_step(j, z[k]);
+            else whole_step(z[k]);
+            if (MT == 2 ? (k & 1) : k == 3) st.coarse(C, 0.0);
+        }
+    }
+    // number of leading whole blocks [0, jb) with no jump inside, <= cap
     __device__ __forceinline__ uint32_t jump_block(uint32_t cap) const {
-        const double q = tau * C.inv_blk_dt;
-        uint32_t jb = q >= (double)cap ? cap : (uint32_t)q;
-        // agree exactly with the slow path's test `tau < (double)j*dt` at the block boundary
-        while (jb > 0 && tau < (double)(4ull * jb) * C.dt) --jb;
-        return jb;
+        const double q = (jnext - 1.0) * 0.25;
+        return q >= (double)cap ? cap : (uint32_t)q;
     }
 };
 
@@ -929,10 +1029,10 @@ __device__ __forceinline__ void mjd_fast_block(const LevelConsts& C, const StepC
 }
 
 template <typename R, int FN, int MT, int SAMP, int SCH>
-__device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid,
+__device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid, double* rec,
                                                 double& vf, double& vc, double& gf, double& gc) {
     PhiloxSource<R, SAMP> src{C, pid};
-    MjdWalker<R, FN, SAMP, SCH> w{C, pid};
+    MjdWalker<R, FN, SAMP, SCH> w{C, pid, rec};
     w.start();
     const StepCoef<R, SCH> co(C);
     const uint32_t nfull = (uint32_t)(C.nsteps >> 2);
@@ -959,11 +1059,10 @@ __device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid,
             if (b < jb) {
                 mjd_fast_block<R, FN, MT, SCH>(C, co, z, Xf, Xc, Gf, Gc);
             } else {
-                // the block that holds a jump (or every block when M is generic): state is clean at
-                // the block start, so the walker restarts its clocks there
+                // the block that holds a jump (or every block when M is generic)
                 w.st.Sf = Xf; w.st.Sc = Xc; w.st.Gf = Gf; w.st.Gc = Gc;
-                if (MT != 0) w.st.tf = w.st.tc = (double)(4ull * b) * C.dt;
-                w.slow_block(4ull * b, 4, z[0], z[1], z[2], z[3]);
+                if (MT != 0 && MLMCB_MJD_UNROLLED) w.template jump_block4<MT>((double)(4ull * b), z);
+                else w.template steps<MT>((double)(4ull * b), 4, z[0], z[1], z[2], z[3]);
                 Xf = w.st.Sf; Xc = w.st.Sc; Gf = w.st.Gf; Gc = w.st.Gc;
                 if (MT != 0) jb = w.jump_block(nfull);
             }
@@ -975,10 +1074,195 @@ __device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid,
     if (rem) {                           // l==0 (1 step), M=2,l=1 (2 steps), odd M
         R z[4];
         src.load4(nfull, z);
-        if (MT != 0) w.st.tf = w.st.tc = (double)(4ull * nfull) * C.dt;
-        w.slow_block(4ull * nfull, rem, z[0], z[1], z[2], z[3]);
+        w.template steps<MT>((double)(4ull * nfull), rem, z[0], z[1], z[2], z[3]);
     }
     w.st.outputs(C, vf, vc, gf, gc);
+}
+
+// ------------------------------------------------------------------------------------------
+// Merton paths of one or two fine steps (l = 0; M = 2, l = 1): the reference's control flow
+// (:455-487) as it stands - draw the next jump time, compare it with the grid time, take the
+// partial step, the jump and the next draw - with nothing prepared ahead.  All lanes of a warp
+// sit in the same step, so the jump loop is shared by the lanes that still have jumps left, and
+// a record is only worked out (exp, square root) if its jump happens.
+// ------------------------------------------------------------------------------------------
+template <typename R, int FN, int SAMP, int SCH>
+__device__ __forceinline__ void mjd_path_coarse(const LevelConsts& C, ull pid,
+                                                double& vf, double& vc, double& gf, double& gc) {
+    JD<R, FN, AR_FAST, SCH> st;
+    st.init(C);
+    R z[4];
+    PhiloxSource<R, SAMP>{C, pid}.load4(0, z);
+    uint32_t jk = 0;
+    int cm = 0;
+    double tau;
+    R zq, zwj;
+    jump_draws<R, SAMP>(C, pid, jk, tau, zq, zwj);                       // :454
+#pragma unroll 1
+    for (int k = 0; k < (int)C.nsteps; ++k) {
+        const R zk = (k & 2) ? ((k & 1) ? z[3] : z[2]) : ((k & 1) ? z[1] : z[0]);
+        const double tn = (double)(k + 1) * C.dt;                        // :456
+        bool whole = true;
+        while (tau < tn) {                                               // :457
+            st.jump(C, tau, zwj, zq);
+            ++jk;
+            double gap;
+            jump_draws<R, SAMP>(C, pid, jk, gap, zq, zwj);
+            tau += gap;                                                  // :474
+            whole = false;
+        }
+        st.grid(C, tn, zk, whole);
+        if (++cm == C.M) { cm = 0; st.coarse(C, tn); }                   // :483
+    }
+    st.outputs(C, vf, vc, gf, gc);
+}
+
+// ------------------------------------------------------------------------------------------
+// Merton, event-driven walk (levels up to a few thousand fine steps).
+// In the block-uniform walk above every lane of a warp is at the same fine step, so a block
+// that holds a jump of one lane is run for that lane alone: per warp and path, lam*T*32 serial
+// passes through the jump code.  That is noise against 4096 steps but most of the time at
+// 4..256 steps - where MLMC puts nearly all of its Merton samples.  Here the lanes are let go
+// of each other: every lane owns a queue of paths (the same ids, in the same order, as in the
+// grid-stride loop, so the sums are unchanged) and a position in its current path, and the
+// warp alternates between two phases that are each uniform in code:
+//   advance: every lane walks toward its own next event - jump-free 4-step blocks through the
+//            GBM-like block code, single steps inside the block that holds the event - for at
+//            most C.run_blocks iterations;
+//   event:   every lane that has reached its event handles it: apply the pending jump record
+//            (or finish the path, emit it and start the next one), then draw the next record.
+// The expensive part of a jump (Philox, log, Box-Muller, exp, square roots, step search) is thus
+// paid once per warp and event phase with nearly all lanes taking part, instead of once per lane.
+// A lane that reaches its event early idles until the phase ends; run_blocks bounds that wait.
+// ------------------------------------------------------------------------------------------
+template <typename R, int FN, int MT, int SAMP, int SCH>
+struct MjdFlat {
+    const LevelConsts& C;
+    JD<R, FN, AR_FAST, SCH> st;
+    ull pid;
+    ull s;              // fine steps completed
+    ull ev;             // steps to complete before the event: (step of the next jump) - 1, or nsteps at the path end
+    uint32_t jp;        // jump records drawn for this path
+    double tlast;       // time and step (1-based; nsteps+1: after the end) of the pending record
+    ull jlast;
+    double d1, d2, sq2; // the pending record: partial steps either side of the jump ...
+    R dW1, dJ;          // ... Brownian increment of the first one, jump size
+    R z[4];             // grid normals of block zb
+    uint32_t zb;
+    int cm;
+
+    __device__ __forceinline__ void produce() {
+        double gap;
+        R zq, zw;
+        jump_draws<R, SAMP>(C, pid, jp, gap, zq, zw);
+        ++jp;
+        const double t = tlast + gap;                                    // :454 / :474
+        const double nd = (double)C.nsteps;
+        double j = nd + 1.0;
+        if (t < nd * C.dt) {                                             // first j with t < j*dt  (:457)
+            j = fmin(floor(t * C.inv_blk_dt * 4.0) + 1.0, nd);
+#pragma unroll 1
+            while (j > 1.0 && t < (j - 1.0) * C.dt) j -= 1.0;
+#pragma unroll 1
+            while (!(t < j * C.dt)) j += 1.0;
+        }
+        const ull ji = (ull)j;
+        d1 = t - (ji == jlast ? tlast : (j - 1.0) * C.dt);               // :458
+        d2 = j * C.dt - t;                                               // :477, if no further jump in step j
+        dW1 = zw * (R)(d1 > 0.0 ? sqrt_pos(d1) : 0.0);                   // :460
+        dJ = JD<R, FN, AR_FAST, SCH>::jump_size(C, zq);                  // :462
+        sq2 = d2 > 0.0 ? sqrt_pos(d2) : 0.0;                             // :479
+        tlast = t; jlast = ji;
+        ev = ji - 1;                                                     // ji == nsteps+1 -> the path end
+    }
+    __device__ __forceinline__ void begin(ull id) {
+        pid = id;
+        st.init(C);
+        s = 0; jp = 0; cm = 0; zb = 0xffffffffu;
+        tlast = 0.0; jlast = 0;
+    }
+    __device__ __forceinline__ void coarse_after_step() {                // s already counts the step
+        if (MT == 2) { if (!(s & 1)) st.coarse(C, 0.0); }
+        else if (MT == 4) { if (!(s & 3)) st.coarse(C, 0.0); }
+        else if (++cm == C.M) { cm = 0; st.coarse(C, 0.0); }             // :483
+    }
+    __device__ __forceinline__ R zsel() const {
+        const int k = (int)(s & 3);
+        return (k & 2) ? ((k & 1) ? z[3] : z[2]) : ((k & 1) ? z[1] : z[0]);
+    }
+    // walk toward the event; on return the normals of the block that holds step s+1 are loaded
+    __device__ __forceinline__ void advance(const StepCoef<R, SCH>& co) {
+        uint32_t budget = C.run_blocks;
+        for (;;) {
+            const uint32_t blk = (uint32_t)(s >> 2);
+            if (zb != blk && s < C.nsteps) {
+                PhiloxSource<R, SAMP>{C, pid}.load4(blk, z);
+                zb = blk;
+            }
+            if (!(s < ev && budget)) break;
+            --budget;
+            if (MT != 0 && !(s & 3) && s + 4 <= ev) {
+                mjd_fast_block<R, FN, MT, SCH>(C, co, z, st.Sf, st.Sc, st.Gf, st.Gc);
+                s += 4;
+            } else {
+                st.grid_pre(C, C.dt, zsel() * (R)C.sqrt_dt);
+                ++s;
+                coarse_after_step();
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ void emit(const LevelConsts& C, ull i, double vf, double vc, double gf, double gc,
+                                     Sums7& acc, double* Pf_out, double* Pc_out);
+
+template <typename R, int FN, int MT, int SAMP, int SCH>
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64 : MLMCB_MINBLOCKS_FLAT)
+mjd_flat_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
+                double* out7, double* Pf_out, double* Pc_out) {
+    Sums7 acc;
+    acc.clear();
+    const ull stride = (ull)gridDim.x * blockDim.x;
+    ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    if (C.nsteps < 4) {
+        for (; i < C.n_paths; i += stride) {
+            double vf, vc, gf, gc;
+            mjd_path_coarse<R, FN, SAMP, SCH>(C, C.path_offset + i, vf, vc, gf, gc);
+            emit(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
+        }
+        grid_finish(acc, partials, ticket, out7);
+        return;
+    }
+    bool active = i < C.n_paths;
+    MjdFlat<R, FN, MT, SAMP, SCH> w{C};
+    const StepCoef<R, SCH> co(C);
+    if (active) { w.begin(C.path_offset + i); w.produce(); }
+    while (__any_sync(0xffffffffu, active)) {
+        if (active) w.advance(co);
+        if (active && w.s == w.ev) {
+            bool draw = true;
+            double d2o = 0.0, sq2o = 0.0;
+            const bool jump = w.jlast <= C.nsteps;
+            if (jump) {                                                  // the jump(s) of step s+1  (:457-474)
+                w.st.jump_pre(C, w.d1, w.dW1, w.dJ);
+                d2o = w.d2; sq2o = w.sq2;
+            } else {                                                     // path end
+                double vf, vc, gf, gc;
+                w.st.outputs(C, vf, vc, gf, gc);
+                emit(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
+                i += stride;
+                active = draw = i < C.n_paths;
+                if (active) w.begin(C.path_offset + i);
+            }
+            if (draw) w.produce();
+            if (jump && w.jlast != w.s + 1) {                            // no further jump in this step: finish it  (:477-482)
+                w.st.grid_pre(C, d2o, w.zsel() * (R)sq2o);
+                ++w.s;
+                w.coarse_after_step();
+            }
+        }
+    }
+    grid_finish(acc, partials, ticket, out7);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1205,6 +1489,19 @@ __device__ __forceinline__ void emit(const LevelConsts& C, ull i, double vf, dou
     }
 }
 
+// the block's jump-record store (Merton kernels only)
+template <int MODEL>
+struct JumpRecStore {
+    __device__ __forceinline__ static double* column() { return nullptr; }
+};
+template <>
+struct JumpRecStore<1> {
+    __device__ __forceinline__ static double* column() {
+        __shared__ double store[kJumpRecs * REC_FIELDS * kThreads];
+        return store + threadIdx.x;
+    }
+};
+
 template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH>
 __global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64 : (MODEL == 0 ? MLMCB_MINBLOCKS : MLMCB_MINBLOCKS_MJD))
 level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
@@ -1274,6 +1571,7 @@ level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* 
         grid_finish(acc, partials, ticket, out7);
         return;
     }
+    double* const rec = JumpRecStore<MODEL>::column();
     for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
         const ull pid = C.path_offset + i;
         double vf, vc, gf, gc;
@@ -1281,7 +1579,7 @@ level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* 
             PhiloxSource<R, SAMP> src{C, pid};
             gbm_path_fast<R, FN, MT, SCH>(C, src, vf, vc, gf, gc);
         } else {
-            mjd_path_philox<R, FN, MT, SAMP, SCH>(C, pid, vf, vc, gf, gc);
+            mjd_path_philox<R, FN, MT, SAMP, SCH>(C, pid, rec, vf, vc, gf, gc);
         }
         emit(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
     }
