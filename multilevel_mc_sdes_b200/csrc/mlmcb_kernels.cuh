@@ -1080,45 +1080,8 @@ __device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid, d
 }
 
 // ------------------------------------------------------------------------------------------
-// Merton paths of one or two fine steps (l = 0; M = 2, l = 1): the reference's control flow
-// (:455-487) as it stands - draw the next jump time, compare it with the grid time, take the
-// partial step, the jump and the next draw - with nothing prepared ahead.  All lanes of a warp
-// sit in the same step, so the jump loop is shared by the lanes that still have jumps left, and
-// a record is only worked out (exp, square root) if its jump happens.
-// ------------------------------------------------------------------------------------------
-template <typename R, int FN, int SAMP, int SCH>
-__device__ __forceinline__ void mjd_path_coarse(const LevelConsts& C, ull pid,
-                                                double& vf, double& vc, double& gf, double& gc) {
-    JD<R, FN, AR_FAST, SCH> st;
-    st.init(C);
-    R z[4];
-    PhiloxSource<R, SAMP>{C, pid}.load4(0, z);
-    uint32_t jk = 0;
-    int cm = 0;
-    double tau;
-    R zq, zwj;
-    jump_draws<R, SAMP>(C, pid, jk, tau, zq, zwj);                       // :454
-#pragma unroll 1
-    for (int k = 0; k < (int)C.nsteps; ++k) {
-        const R zk = (k & 2) ? ((k & 1) ? z[3] : z[2]) : ((k & 1) ? z[1] : z[0]);
-        const double tn = (double)(k + 1) * C.dt;                        // :456
-        bool whole = true;
-        while (tau < tn) {                                               // :457
-            st.jump(C, tau, zwj, zq);
-            ++jk;
-            double gap;
-            jump_draws<R, SAMP>(C, pid, jk, gap, zq, zwj);
-            tau += gap;                                                  // :474
-            whole = false;
-        }
-        st.grid(C, tn, zk, whole);
-        if (++cm == C.M) { cm = 0; st.coarse(C, tn); }                   // :483
-    }
-    st.outputs(C, vf, vc, gf, gc);
-}
-
-// ------------------------------------------------------------------------------------------
-// Merton, event-driven walk (levels up to a few thousand fine steps).
+// Merton, event-driven walk (levels of 2 .. MLMCB_MJD_FLAT_BELOW-1 fine steps; l = 0 has its own loop
+// in the kernel below).
 // In the block-uniform walk above every lane of a warp is at the same fine step, so a block
 // that holds a jump of one lane is run for that lane alone: per warp and path, lam*T*32 serial
 // passes through the jump code.  That is noise against 4096 steps but most of the time at
@@ -1224,11 +1187,41 @@ mjd_flat_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigne
     acc.clear();
     const ull stride = (ull)gridDim.x * blockDim.x;
     ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x;
-    if (C.nsteps < 4) {
-        for (; i < C.n_paths; i += stride) {
-            double vf, vc, gf, gc;
-            mjd_path_coarse<R, FN, SAMP, SCH>(C, C.path_offset + i, vf, vc, gf, gc);
-            emit(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
+    if (C.nsteps == 1) {
+        // l = 0: a path is its jumps and one closing step, every one of them "draw a record, step to
+        // min(jump time, T)".  Each lane runs that loop over its own queue of paths, so the warp never
+        // waits for the lane with the most jumps.  The closing step takes the Brownian normal of the
+        // record that overshoots T (that record's jump never happens, and its normal is independent of
+        // its arrival time), so a path of N jumps costs exactly N+1 Philox calls.
+        bool active = i < C.n_paths;
+        JD<R, FN, AR_FAST, SCH> st;
+        st.init(C);
+        double t = 0.0;
+        uint32_t k = 0;
+        const double tend = C.dt;                                        // (double)1 * dt, the grid time  :456
+        while (__any_sync(0xffffffffu, active)) {
+            if (active) {
+                double gap;
+                R zq, zw;
+                jump_draws<R, SAMP>(C, C.path_offset + i, k, gap, zq, zw);
+                const double tau = t + gap;                              // :454 / :474
+                const bool jump = tau < tend;                            // :457
+                const double d = (jump ? tau : tend) - t;                // :458 / :477
+                const R dW = zw * (R)(d > 0.0 ? sqrt_pos(d) : 0.0);      // :460 / :479
+                if (jump) {
+                    st.jump_pre(C, d, dW, JD<R, FN, AR_FAST, SCH>::jump_size(C, zq));
+                    t = tau; ++k;
+                } else {
+                    st.grid_pre(C, d, dW);
+                    double vf, vc, gf, gc;
+                    st.outputs(C, vf, vc, gf, gc);
+                    emit(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
+                    i += stride;
+                    active = i < C.n_paths;
+                    st.init(C);
+                    t = 0.0; k = 0;
+                }
+            }
         }
         grid_finish(acc, partials, ticket, out7);
         return;

@@ -419,7 +419,8 @@ def test_philox_mode_equals_replay_of_its_own_draws_merton(cuda_lib, lam):
     kernel against the straightforward replay loop."""
     import torch
     for cls in (mm.Euro_Merton, mm.Asian_Merton, mm.Lookback_Merton):
-        for l, M in ((0, 2), (1, 2), (3, 2), (3, 4), (2, 3), (5, 2)):
+        # 1 step: lane-queue loop; 2: lockstep; 8, 9, 32, 64: event-driven kernel; 128, 256: block-uniform kernel
+        for l, M in ((0, 2), (1, 2), (3, 2), (3, 4), (2, 3), (5, 2), (7, 2), (4, 4)):
             n, off, seed, K = 600, 999, 17, 64
             opt = cls(seed=seed, lam=lam)
             opt._next_path[l] = off
@@ -446,7 +447,8 @@ def test_philox_mode_equals_replay_of_its_own_draws_merton(cuda_lib, lam):
                         assert k < K
                         E.append(rec[0, k, i])
                         tau += rec[0, k, i]
-                    zW.append(Z[j - 1, i])
+                    # l = 0: the closing step takes the normal of the record that overshoots T
+                    zW.append(rec[2, k, i] if nsteps == 1 else Z[j - 1, i])
                 oW.append(len(zW)); oQ.append(len(zQ)); oE.append(len(E))
             packed = dict(zW=np.array(zW), offW=np.array(oW, dtype=np.int64), zQ=np.array(zQ),
                           offQ=np.array(oQ, dtype=np.int64), E=np.array(E), offE=np.array(oE, dtype=np.int64))
