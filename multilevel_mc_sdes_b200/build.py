@@ -7,12 +7,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmlmcb.so")
-SOURCES = ["mlmcb_api.cu"]
-HEADERS = ["mlmcb_kernels.cuh", os.path.join("..", "..", "include", "mlmcb.h")]
+# one translation unit per kernel family, compiled side by side
+SOURCES = ["mlmcb_api.cu", "mlmcb_merton_uniform.cu", "mlmcb_merton_flat.cu"]
+HEADERS = ["mlmcb_kernels.cuh", "mlmcb_pick.cuh", os.path.join("..", "..", "include", "mlmcb.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17", "-shared",
+    "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
 ]
 
@@ -31,17 +32,38 @@ def is_stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+def compile_lib(out, extra=(), verbose=False):
+    """nvcc -c every source (in parallel), then link them into the shared library `out`."""
+    objdir = out + ".obj"
+    os.makedirs(objdir, exist_ok=True)
+    flags = NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else [])
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        procs.append((obj, subprocess.Popen([nvcc_path()] + flags + ["-c", "-o", obj, src], cwd=CSRC,
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log, ok = "", True
+    for obj, p in procs:
+        log += p.communicate()[0]
+        ok = ok and p.returncode == 0
+    if ok:
+        r = subprocess.run([nvcc_path(), "-shared", "-o", out] + [o for o, _ in procs], cwd=CSRC, capture_output=True, text=True)
+        log += r.stdout + r.stderr
+        ok = r.returncode == 0
+    shutil.rmtree(objdir, ignore_errors=True)
+    if not ok:
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed building " + os.path.basename(out))
+    if verbose:
+        sys.stderr.write(log)
+    return out
+
+
 def build(force=False, verbose=False):
     """Compile csrc/*.cu -> csrc/libmlmcb.so.  Returns the library path."""
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libmlmcb.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+    compile_lib(LIB, verbose=verbose)
     write_sass_mix()
     return LIB
 

@@ -3,7 +3,7 @@
 // order numpy evaluates the reference's expressions), kernel selection, launch geometry,
 // stream-ordered workspace, and the pipe micro-benchmarks.  No torch types, no CPU fallback.
 #include "../../include/mlmcb.h"
-#include "mlmcb_kernels.cuh"
+#include "mlmcb_pick.cuh"
 
 #include <math.h>
 #include <map>
@@ -148,7 +148,6 @@ int make_consts(const mlmcb_params* p, int model, int payoff, int l, int M, ull 
 int fn_of(int payoff) { return payoff == MLMCB_ASIAN ? FN_AVG : payoff == MLMCB_LOOKBACK ? FN_MIN : FN_FINAL; }
 int mt_of(int M) { return M == 2 ? 2 : M == 4 ? 4 : 0; }
 
-typedef void (*LevelKernel)(const LevelConsts, double*, unsigned*, double*, double*, double*);
 
 // Merton levels below this many fine steps run the event-driven kernel (mjd_flat_kernel), the rest the
 // block-uniform one; MLMCB_MJD_FLAT_BELOW / MLMCB_MJD_RUN_BLOCKS in the environment override (tuning).
@@ -170,42 +169,14 @@ uint32_t run_blocks_for(ull nsteps) {
     return r < 4.0 ? 4u : r > 4096.0 ? 4096u : (uint32_t)r;
 }
 
-template <typename R, int MODEL, int FN, int SAMP, int SCH>
-LevelKernel pick_mt(int mt, bool flat) {
-    if (MODEL == 1 && flat) {
-        switch (mt) {
-        case 2: return mjd_flat_kernel<R, FN, 2, SAMP, SCH>;
-        case 4: return mjd_flat_kernel<R, FN, 4, SAMP, SCH>;
-        default: return mjd_flat_kernel<R, FN, 0, SAMP, SCH>;
-        }
-    }
-    switch (mt) {
-    case 2: return level_kernel<R, MODEL, FN, 2, SAMP, SCH>;
-    case 4: return level_kernel<R, MODEL, FN, 4, SAMP, SCH>;
-    default: return level_kernel<R, MODEL, FN, 0, SAMP, SCH>;
-    }
-}
-template <typename R, int MODEL, int SAMP, int SCH>
-LevelKernel pick_fn(int fn, int mt, bool flat) {
-    switch (fn) {
-    case FN_AVG: return pick_mt<R, MODEL, FN_AVG, SAMP, SCH>(mt, flat);
-    case FN_MIN: return pick_mt<R, MODEL, FN_MIN, SAMP, SCH>(mt, flat);
-    default: return pick_mt<R, MODEL, FN_FINAL, SAMP, SCH>(mt, flat);
-    }
-}
-template <typename R, int SAMP, int SCH = SCH_EM>
-LevelKernel pick_model(int model, int fn, int mt, bool flat) {
-    return model == MLMCB_GBM ? pick_fn<R, 0, SAMP, SCH>(fn, mt, false) : pick_fn<R, 1, SAMP, SCH>(fn, mt, flat);
-}
+struct GbmFamily {
+    template <typename R, int FN, int MT, int SAMP, int SCH>
+    static LevelKernel get() { return level_kernel<R, 0, FN, MT, SAMP, SCH>; }
+};
 LevelKernel pick_kernel(int model, int payoff, int M, int flags, ull nsteps) {
-    const int fn = fn_of(payoff), mt = mt_of(M), samp = flags & MLMCB_SAMPLER_MASK;
-    const bool flat = model == MLMCB_MERTON && nsteps < flat_below();
-    if (flags & MLMCB_MILSTEIN) return pick_model<double, SAMP_F32BM, SCH_MILSTEIN>(model, fn, mt, flat);
-    if (flags & MLMCB_FP32_PATHS)
-        return samp == MLMCB_SAMPLER_F64BM ? pick_model<float, SAMP_F64BM>(model, fn, mt, flat)
-                                           : pick_model<float, SAMP_F32BM>(model, fn, mt, flat);
-    return samp == MLMCB_SAMPLER_F64BM ? pick_model<double, SAMP_F64BM>(model, fn, mt, flat)
-                                       : pick_model<double, SAMP_F32BM>(model, fn, mt, flat);
+    const int fn = fn_of(payoff), mt = mt_of(M);
+    if (model == MLMCB_GBM) return pick_family<GbmFamily>(fn, mt, flags);
+    return nsteps < flat_below() ? pick_merton_flat(fn, mt, flags) : pick_merton_uniform(fn, mt, flags);
 }
 
 // Launch geometry: a grid-stride loop over paths.  The grid never exceeds the number of

@@ -1281,6 +1281,7 @@ __device__ __forceinline__ double amer_eb(const LevelConsts& C, double t) {
     return fmax(__dmul_rn(C.K, __dsub_rn(1.0, __dmul_rn(C.boundary_c, __dsqrt_rn(__dsub_rn(C.T, t))))), 0.0);
 }
 
+#ifndef MLMCB_TEMPLATES_ONLY   // the one non-template kernel: defined in mlmcb_api.cu only
 __global__ void amer_table_kernel(const __grid_constant__ LevelConsts C, AmerRow* tab) {
     const ull j = (ull)blockIdx.x * blockDim.x + threadIdx.x;
     if (j > C.nsteps) return;
@@ -1300,6 +1301,7 @@ __global__ void amer_table_kernel(const __grid_constant__ LevelConsts C, AmerRow
     }
     tab[j] = row;
 }
+#endif
 
 template <int AR>
 struct AmerState {
