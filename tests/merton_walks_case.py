@@ -1,0 +1,18 @@
+"""Helper for test_gpu_philox.py::test_merton_walks_agree_per_path (run as a subprocess, because the walk
+selection is read from the environment once per process): per-path payoffs of the Merton products at a few
+levels, written to the .npz given as argv[1]."""
+import sys
+
+import numpy as np
+
+import multilevel_mc_sdes_b200 as mm
+
+out = {}
+for cname in ("Euro_Merton", "Asian_Merton", "Lookback_Merton", "Digital_Merton"):
+    for l, M, kw in ((1, 2, {}), (2, 2, {}), (3, 2, {}), (2, 4, {}), (2, 3, {}), (6, 2, {"lam": 5.0}), (3, 4, {"scheme": "milstein"})):
+        opt = getattr(mm, cname)(seed=23, **kw)
+        opt._next_path[l] = 77
+        Pf, Pc = opt.payoff(4099, l, M)
+        out[f"{cname}_{l}_{M}_f"] = Pf
+        out[f"{cname}_{l}_{M}_c"] = Pc
+np.savez(sys.argv[1], **out)
