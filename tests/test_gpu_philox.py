@@ -70,6 +70,8 @@ def _moments(s, n, l):
 
 
 CASES = [(c, l, M) for c in sorted(CLASS_CODES) for (l, M) in ((0, 2), (1, 2), (2, 4), (3, 4), (4, 2))]
+# Merton above 128 fine steps runs the block-uniform walk (jump records in shared memory)
+CASES += [(c, l, M) for c in sorted(CLASS_CODES) if CLASS_CODES[c][0] == O.MERTON for (l, M) in ((8, 2), (4, 4))]
 
 
 @pytest.mark.parametrize("cname,l,M", CASES)
