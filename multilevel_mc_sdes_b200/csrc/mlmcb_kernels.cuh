@@ -844,7 +844,11 @@ template <typename R, int SAMP>
 __device__ __forceinline__ void jump_draws(const LevelConsts& C, ull pid, uint32_t jk, double& gap, R& zq, R& zw) {
     if (SAMP == SAMP_F32BM) {
         U4 r = philox_at(C, pid, STREAM_JUMP, jk);
-        gap = neg2_log(C, u52(r.x, r.y)) * (0.5 * C.inv_lam);        // Exp(lam) inter-arrival time :454/:474
+        // Exp(lam) inter-arrival time :454/:474.  Like the normals of this sampler it is an fp32 draw:
+        // u = (x + 1/2) 2^-32 from one word, -ln u by MUFU.LG2 (relative error ~1e-7), u kept below 1
+        // so that a gap is never zero.
+        const float u = fminf(fmaf(__uint2float_rn(r.x), 0x1p-32f, 0x1p-33f), 0x1.fffffep-1f);
+        gap = (double)(lg2_approx(u) * -0.693147180559945309f) * C.inv_lam;
         float a, b;
         bm_pair_f32(C.poly_q4, C.poly_c4, r.z, r.w, a, b);
         zq = (R)a; zw = (R)b;
