@@ -28,6 +28,10 @@ for cname, model, pay in (("Euro_GBM", O.GBM, O.EURO), ("Asian_GBM", O.GBM, O.AS
                           ("Lookback_Merton", O.MERTON, O.LOOKBACK), ("Digital_Merton", O.MERTON, O.DIGITAL)):
     for l, M in ((3, 4), (5, 2)):
         cases.append((cname, model, pay, l, M, "em", False))
+# the Merton walks: l=0 lane-queue loop, 2 steps event-driven (as are (3,4) and (5,2) above), 256 steps block-uniform
+for cname, pay in (("Euro_Merton", O.EURO), ("Asian_Merton", O.ASIAN), ("Lookback_Merton", O.LOOKBACK), ("Digital_Merton", O.DIGITAL)):
+    for l, M in ((0, 2), (1, 2), (8, 2)):
+        cases.append((cname, O.MERTON, pay, l, M, "em", False))
 cases += [("Euro_GBM", O.GBM, O.EURO, 3, 4, "milstein", False), ("Asian_Merton", O.MERTON, O.ASIAN, 3, 4, "milstein", False),
           ("Euro_GBM", O.GBM, O.EURO, 3, 4, "em", True), ("Asian_GBM", O.GBM, O.ASIAN, 4, 2, "em", True),
           ("Amer_GBM", O.GBM, O.AMERICAN, 4, 2, "em", False), ("Amer_GBM", O.GBM, O.AMERICAN, 6, 2, "em", False)]
