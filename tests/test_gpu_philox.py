@@ -479,6 +479,21 @@ def test_merton_walks_agree_per_path(cuda_lib, tmp_path):
             assert np.array_equal(v, res[tag][k]), (tag, k, np.abs(v - res[tag][k]).max())
 
 
+def test_merton_without_jumps_is_gbm(cuda_lib):
+    """lam = 0: no record ever falls inside the path (infinite arrival times), the drift is r, and the grid
+    normals are addressed like the GBM kernel's - so every Merton walk reproduces the GBM payoffs."""
+    for mer, gbm in ((mm.Euro_Merton, mm.Euro_GBM), (mm.Asian_Merton, mm.Asian_GBM), (mm.Lookback_Merton, mm.Lookback_GBM)):
+        for l, M in ((2, 2), (3, 4), (4, 4), (2, 3)):       # 4, 64 steps event-driven; 256 block-uniform; 9 generic M
+            a, b = mer(lam=0.0, sig=0.3, seed=5), gbm(sig=0.3, seed=5)
+            a._next_path[l] = b._next_path[l] = 1234
+            Pf, Pc = a.payoff(3001, l, M)
+            Gf, Gc = b.payoff(3001, l, M)
+            np.testing.assert_allclose(Pf, Gf, rtol=1e-13, atol=1e-12)
+            np.testing.assert_allclose(Pc, Gc, rtol=1e-13, atol=1e-12)
+        s = mer(lam=0.0, sig=0.3, seed=5).looper(100_000, 0, 2, False)      # l = 0: own draw mapping, finite sums
+        assert np.isfinite(s).all() and s[0] == s[2]
+
+
 def test_jump_stream_distributions(cuda_lib):
     """Jump records: inter-arrival times ~ Exp(lam) (:1294), jump-size and sub-step normals ~ N(0,1),
     mutually uncorrelated, and independent of the grid-step normals of the same path."""
