@@ -9,10 +9,12 @@ import multilevel_mc_sdes_b200 as mm
 
 out = {}
 for cname in ("Euro_Merton", "Asian_Merton", "Lookback_Merton", "Digital_Merton"):
-    for l, M, kw in ((1, 2, {}), (2, 2, {}), (3, 2, {}), (2, 4, {}), (2, 3, {}), (6, 2, {"lam": 5.0}), (3, 4, {"scheme": "milstein"})):
+    for l, M, kw in ((1, 2, {}), (2, 2, {}), (3, 2, {}), (2, 4, {}), (2, 3, {}), (6, 2, {"lam": 5.0}), (3, 4, {"scheme": "milstein"}),
+                     (3, 2, {"lam": 40.0}), (8, 2, {"lam": 12.0})):        # many more jumps than records kept ahead
         opt = getattr(mm, cname)(seed=23, **kw)
         opt._next_path[l] = 77
         Pf, Pc = opt.payoff(4099, l, M)
-        out[f"{cname}_{l}_{M}_f"] = Pf
-        out[f"{cname}_{l}_{M}_c"] = Pc
+        key = f"{cname}_{l}_{M}_{sorted(kw.items())}"
+        out[key + "_f"] = Pf
+        out[key + "_c"] = Pc
 np.savez(sys.argv[1], **out)
