@@ -21,7 +21,8 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rep = {"world": world}
 worst = 0.0
 for cls, l, M, n in ((mm.Euro_GBM, 6, 4, 1_000_003), (mm.Asian_GBM, 3, 2, 5_000_001), (mm.Lookback_Merton, 4, 4, 2_000_000),
-                     (mm.Digital_Merton, 2, 2, 3_000_000), (mm.Amer_GBM, 5, 2, 1_000_000)):
+                     (mm.Digital_Merton, 2, 2, 3_000_000), (mm.Euro_Merton, 0, 2, 7_000_001), (mm.Asian_Merton, 4, 4, 500_000),
+                     (mm.Amer_GBM, 5, 2, 1_000_000)):
     d = cls(seed=11, device=local, distributed=True, verbose=False).looper(n, l, M, False)
     s = cls(seed=11, device=local, distributed=False, verbose=False).looper(n, l, M, False)
     rel = float(np.max(np.abs(d - s) / np.maximum(np.abs(s), 1e-300)[np.abs(s) > 0].max()))
