@@ -135,6 +135,7 @@ int make_consts(const mlmcb_params* p, int model, int payoff, int l, int M, ull 
                                  1.479819860511658591e-01};
     memcpy(C->dq, dq, sizeof dq); memcpy(C->dc, dc, sizeof dc); memcpy(C->lg, lg, sizeof lg);
     C->ln2_hi = 6.93147180369123816490e-01; C->ln2_lo = 1.90821492927058770002e-10;
+    { double f = 1.0; for (int k = 2; k <= 13; ++k) { f *= (double)k; C->ex[k - 2] = 1.0 / f; } }
     C->r = p->r; C->boundary_c = p->boundary_c;
     C->sig2 = pow(p->sig, 2.0);                                                      // self.sig**2
     C->half_sig2 = 0.5 * C->sig2;

@@ -104,6 +104,7 @@ struct LevelConsts {
     float poly_q4, poly_c4;         // leading sin/cos coefficients as uniform operands (no per-block MOV)
     // fp64 sampler constants, read straight from the constant bank by DFMA (no 64-bit immediates exist)
     double dq[9], dc[9], lg[7], ln2_hi, ln2_lo;
+    double ex[12];                  // 1/k!, k = 2..13 (exp_bounded)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -273,6 +274,25 @@ __device__ __forceinline__ double sqrt_pos(double s) {
     const double r = fma(-g, h, 0.5);
     g = fma(g, r, g); h = fma(h, r, h);
     return fma(fma(-g, g, s), h, g);
+}
+
+// exp(x) for the jump size (:462), x clamped to [-700, 700] so the result is a normal number and the
+// scaling is one integer add: n = rint(x/ln2) by the 1.5*2^52 shift, r = x - n*ln2 (two-part ln2, |r| <= 0.347),
+// Taylor to r^13/13! (truncation 4e-18), 2^n into the exponent field.  <= 1 ulp; coefficients from the
+// constant bank (libdevice's exp spends as many uniform moves on its constants as FMAs on the polynomial).
+__device__ __forceinline__ double exp_bounded(const LevelConsts& C, double x) {
+    x = fmin(fmax(x, -700.0), 700.0);
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const int n = __double2loint(t);
+    const double nf = t - 6755399441055744.0;
+    double r = fma(nf, -C.ln2_hi, x);
+    r = fma(nf, -C.ln2_lo, r);
+    double p = fma(r, C.ex[11], C.ex[10]);
+#pragma unroll
+    for (int i = 9; i >= 0; --i) p = fma(p, r, C.ex[i]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
 // sin(pi h)/h and cos(pi h) on |h| <= 1/2 as degree-8 polynomials in h^2 (tools/gen_trig_poly.py,
@@ -759,7 +779,7 @@ struct JD {
     // one pass of the `while tau<tn` body :458-474 (the caller advances tau afterwards)
     __device__ __forceinline__ static R jump_size(const LevelConsts& C, R zq) {                          // :462
         if (AR == AR_EXACT) return (R)__dsub_rn(exp(__dadd_rn(C.jm, __dmul_rn(C.js, (double)zq))), 1.0);
-        return (R)(exp(fma(C.js, (double)zq, C.jm)) - 1.0);
+        return (R)(exp_bounded(C, fma(C.js, (double)zq, C.jm)) - 1.0);
     }
     __device__ __forceinline__ void jump(const LevelConsts& C, double tau, R zw, R zq) {
         jump_dJ(C, tau, zw, jump_size(C, zq));
