@@ -276,12 +276,15 @@ __device__ __forceinline__ double sqrt_pos(double s) {
     return fma(fma(-g, g, s), h, g);
 }
 
+// max(x, 0) as one compare and a select (fmax's NaN and signed-zero handling costs eight instructions in fp64)
+__device__ __forceinline__ double pos_part(double x) { return x > 0.0 ? x : 0.0; }
+
 // exp(x) for the jump size (:462), x clamped to [-700, 700] so the result is a normal number and the
 // scaling is one integer add: n = rint(x/ln2) by the 1.5*2^52 shift, r = x - n*ln2 (two-part ln2, |r| <= 0.347),
 // Taylor to r^13/13! (truncation 4e-18), 2^n into the exponent field.  <= 1 ulp; coefficients from the
 // constant bank (libdevice's exp spends as many uniform moves on its constants as FMAs on the polynomial).
 __device__ __forceinline__ double exp_bounded(const LevelConsts& C, double x) {
-    x = fmin(fmax(x, -700.0), 700.0);
+    x = x < -700.0 ? -700.0 : (x > 700.0 ? 700.0 : x);
     const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
     const int n = __double2loint(t);
     const double nf = t - 6755399441055744.0;
@@ -388,7 +391,7 @@ struct ReplaySource {
 __device__ __forceinline__ double payoff_fine(const LevelConsts& C, double v, double g) {
     switch (C.payoff) {
     case PAY_EURO:
-    case PAY_ASIAN: return __dmul_rn(C.disc, fmax(0.0, __dsub_rn(v, C.K)));                 // :79-80
+    case PAY_ASIAN: return __dmul_rn(C.disc, pos_part(__dsub_rn(v, C.K)));                  // :79-80
     case PAY_LOOKBACK: return __dmul_rn(C.disc, __dsub_rn(v, __dmul_rn(g, C.look_cf)));      // :105-106
     default: return v > C.K ? C.discK : 0.0;                                                 // :131
     }
@@ -396,7 +399,7 @@ __device__ __forceinline__ double payoff_fine(const LevelConsts& C, double v, do
 __device__ __forceinline__ double payoff_coarse(const LevelConsts& C, double v, double g) {
     switch (C.payoff) {
     case PAY_EURO:
-    case PAY_ASIAN: return __dmul_rn(C.disc, fmax(0.0, __dsub_rn(v, C.K)));                 // :84-85
+    case PAY_ASIAN: return __dmul_rn(C.disc, pos_part(__dsub_rn(v, C.K)));                  // :84-85
     case PAY_LOOKBACK: return __dmul_rn(C.disc, __dsub_rn(v, __dmul_rn(g, C.look_cc)));      // :110-111
     default: return v > C.K ? C.discK : 0.0;                                                 // :135
     }
@@ -790,26 +793,40 @@ struct JD {
         jump_pre(C, dt, dWf, dJ);
         tf = tau; tc = tau;                                              // :472-473
     }
-    // the same with the step length and Brownian increment already formed (clocks untouched)
+    // the same with the step length and Brownian increment already formed (clocks untouched).
+    // COARSE = false (l = 0 only): between jumps the coarse path of a one-step level does not move, and at
+    // a jump it takes the very increments of the fine one (dtc = dt, dWc = dWf), so it IS the fine
+    // state after the jump - copied instead of recomputed.
+    template <bool COARSE = true>
     __device__ __forceinline__ void jump_pre(const LevelConsts& C, double dt, R dWf, R dJ) {
-        dtc += dt;                                                       // :459
-        dWc = add(dWc, dWf);                                             // :461
+        if (COARSE) {
+            dtc += dt;                                                   // :459
+            dWc = add(dWc, dWf);                                         // :461
+        }
         if (FN == FN_AVG) {                                              // :532-540
             Gf = add(Gf, half_area(Sf, dt));
             Sf = add(Sf, dx(C, Sf, dt, dWf));
             Gf = add(Gf, half_area(Sf, dt));
             Sf = add(Sf, mul(Sf, dJ));
-            Gc = add(Gc, half_area(Sc, dtc));
-            Sc = add(Sc, dx(C, Sc, dtc, dWc));
-            Gc = add(Gc, half_area(Sc, dtc));
-            Sc = add(Sc, mul(Sc, dJ));
+            if (COARSE) {
+                Gc = add(Gc, half_area(Sc, dtc));
+                Sc = add(Sc, dx(C, Sc, dtc, dWc));
+                Gc = add(Gc, half_area(Sc, dtc));
+                Sc = add(Sc, mul(Sc, dJ));
+            }
         } else {                                                         // :465-468, sde with dJ :1315
             R d = dx(C, Sf, dt, dWf);
             Sf = add(Sf, add(d, mul(add(d, Sf), dJ)));
-            d = dx(C, Sc, dtc, dWc);
-            Sc = add(Sc, add(d, mul(add(d, Sc), dJ)));
-            if (FN == FN_MIN) { Gf = min_<R>(Gf, Sf); Gc = min_<R>(Gc, Sc); }   // :621-622
+            if (COARSE) {
+                d = dx(C, Sc, dtc, dWc);
+                Sc = add(Sc, add(d, mul(add(d, Sc), dJ)));
+            }
+            if (FN == FN_MIN) {                                          // :621-622
+                Gf = min_<R>(Gf, Sf);
+                if (COARSE) Gc = min_<R>(Gc, Sc);
+            }
         }
+        if (!COARSE) { Sc = Sf; Gc = Gf; }
         dWc = (R)0; dtc = 0.0;                                           // :470-471
     }
 
@@ -1233,7 +1250,7 @@ mjd_flat_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigne
                 const double d = (jump ? tau : tend) - t;                // :458 / :477
                 const R dW = zw * (R)(d > 0.0 ? sqrt_pos(d) : 0.0);      // :460 / :479
                 if (jump) {
-                    st.jump_pre(C, d, dW, JD<R, FN, AR_FAST, SCH>::jump_size(C, zq));
+                    st.template jump_pre<false>(C, d, dW, JD<R, FN, AR_FAST, SCH>::jump_size(C, zq));
                     t = tau; ++k;
                 } else {
                     st.grid_pre(C, d, dW);
@@ -1349,9 +1366,9 @@ struct AmerState {
         y = fma(y, fma(-g, y, 1.0), y);
         return C.amer_cneg * y;
     }
-    __device__ __forceinline__ static double exp_or_zero(double arg) {
+    __device__ __forceinline__ static double exp_or_zero(const LevelConsts& C, double arg) {
         if (__all_sync(__activemask(), arg < -750.0)) return 0.0;
-        return exp(arg);
+        return arg < -700.0 ? 0.0 : exp_bounded(C, arg);
     }
     __device__ __forceinline__ static double inc_exact(const LevelConsts& C, double X, double h, double dW) {
         return __dadd_rn(__dmul_rn(__dmul_rn(C.mu, X), h), __dmul_rn(__dmul_rn(C.sig, X), dW));
@@ -1367,8 +1384,8 @@ struct AmerState {
             dWc += z;                                                    // in units of sqrt(dt)
             Xr = fma(Xl, fma(C.b_f, z, C.a_f), Xl);
         }
-        const double A = fmax(Xl - lbF, 0.0), B = fmax(Xr - row.bR, 0.0);
-        const double P1 = AR == AR_EXACT ? touch_exact(C, A, B, Xl) : exp_or_zero(inv_scale(C, Xl) * A * B);
+        const double A = pos_part(Xl - lbF), B = pos_part(Xr - row.bR);
+        const double P1 = AR == AR_EXACT ? touch_exact(C, A, B, Xl) : exp_or_zero(C, inv_scale(C, Xl) * A * B);
         if (AR == AR_EXACT) {
             f2 = __dadd_rn(f2, __dmul_rn(__dmul_rn(__dmul_rn(f1, P1), row.mkF), row.eF));      // :1569
             f1 = __dmul_rn(f1, __dsub_rn(1.0, P1));                      // :1571
@@ -1390,13 +1407,13 @@ struct AmerState {
             Xr = fma(Xl, fma(C.b_f, dWc, C.a_c), Xl);
             Xmid = fma(C.b_f * Xl, 0.5 * dWc, fma(0.5, Xr - Xl, Xl));
         }
-        const double A = fmax(Xl - lbC, 0.0), Bm = fmax(Xmid - row.mb1, 0.0), B = fmax(Xr - row.bR, 0.0);
+        const double A = pos_part(Xl - lbC), Bm = pos_part(Xmid - row.mb1), B = pos_part(Xr - row.bR);
         double P11, P12;                                                 // :1600-1601
         if (AR == AR_EXACT) {
             P11 = touch_exact(C, A, Bm, Xl); P12 = touch_exact(C, Bm, B, Xl);
         } else {
             const double w = inv_scale(C, Xl) * Bm;
-            P11 = exp_or_zero(w * A); P12 = exp_or_zero(w * B);
+            P11 = exp_or_zero(C, w * A); P12 = exp_or_zero(C, w * B);
         }
         if (AR == AR_EXACT) {
             const double P1 = __dsub_rn(1.0, __dmul_rn(__dsub_rn(1.0, P11), __dsub_rn(1.0, P12)));   // :1603
@@ -1413,8 +1430,8 @@ struct AmerState {
     }
     // Amer_payoff :153-157
     __device__ __forceinline__ void payoffs(const LevelConsts& C, double& Pf, double& Pc) const {
-        Pf = __dadd_rn(f2, __dmul_rn(__dmul_rn(f1, fmax(__dsub_rn(C.K, f0), 0.0)), C.disc));
-        Pc = C.is_l0 ? 0.0 : __dadd_rn(c2, __dmul_rn(__dmul_rn(c1, fmax(__dsub_rn(C.K, c0), 0.0)), C.disc));
+        Pf = __dadd_rn(f2, __dmul_rn(__dmul_rn(f1, pos_part(__dsub_rn(C.K, f0))), C.disc));
+        Pc = C.is_l0 ? 0.0 : __dadd_rn(c2, __dmul_rn(__dmul_rn(c1, pos_part(__dsub_rn(C.K, c0))), C.disc));
     }
 };
 
