@@ -1479,15 +1479,26 @@ amer_level_kernel(const __grid_constant__ LevelConsts C, const AmerRow* tab, dou
         PhiloxSource<double, SAMP> src{C, C.path_offset + i};
         AmerState<AR_FAST> st;
         st.init(C, tab);
-        const uint32_t nblk = (uint32_t)((C.nsteps + 3) >> 2);
-        for (uint32_t b = 0; b < nblk; ++b) {
+        const uint32_t nblk = (uint32_t)(C.nsteps >> 2);
+        const AmerRow* rows = tab + 1;                                   // row of fine step j = 4b+k+1
+        for (uint32_t b = 0; b < nblk; ++b, rows += 4) {
             double z[4];
             src.load4(b, z);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const ull j = 4ull * b + k + 1;
-                if (j <= C.nsteps) {
-                    const AmerRow row = load_row(tab, j);
+                const AmerRow row = load_row(rows, k);
+                st.fine(C, row, z[k]);
+                if (k & 1) st.coarse(C, row);
+            }
+        }
+        const int rem = (int)(C.nsteps & 3);                             // l = 0 (1 step), l = 1 (2 steps)
+        if (rem) {
+            double z[4];
+            src.load4(nblk, z);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (k < rem) {
+                    const AmerRow row = load_row(rows, k);
                     st.fine(C, row, z[k]);
                     if (k & 1) st.coarse(C, row);
                 }
