@@ -46,7 +46,7 @@ enum {
     MLMCB_SAMPLER_F32BM = 0,   /* default: 32-bit uniforms, fp32 Box-Muller, promoted to fp64      */
     MLMCB_SAMPLER_F64BM = 1,   /* canonical: 53-bit uniforms, fp64 Box-Muller (log/sqrt/sincospi)  */
     MLMCB_SAMPLER_MASK  = 0xF,
-    MLMCB_FP32_PATHS    = 0x10,/* opt-in: path arithmetic in fp32 (sums stay fp64)                 */
+    MLMCB_FP32_PATHS    = 0x10,/* opt-in: path arithmetic in fp32 (sums stay fp64); F32BM sampler  */
     MLMCB_MILSTEIN      = 0x40,/* Milstein instead of Euler-Maruyama increments: the reference's demo
                                   notebook swaps `sde` for milstein_GBM / milstein_Merton
                                   (ExampleUsages.ipynb cell 1: + 0.5*X*sig**2*(dW**2-dt)).  fp64 paths and

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmlmcb.so")
 # one translation unit per kernel family, compiled side by side
-SOURCES = ["mlmcb_api.cu", "mlmcb_merton_uniform.cu", "mlmcb_merton_flat.cu"]
+SOURCES = ["mlmcb_api.cu", "mlmcb_gbm.cu", "mlmcb_merton_uniform.cu", "mlmcb_merton_flat.cu"]
 HEADERS = ["mlmcb_kernels.cuh", "mlmcb_pick.cuh", os.path.join("..", "..", "include", "mlmcb.h")]
 
 NVCC_FLAGS = [

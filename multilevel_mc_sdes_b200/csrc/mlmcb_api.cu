@@ -170,13 +170,9 @@ uint32_t run_blocks_for(ull nsteps) {
     return r < 4.0 ? 4u : r > 4096.0 ? 4096u : (uint32_t)r;
 }
 
-struct GbmFamily {
-    template <typename R, int FN, int MT, int SAMP, int SCH>
-    static LevelKernel get() { return level_kernel<R, 0, FN, MT, SAMP, SCH>; }
-};
 LevelKernel pick_kernel(int model, int payoff, int M, int flags, ull nsteps) {
     const int fn = fn_of(payoff), mt = mt_of(M);
-    if (model == MLMCB_GBM) return pick_family<GbmFamily>(fn, mt, flags);
+    if (model == MLMCB_GBM) return pick_gbm(fn, mt, flags);
     return nsteps < flat_below() ? pick_merton_flat(fn, mt, flags) : pick_merton_uniform(fn, mt, flags);
 }
 
@@ -243,6 +239,8 @@ int check_flags(int flags) {
         return fail(MLMCB_EINVAL, "unknown flag bits 0x%x", flags);
     if ((flags & MLMCB_MILSTEIN) && ((flags & (MLMCB_FP32_PATHS | MLMCB_ANTITHETIC)) || samp != MLMCB_SAMPLER_F32BM))
         return fail(MLMCB_ENOTIMPL, "Milstein is built for fp64 paths with the default sampler, without the antithetic estimator");
+    if ((flags & MLMCB_FP32_PATHS) && samp != MLMCB_SAMPLER_F32BM)
+        return fail(MLMCB_ENOTIMPL, "fp32 path arithmetic is built with the default (fp32) sampler only");
     return 0;
 }
 
@@ -265,8 +263,7 @@ LevelKernel pick_anti_fn(int fn, int mt) {
 }
 LevelKernel pick_anti_kernel(int payoff, int M, int flags) {
     const int fn = fn_of(payoff), mt = mt_of(M), samp = flags & MLMCB_SAMPLER_MASK;
-    if (flags & MLMCB_FP32_PATHS)
-        return samp == MLMCB_SAMPLER_F64BM ? pick_anti_fn<float, SAMP_F64BM>(fn, mt) : pick_anti_fn<float, SAMP_F32BM>(fn, mt);
+    if (flags & MLMCB_FP32_PATHS) return pick_anti_fn<float, SAMP_F32BM>(fn, mt);      // check_flags: default sampler only
     return samp == MLMCB_SAMPLER_F64BM ? pick_anti_fn<double, SAMP_F64BM>(fn, mt) : pick_anti_fn<double, SAMP_F32BM>(fn, mt);
 }
 

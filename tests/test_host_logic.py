@@ -208,3 +208,15 @@ def test_invalid_arguments_are_value_errors():
     if torch.cuda.is_available():
         with pytest.raises(ValueError):
             mm.Euro_GBM().looper(100, 1, 1, False)           # M < 2
+
+
+def test_flag_combinations_are_checked_before_the_device():
+    """Flag validation needs no GPU: unknown bits are EINVAL, combinations that were never built are ENOTIMPL."""
+    import ctypes as C
+    lib = _lib.load()
+    t, b = C.c_int(), C.c_int()
+    geo = lambda flags: lib.mlmcb_launch_geometry(0, 0, 4, flags, 0, C.byref(t), C.byref(b))
+    assert geo(0x1000) == _lib.EINVAL
+    assert geo(_lib.FP32_PATHS | _lib.SAMPLER_F64BM) == _lib.ENOTIMPL          # fp32 paths: default sampler only
+    assert geo(_lib.MILSTEIN | _lib.ANTITHETIC) == _lib.ENOTIMPL
+    assert b"sampler" in lib.mlmcb_last_error() or b"Milstein" in lib.mlmcb_last_error()
