@@ -119,6 +119,26 @@ def test_per_path_outputs_consistent_and_deterministic(cuda_lib):
         assert s3[2] != s[2]
 
 
+def test_merton_walks_ragged_sizes(cuda_lib):
+    """Fewer paths than a warp / a block, sizes that are no multiple of anything, on each Merton walk
+    (1 step: lane-queue loop, 4 and 64: event-driven, 256: block-uniform): sums equal the per-path outputs,
+    and a path's payoff does not depend on how many neighbours were simulated with it."""
+    for cls in (mm.Euro_Merton, mm.Asian_Merton, mm.Lookback_Merton):
+        for l, M in ((0, 2), (2, 2), (3, 4), (8, 2)):
+            ref = cls(seed=8)
+            ref._next_path[l] = 40
+            Rf, Rc = ref.payoff(300, l, M)
+            for n in (1, 5, 33, 129):
+                a = cls(seed=8)
+                a._next_path[l] = 40
+                Pf, Pc = a.payoff(n, l, M)
+                assert np.array_equal(Pf, Rf[:n]) and np.array_equal(Pc, Rc[:n]), (cls.__name__, l, M, n)
+                s = level_sums(a, n, l, M, offset=40)
+                want = [Pf.sum(), (Pf ** 2).sum(), Pf.sum(), (Pf ** 2).sum(), 0, 0, 0] if l == 0 else \
+                    [(Pf - Pc).sum(), ((Pf - Pc) ** 2).sum(), Pf.sum(), (Pf ** 2).sum(), Pc.sum(), (Pc ** 2).sum(), (Pf * Pc).sum()]
+                np.testing.assert_allclose(s, want, rtol=1e-12, atol=1e-12)
+
+
 def test_coupling_fine_equals_previous_level_distribution(cuda_lib):
     """Telescoping check: E[Pc at level l] = E[Pf at level l-1] (same discretisation)."""
     for cname in ("Euro_GBM", "Asian_GBM", "Lookback_GBM", "Euro_Merton", "Asian_Merton", "Lookback_Merton"):
