@@ -311,7 +311,12 @@ int level_sums_impl(const mlmcb_params* p, int model, int payoff, int l, int M, 
     }
     if (n_paths == 0) { CU(cudaMemsetAsync(d_out7, 0, 7 * sizeof(double), st)); return 0; }
     if (payoff == MLMCB_AMERICAN) return amer_level_sums(C, flags, device, st, d_out7, d_Pf, d_Pc);
-    LevelKernel k = (flags & MLMCB_ANTITHETIC) ? pick_anti_kernel(payoff, M, flags) : pick_kernel(model, payoff, M, flags, C.nsteps);
+    // l = 0 has no antithetic twin (diffusion_anti_path :212-214 takes one plain step and anti_EA_payoff :310
+    // returns the plain Pf), so the sums come from the plain kernel and its packed draws; the antithetic
+    // kernel still serves per-path outputs there (its coarse output is X0, :214)
+    const bool anti = (flags & MLMCB_ANTITHETIC) && !(C.is_l0 && !d_Pf && !d_Pc && !d_raw);
+    LevelKernel k = anti ? pick_anti_kernel(payoff, M, flags)
+                         : pick_kernel(model, payoff, M, flags & ~MLMCB_ANTITHETIC, C.nsteps);
     int grid = 1;
     if (int rc = geometry(k, device, n_paths, &grid, nullptr)) return rc;
     Workspace w;

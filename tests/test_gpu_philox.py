@@ -212,6 +212,10 @@ def test_antithetic_level_moments(cuda_lib, c_oracle, cname, l, M):
         assert s[1] == pytest.approx(s[3] - 2 * s[6] + s[5], rel=1e-9, abs=1e-9 * s[3])
     Pf, Pc = opt.anti_payoff(1000, l, M)
     assert Pf.shape == (1000,) and Pc.shape == (1000,)
+    if l == 0:      # no antithetic twin at l = 0 (:212-214, :310): the sums are the plain kernel's
+        a, b = getattr(mm, cname)(seed=77), getattr(mm, cname)(seed=77)
+        assert np.array_equal(a.looper(123_457, 0, M, True), b.looper(123_457, 0, M, False))
+        assert np.all(Pc == opt.X0)
 
 
 @pytest.mark.parametrize("cname", ["Euro_GBM", "Asian_GBM", "Lookback_GBM", "Euro_Merton", "Asian_Merton"])
