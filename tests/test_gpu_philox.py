@@ -119,6 +119,25 @@ def test_per_path_outputs_consistent_and_deterministic(cuda_lib):
         assert s3[2] != s[2]
 
 
+@pytest.mark.parametrize("sampler", ["f32bm", "f64bm"])
+def test_level0_mean_against_closed_form(cuda_lib, sampler):
+    """l = 0 is one Euler step, X = X0(1+rT) + X0 sig sqrt(T) z, so E[Pf] is known exactly (normal X):
+    4e9 samples resolve 1e-5 in the mean of z.  (tools/l0_exact_check.py runs this at 3e12 samples.)"""
+    import math
+    Phi = lambda x: 0.5 * math.erfc(-x / math.sqrt(2.0))
+    phi = lambda x: math.exp(-0.5 * x * x) / math.sqrt(2.0 * math.pi)
+    n = 4_000_000_000 if sampler == "f32bm" else 1_000_000_000
+    for kw in ({}, dict(X0=125, K=105, r=0.02, sig=0.5)):
+        o = mm.Euro_GBM(seed=321, sampler=sampler, **kw)
+        m, s_, disc = o.X0 * (1 + o.r * o.T), o.X0 * o.sig * math.sqrt(o.T), math.exp(-o.r * o.T)
+        d = (m - o.K) / s_
+        exact = disc * ((m - o.K) * Phi(d) + s_ * phi(d))
+        second = disc ** 2 * (((m - o.K) ** 2 + s_ * s_) * Phi(d) + (m - o.K) * s_ * phi(d))
+        sums = o.looper(n, 0, 2, False)
+        assert abs(sums[2] / n - exact) < 4 * math.sqrt((second - exact ** 2) / n)
+        assert abs(sums[3] / n - second) < 4 * second * math.sqrt(30 / n)          # second moment, loose kurtosis bound
+
+
 def test_merton_walks_ragged_sizes(cuda_lib):
     """Fewer paths than a warp / a block, sizes that are no multiple of anything, on each Merton walk
     (1 step: lane-queue loop, 4 and 64: event-driven, 256: block-uniform): sums equal the per-path outputs,
