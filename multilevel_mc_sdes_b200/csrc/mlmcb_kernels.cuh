@@ -35,12 +35,6 @@
 #ifndef MLMCB_MINBLOCKS_MJD
 #define MLMCB_MINBLOCKS_MJD 6
 #endif
-#ifndef MLMCB_MJD_UNROLLED
-#define MLMCB_MJD_UNROLLED 1
-#endif
-#ifndef MLMCB_MJD_LAZY_STEPS
-#define MLMCB_MJD_LAZY_STEPS 0
-#endif
 #ifndef MLMCB_MJD_FLAT_BELOW
 #define MLMCB_MJD_FLAT_BELOW 128    // Merton: levels with fewer fine steps run the event-driven kernel
 #endif
@@ -993,11 +987,9 @@ struct MjdWalker {
         st.init(C);
         jk = jp = 0; cm = 0;
         tlast = 0.0; jlast = 0.0;
-        // paths of a few steps reach their jumps together anyway: one record, the rest on demand
-        const uint32_t ahead = C.nsteps <= MLMCB_MJD_LAZY_STEPS ? 1u : (uint32_t)kJumpRecs;
         const double nd = (double)C.nsteps;
 #pragma unroll 1
-        while (jp < ahead) {
+        while (jp < (uint32_t)kJumpRecs) {
             produce();
             if (__all_sync(__activemask(), jlast > nd)) break;           // nobody will look further
         }
@@ -1131,7 +1123,7 @@ __device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid, d
             } else {
                 // the block that holds a jump (or every block when M is generic)
                 w.st.Sf = Xf; w.st.Sc = Xc; w.st.Gf = Gf; w.st.Gc = Gc;
-                if (MT != 0 && MLMCB_MJD_UNROLLED) w.template jump_block4<MT>((double)(4ull * b), z);
+                if (MT != 0) w.template jump_block4<MT>((double)(4ull * b), z);
                 else w.template steps<MT>((double)(4ull * b), 4, z[0], z[1], z[2], z[3]);
                 Xf = w.st.Sf; Xc = w.st.Sc; Gf = w.st.Gf; Gc = w.st.Gc;
                 if (MT != 0) jb = w.jump_block(nfull);
