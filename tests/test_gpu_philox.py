@@ -456,50 +456,71 @@ def test_philox_mode_equals_replay_of_its_own_draws_gbm(cuda_lib, sampler):
     np.testing.assert_allclose(Pc, Rc, rtol=1e-13, atol=1e-11)
 
 
+def _merton_own_draws_case(cuda_lib, cls, kw, l, M, n=600, off=999, seed=17, K=64):
+    """Per-path payoffs of the production Merton kernel against the replay of its own draws: grid normals
+    from the sampler probe, jump records from the jump probe, interleaved on the host in the order the
+    reference consumes them (:454-479)."""
+    import torch
+    opt = cls(seed=seed, **kw)
+    opt._next_path[l] = off
+    Pf, Pc = opt.payoff(n, l, M)
+    nsteps = M ** l
+    # grid normals: the coarsest GBM-style packing does not apply to Merton; block-addressed stream
+    Z = _probe_normals(cuda_lib, _lib.SAMPLER_F32BM, seed, l, off, n, max(nsteps, 1))
+    rec = torch.empty(3 * K * n, dtype=torch.float64, device="cuda")
+    _lib.check(cuda_lib.mlmcb_jump_probe(_lib.SAMPLER_F32BM, seed, l, opt.lam, off, n, K, 0, 0, rec.data_ptr()))
+    torch.cuda.synchronize()
+    rec = rec.cpu().numpy().reshape(3, K, n)
+    zW, zQ, E, oW, oQ, oE = [], [], [], [0], [0], [0]
+    dt = opt.T / nsteps
+    for i in range(n):
+        k = 0
+        tau = rec[0, 0, i]
+        E.append(rec[0, 0, i])
+        for j in range(1, nsteps + 1):
+            tn = j * dt                     # the production kernel's grid time (double)j*dt
+            while tau < tn:
+                zW.append(rec[2, k, i]); zQ.append(rec[1, k, i])
+                k += 1
+                assert k < K
+                E.append(rec[0, k, i])
+                tau += rec[0, k, i]
+            # l = 0: the closing step takes the normal of the record that overshoots T
+            zW.append(rec[2, k, i] if nsteps == 1 else Z[j - 1, i])
+        oW.append(len(zW)); oQ.append(len(zQ)); oE.append(len(E))
+    packed = dict(zW=np.array(zW), offW=np.array(oW, dtype=np.int64), zQ=np.array(zQ),
+                  offQ=np.array(oQ, dtype=np.int64), E=np.array(E), offE=np.array(oE, dtype=np.int64))
+    Rf, Rc = cls(**kw).payoff_replay(packed, l, M, arith="fast")
+    scale = 1e-12 * max(opt.X0, opt.K or 0.0)
+    np.testing.assert_allclose(Pf, Rf, rtol=1e-12, atol=100 * scale)
+    np.testing.assert_allclose(Pc, Rc, rtol=1e-12, atol=100 * scale)
+
+
 @pytest.mark.parametrize("lam", [1.0, 6.0])
 def test_philox_mode_equals_replay_of_its_own_draws_merton(cuda_lib, lam):
-    """The same for the jump-adapted kernels: grid normals from the sampler probe, jump records from the
-    jump probe, interleaved on the host in the order the reference consumes them (:454-479), replayed.
-    Exercises the jump-free run length agreement, the mixed blocks and the tail block of the production
-    kernel against the straightforward replay loop."""
-    import torch
+    """Exercises the jump-free run length agreement, the jump blocks and the tail of the block-uniform kernel,
+    the event-driven kernel and the l = 0 loop against the straightforward replay loop."""
     for cls in (mm.Euro_Merton, mm.Asian_Merton, mm.Lookback_Merton):
-        # 1 step: lane-queue loop; 2: lockstep; 8, 9, 32, 64: event-driven kernel; 128, 256: block-uniform kernel
+        # 1 step: lane-queue loop; 2, 8, 9, 32, 64: event-driven kernel; 128, 256: block-uniform kernel
         for l, M in ((0, 2), (1, 2), (3, 2), (3, 4), (2, 3), (5, 2), (7, 2), (4, 4)):
-            n, off, seed, K = 600, 999, 17, 64
-            opt = cls(seed=seed, lam=lam)
-            opt._next_path[l] = off
-            Pf, Pc = opt.payoff(n, l, M)
-            nsteps = M ** l
-            # grid normals: the coarsest GBM-style packing does not apply to Merton; block-addressed stream
-            Z = _probe_normals(cuda_lib, _lib.SAMPLER_F32BM, seed, l, off, n, max(nsteps, 1))
-            rec = torch.empty(3 * K * n, dtype=torch.float64, device="cuda")
-            _lib.check(cuda_lib.mlmcb_jump_probe(_lib.SAMPLER_F32BM, seed, l, lam, off, n, K, 0, 0, rec.data_ptr()))
-            torch.cuda.synchronize()
-            rec = rec.cpu().numpy().reshape(3, K, n)
-            zW, zQ, E, oW, oQ, oE = [], [], [], [0], [0], [0]
-            T = 1.0
-            dt = T / nsteps
-            for i in range(n):
-                k = 0
-                tau = rec[0, 0, i]
-                E.append(rec[0, 0, i])
-                for j in range(1, nsteps + 1):
-                    tn = j * dt                     # the production kernel's grid time (double)j*dt
-                    while tau < tn:
-                        zW.append(rec[2, k, i]); zQ.append(rec[1, k, i])
-                        k += 1
-                        assert k < K
-                        E.append(rec[0, k, i])
-                        tau += rec[0, k, i]
-                    # l = 0: the closing step takes the normal of the record that overshoots T
-                    zW.append(rec[2, k, i] if nsteps == 1 else Z[j - 1, i])
-                oW.append(len(zW)); oQ.append(len(zQ)); oE.append(len(E))
-            packed = dict(zW=np.array(zW), offW=np.array(oW, dtype=np.int64), zQ=np.array(zQ),
-                          offQ=np.array(oQ, dtype=np.int64), E=np.array(E), offE=np.array(oE, dtype=np.int64))
-            Rf, Rc = cls(lam=lam).payoff_replay(packed, l, M, arith="fast")
-            np.testing.assert_allclose(Pf, Rf, rtol=1e-12, atol=1e-10)
-            np.testing.assert_allclose(Pc, Rc, rtol=1e-12, atol=1e-10)
+            _merton_own_draws_case(cuda_lib, cls, dict(lam=lam), l, M)
+
+
+def test_philox_mode_equals_replay_of_its_own_draws_merton_random_parameters(cuda_lib):
+    """The same with every model parameter drawn at random - in particular T != 1, on which the step search,
+    the block index of a jump and the end-of-path test of the three walks depend."""
+    rng = np.random.default_rng(2718)
+    classes = (mm.Euro_Merton, mm.Asian_Merton, mm.Lookback_Merton, mm.Digital_Merton)
+    levels = ((0, 2), (1, 2), (2, 2), (2, 4), (3, 4), (2, 5), (7, 2), (4, 4))
+    for it in range(16):
+        kw = dict(X0=float(rng.uniform(20, 300)), T=float(rng.uniform(0.2, 3.0)), r=float(rng.uniform(0.0, 0.1)),
+                  sig=float(rng.uniform(0.05, 0.6)), lam=float(rng.uniform(0.2, 8.0)),
+                  jumpmean=float(rng.uniform(-0.3, 0.3)), jumpstd=float(rng.uniform(0.05, 0.5)))
+        kw["K"] = kw["X0"] * float(rng.uniform(0.7, 1.3))
+        cls = classes[it % 4]
+        l, M = levels[it % len(levels)]
+        _merton_own_draws_case(cuda_lib, cls, kw, l, M, n=300, off=int(rng.integers(0, 2 ** 40)), seed=int(rng.integers(0, 2 ** 31)),
+                               K=128)
 
 
 def test_merton_walks_agree_per_path(cuda_lib, tmp_path):
