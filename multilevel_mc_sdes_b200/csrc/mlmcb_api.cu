@@ -172,7 +172,7 @@ uint32_t run_blocks_for(ull nsteps) {
 
 LevelKernel pick_kernel(int model, int payoff, int M, int flags, ull nsteps) {
     const int fn = fn_of(payoff), mt = mt_of(M);
-    if (model == MLMCB_GBM) return pick_gbm(fn, mt, flags);
+    if (model == MLMCB_GBM) return nsteps <= 2 ? pick_gbm_packed(fn, flags) : pick_gbm(fn, mt, flags);
     return nsteps < flat_below() ? pick_merton_flat(fn, mt, flags) : pick_merton_uniform(fn, mt, flags);
 }
 

@@ -270,8 +270,12 @@ __device__ __forceinline__ double sqrt_pos(double s) {
     return fma(fma(-g, g, s), h, g);
 }
 
-// max(x, 0) as one compare and a select (fmax's NaN and signed-zero handling costs eight instructions in fp64)
-__device__ __forceinline__ double pos_part(double x) { return x > 0.0 ? x : 0.0; }
+// max(x, 0) by masking with the sign: one shift and two logic operations.  (fp64 fmax - which is also what
+// nvcc turns `x > 0 ? x : 0` into - expands to DSETP.MAX, two selects, a NaN-quieting LOP3 and moves.)
+__device__ __forceinline__ double pos_part(double x) {
+    const int hi = __double2hiint(x), keep = ~(hi >> 31);
+    return __hiloint2double(hi & keep, __double2loint(x) & keep);
+}
 
 // exp(x) for the jump size (:462), x clamped to [-700, 700] so the result is a normal number and the
 // scaling is one integer add: n = rint(x/ln2) by the 1.5*2^52 shift, r = x - n*ln2 (two-part ln2, |r| <= 0.347),
@@ -1567,6 +1571,76 @@ struct JumpRecStore<1> {
     }
 };
 
+// GBM paths of one or two fine steps (l = 0; M = 2, l = 1), a kernel of their own so that the long-path
+// kernel's register allocation and code placement do not move when this one is tuned.
+template <typename R, int FN, int SAMP, int SCH>
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64 : MLMCB_MINBLOCKS)
+gbm_packed_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
+                  double* out7, double* Pf_out, double* Pc_out) {
+    Sums7 acc;
+    acc.clear();
+    const ull stride = (ull)gridDim.x * blockDim.x;
+    // The coarsest levels (1 or 2 fine steps per path) are where MLMC puts most of its samples and
+    // a path needs fewer normals than one Philox block holds: 4 (or 2) consecutive global path ids
+    // share one block (stream STREAM_PACK, counter = id / paths-per-block), each taking its own
+    // normals.  Still a pure function of (seed, level, global path id).
+    const int per = C.nsteps == 1 ? 4 : 2;
+    const ull first = C.path_offset / per, last = (C.path_offset + C.n_paths - 1) / per;
+    const ull lo = C.path_offset, hi = C.path_offset + C.n_paths;
+    if (C.nsteps == 1) {
+        // l == 0: one Euler step, no coarse path (:341), sums row [Pf, Pf^2, Pf, Pf^2, 0, 0, 0] (:949)
+        const StepCoef<R, SCH> co(C);
+        const R X0 = (R)C.X0;
+        const double h0 = 0.5 * C.X0, vc0 = FN == FN_AVG ? 0.0 : C.X0, gc0 = FN == FN_MIN ? C.X0 : 0.0;
+        double s0 = 0.0, s1 = 0.0;
+        for (ull c = first + (ull)blockIdx.x * blockDim.x + threadIdx.x; c <= last; c += stride) {
+            R z[4];
+            PhiloxSource<R, SAMP>{C, c}.load4_stream(STREAM_PACK, 0, z);
+            const ull p0 = c << 2;
+            const bool inner = p0 >= lo && p0 + 4 <= hi;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const R Xf = fma_<R>(X0, co.t(z[k]), X0);
+                double vf = (double)Xf, gf = 0.0;
+                if (FN == FN_AVG) vf = C.avg_wf * ((double)Xf + fma(-0.5, (double)Xf, h0));      // :369-386
+                if (FN == FN_MIN) gf = (double)min_<R>(X0, Xf);                                    // :420
+                const double Pf = payoff_fine(C, vf, gf);
+                if (inner || (p0 + k >= lo && p0 + k < hi)) {
+                    s0 += Pf;
+                    s1 = fma(Pf, Pf, s1);
+                    if (Pf_out || Pc_out || C.raw) {
+                        const ull i = p0 + k - lo;
+                        if (Pf_out) Pf_out[i] = Pf;
+                        if (Pc_out) Pc_out[i] = vc0;                                               // raw coarse output :82
+                        if (C.raw) {
+                            C.raw[i] = vf; C.raw[C.n_paths + i] = gf;
+                            C.raw[2 * C.n_paths + i] = vc0; C.raw[3 * C.n_paths + i] = gc0;
+                        }
+                    }
+                }
+            }
+        }
+        acc.s[0] = acc.s[2] = s0;
+        acc.s[1] = acc.s[3] = s1;
+    } else {
+        for (ull c = first + (ull)blockIdx.x * blockDim.x + threadIdx.x; c <= last; c += stride) {
+            PhiloxSource<R, SAMP> quad{C, c};
+            PackedSource<R> src;
+            quad.load4_stream(STREAM_PACK, 0, src.z);
+#pragma unroll 1
+            for (int k = 0; k < 2; ++k) {
+                const ull pid = c * 2 + k;
+                if (pid < lo || pid >= hi) continue;
+                src.base = 2 * k;
+                double vf, vc, gf, gc;
+                gbm_path_fast<R, FN, 0, SCH>(C, src, vf, vc, gf, gc);
+                emit_t<FN>(C, pid - lo, vf, vc, gf, gc, acc, Pf_out, Pc_out);
+            }
+        }
+    }
+    grid_finish(acc, partials, ticket, out7);
+}
+
 template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH>
 __global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64 : (MODEL == 0 ? MLMCB_MINBLOCKS : MLMCB_MINBLOCKS_MJD))
 level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
@@ -1574,68 +1648,6 @@ level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* 
     Sums7 acc;
     acc.clear();
     const ull stride = (ull)gridDim.x * blockDim.x;
-    if (MODEL == 0 && C.nsteps <= 2) {
-        // The coarsest levels (1 or 2 fine steps per path) are where MLMC puts most of its samples and
-        // a path needs fewer normals than one Philox block holds: 4 (or 2) consecutive global path ids
-        // share one block (stream STREAM_PACK, counter = id / paths-per-block), each taking its own
-        // normals.  Still a pure function of (seed, level, global path id).
-        const int per = C.nsteps == 1 ? 4 : 2;
-        const ull first = C.path_offset / per, last = (C.path_offset + C.n_paths - 1) / per;
-        const ull lo = C.path_offset, hi = C.path_offset + C.n_paths;
-        if (C.nsteps == 1) {
-            // l == 0: one Euler step, no coarse path (:341), sums row [Pf, Pf^2, Pf, Pf^2, 0, 0, 0] (:949)
-            const StepCoef<R, SCH> co(C);
-            const R X0 = (R)C.X0;
-            const double h0 = 0.5 * C.X0, vc0 = FN == FN_AVG ? 0.0 : C.X0, gc0 = FN == FN_MIN ? C.X0 : 0.0;
-            double s0 = 0.0, s1 = 0.0;
-            for (ull c = first + (ull)blockIdx.x * blockDim.x + threadIdx.x; c <= last; c += stride) {
-                R z[4];
-                PhiloxSource<R, SAMP>{C, c}.load4_stream(STREAM_PACK, 0, z);
-                const ull p0 = c << 2;
-                const bool inner = p0 >= lo && p0 + 4 <= hi;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const R Xf = fma_<R>(X0, co.t(z[k]), X0);
-                    double vf = (double)Xf, gf = 0.0;
-                    if (FN == FN_AVG) vf = C.avg_wf * ((double)Xf + fma(-0.5, (double)Xf, h0));      // :369-386
-                    if (FN == FN_MIN) gf = (double)min_<R>(X0, Xf);                                    // :420
-                    const double Pf = payoff_fine(C, vf, gf);
-                    if (inner || (p0 + k >= lo && p0 + k < hi)) {
-                        s0 += Pf;
-                        s1 = fma(Pf, Pf, s1);
-                        if (Pf_out || Pc_out || C.raw) {
-                            const ull i = p0 + k - lo;
-                            if (Pf_out) Pf_out[i] = Pf;
-                            if (Pc_out) Pc_out[i] = vc0;                                               // raw coarse output :82
-                            if (C.raw) {
-                                C.raw[i] = vf; C.raw[C.n_paths + i] = gf;
-                                C.raw[2 * C.n_paths + i] = vc0; C.raw[3 * C.n_paths + i] = gc0;
-                            }
-                        }
-                    }
-                }
-            }
-            acc.s[0] = acc.s[2] = s0;
-            acc.s[1] = acc.s[3] = s1;
-        } else {
-            for (ull c = first + (ull)blockIdx.x * blockDim.x + threadIdx.x; c <= last; c += stride) {
-                PhiloxSource<R, SAMP> quad{C, c};
-                PackedSource<R> src;
-                quad.load4_stream(STREAM_PACK, 0, src.z);
-#pragma unroll 1
-                for (int k = 0; k < 2; ++k) {
-                    const ull pid = c * 2 + k;
-                    if (pid < lo || pid >= hi) continue;
-                    src.base = 2 * k;
-                    double vf, vc, gf, gc;
-                    gbm_path_fast<R, FN, 0, SCH>(C, src, vf, vc, gf, gc);
-                    emit_t<FN>(C, pid - lo, vf, vc, gf, gc, acc, Pf_out, Pc_out);
-                }
-            }
-        }
-        grid_finish(acc, partials, ticket, out7);
-        return;
-    }
     double* const rec = JumpRecStore<MODEL>::column();
     for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
         const ull pid = C.path_offset + i;

@@ -37,6 +37,7 @@ LevelKernel pick_family(int fn, int mt, int flags) {
 }
 
 LevelKernel pick_gbm(int fn, int mt, int flags);              // mlmcb_gbm.cu
+LevelKernel pick_gbm_packed(int fn, int flags);               // mlmcb_gbm.cu: paths of one or two fine steps
 LevelKernel pick_merton_uniform(int fn, int mt, int flags);   // mlmcb_merton_uniform.cu
 LevelKernel pick_merton_flat(int fn, int mt, int flags);      // mlmcb_merton_flat.cu
 
