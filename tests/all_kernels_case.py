@@ -13,7 +13,8 @@ from oracle import np_oracle as O  # noqa: E402
 
 for cls in (mm.Euro_GBM, mm.Asian_GBM, mm.Lookback_GBM, mm.Digital_GBM, mm.Euro_Merton, mm.Asian_Merton,
             mm.Lookback_Merton, mm.Digital_Merton):
-    for (l, M) in ((0, 2), (1, 2), (2, 4), (2, 3)):
+    # GBM: packed kernel (1, 2 steps) and level kernel; Merton: l = 0 loop, event-driven (2, 16, 9 steps), block-uniform (256)
+    for (l, M) in ((0, 2), (1, 2), (2, 4), (2, 3), (8, 2)):
         o = cls(seed=1)
         s = o.looper(3001, l, M, False)
         assert np.isfinite(s).all()
