@@ -272,8 +272,8 @@ def run_b200(args):
         "unit": "G FP64 issue-slots/s (algorithmic 44.5 per coupled fine step, SURVEY 8(d))",
         "frac": achieved / dfma_lane_per_s,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
-        # kernel (profiles/r01_ncu_gbm_euro_f32bm.txt: 98.8 KB read - kernel image and constants - 0 written)
-        "traffic": 98816 if sampler == "f32bm" else None,
+        # kernel (profiles/r01_ncu_gbm_euro_f32bm.txt: 71.7 KB read - kernel image and constants - 0 written)
+        "traffic": 71680 if sampler == "f32bm" else None,
         "peak_source": "DFMA chain micro-benchmark (mlmcb_pipe_probe) measured in this run; "
                        "MEASURED_PEAKS.json has no FP64 entry",
         "kernel_ms_per_launch": ms / args.steps,
