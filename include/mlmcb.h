@@ -34,6 +34,15 @@ typedef struct mlmcb_params {
     double disc;
     double J_bar;
     double boundary_c;   /* MLMCB_AMERICAN: exercise boundary b(t) = max(K*(1 - c*sqrt(T-t)), 0) */
+    /* MLMCB_AMERICAN, optional: a tabulated exercise boundary for callers whose boundary is code the
+     * kernel cannot run (the reference takes any Python callable, Amer_GBM.__init__ :1495-1497).  For a
+     * level l < amer_levels with amer_boundary[l] != NULL the n = 2^l-step table is built from these HOST
+     * values instead of boundary_c:  b(j*dt), j = 0..n  (:1561/:1568)  |  b((j-1)*dt + dt/2), j = 1..n
+     * (:1565/:1571)  |  b((j-2)*dt + M*dt/2), j = 2,4,..,n  (:1593/:1599)  - 2n+1+n/2 doubles, in this
+     * order, evaluated by the caller at exactly those times.  NULL / 0: the boundary_c family. */
+    const double* const* amer_boundary;
+    int amer_levels;
+    int reserved_;
 } mlmcb_params;
 
 enum { MLMCB_GBM = 0, MLMCB_MERTON = 1 };                                   /* model   */

@@ -20,7 +20,8 @@ class Params(C.Structure):
     """struct mlmcb_params (include/mlmcb.h)."""
     _fields_ = [(k, C.c_double) for k in
                 ("X0", "K", "T", "r", "sig", "drift", "lam", "jumpmean", "jumpstd", "beta", "disc", "J_bar",
-                 "boundary_c")]
+                 "boundary_c")] + [("amer_boundary", C.POINTER(C.c_void_p)), ("amer_levels", C.c_int),
+                                   ("reserved_", C.c_int)]
 
 
 class MlmcbError(RuntimeError):

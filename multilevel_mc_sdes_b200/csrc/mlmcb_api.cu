@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 using namespace mlmcb;
 
@@ -134,6 +135,7 @@ int make_consts(const mlmcb_params* p, int model, int payoff, int l, int M, ull 
                                  2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
                                  1.479819860511658591e-01};
     memcpy(C->dq, dq, sizeof dq); memcpy(C->dc, dc, sizeof dc); memcpy(C->lg, lg, sizeof lg);
+    C->amer_vals = (payoff == MLMCB_AMERICAN && p->amer_boundary && l < p->amer_levels) ? p->amer_boundary[l] : nullptr;
     C->ln2_hi = 6.93147180369123816490e-01; C->ln2_lo = 1.90821492927058770002e-10;
     { double f = 1.0; for (int k = 2; k <= 13; ++k) { f *= (double)k; C->ex[k - 2] = 1.0 / f; } }
     C->r = p->r; C->boundary_c = p->boundary_c;
@@ -273,6 +275,32 @@ constexpr ull kAmerMaxSteps = 1ull << 22;
 int amer_table(const LevelConsts& C, cudaStream_t st, AmerRow** tab) {
     if (C.nsteps > kAmerMaxSteps) return fail(MLMCB_EINVAL, "American put: M**l above 2^22 fine steps is not supported");
     CU(cudaMallocAsync((void**)tab, (size_t)(C.nsteps + 1) * sizeof(AmerRow), st));
+    if (C.amer_vals) {
+        // tabulated boundary: the same rows as amer_table_kernel, built here from the caller's values
+        // (b on the grid | at the fine mid-points | at the coarse mid-points), same operation order
+        const ull n = C.nsteps;
+        const double *bg = C.amer_vals, *bf = bg + n + 1, *bc = bf + n;
+        std::vector<AmerRow> rows(n + 1);
+        for (ull j = 0; j <= n; ++j) {
+            AmerRow row = {0, 0, 0, 0, 0, 0, 0, 0};
+            row.bR = bg[j];
+            if (j >= 1) {
+                const double t_ = (double)(j - 1) * C.dt, tm = t_ + C.dt / 2.0;                 // :1546, :1562
+                row.mkF = fmax(C.K - bf[j - 1], 0.0);
+                row.eF = exp(-C.r * tm);                                                       // :1571
+                if (j % 2 == 0) {
+                    const double tc = (double)(j - 2) * C.dt, tcm = tc + C.Mdt / 2.0;           // :1580, :1590
+                    row.mkC = fmax(C.K - bc[j / 2 - 1], 0.0);
+                    row.eC = exp(-C.r * tcm);                                                  // :1605
+                    row.mb1 = 0.5 * (row.bR + bg[j - 2]);                                      // :1599
+                }
+            }
+            rows[j] = row;
+        }
+        CU(cudaMemcpyAsync(*tab, rows.data(), rows.size() * sizeof(AmerRow), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));          // `rows` must outlive the copy
+        return 0;
+    }
     const int threads = 128;
     const int blocks = (int)((C.nsteps + 1 + threads - 1) / threads);
     amer_table_kernel<<<blocks, threads, 0, st>>>(C, *tab);

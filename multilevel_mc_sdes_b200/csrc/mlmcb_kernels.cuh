@@ -99,6 +99,7 @@ struct LevelConsts {
     // fp64 sampler constants, read straight from the constant bank by DFMA (no 64-bit immediates exist)
     double dq[9], dc[9], lg[7], ln2_hi, ln2_lo;
     double ex[12];                  // 1/k!, k = 2..13 (exp_bounded)
+    const double* amer_vals;        // HOST pointer (never read on the device): tabulated exercise boundary of this level, or null
 };
 
 // ------------------------------------------------------------------------------------------

@@ -165,7 +165,7 @@ class Option:
         dev = torch.device("cuda", self.device)
         raw = torch.empty((rows, n), dtype=torch.float64, device=dev)
         out7 = torch.empty(7, dtype=torch.float64, device=dev)
-        p = self._params()
+        p = self._params((int(l),))
         _lib.check(_lib.load().mlmcb_level_paths(
             C.byref(p), self._model, self._payoff_kind, int(l), int(M), n, self.seed, start, flags,
             self.device, _stream_handle(self.device), out7.data_ptr(), raw.data_ptr()))
@@ -181,7 +181,8 @@ class Option:
         raise NotImplementedError("Option instance has no implemented asset_plot method")
 
     # -- plumbing ----------------------------------------------------------------------------
-    def _params(self):
+    def _params(self, levels=()):
+        """struct mlmcb_params for a call that touches `levels` (only Amer_GBM looks at them)."""
         p = _lib.Params()
         p.X0 = float(self.X0)
         p.K = float(self.K) if self.K is not None else 0.0
@@ -251,7 +252,7 @@ class Option:
         Pf = torch.empty(n, dtype=torch.float64, device=dev)
         Pc = torch.empty(n, dtype=torch.float64, device=dev)
         out7 = torch.empty(7, dtype=torch.float64, device=dev)
-        p = self._params()
+        p = self._params((int(l),))
         _lib.check(_lib.load().mlmcb_level_sums(
             C.byref(p), self._model, self._payoff_kind, int(l), int(M), n, self.seed, start,
             self._flags() | extra_flags,
@@ -279,7 +280,7 @@ class Option:
         dev = torch.device("cuda", self.device)
         if out is None:
             out = torch.empty(7, dtype=torch.float64, device=dev)
-        p = self._params()
+        p = self._params((int(l),))
         _lib.check(_lib.load().mlmcb_level_sums(
             C.byref(p), self._model, self._payoff_kind, int(l), int(M), n_loc, self.seed, start_loc,
             self._flags() | (_lib.ANTITHETIC if anti else 0), self.device, _stream_handle(self.device),
@@ -305,7 +306,7 @@ class Option:
         n_arr = (C.c_uint64 * k)(*counts)
         o_arr = (C.c_uint64 * k)(*offsets)
         out = np.zeros((k, 7))
-        p = self._params()
+        p = self._params(tuple(int(l) for _, l in requests))
         _lib.check(_lib.load().mlmcb_level_sweep_host(
             C.byref(p), self._model, self._payoff_kind, int(M), k, levels, n_arr, o_arr, self.seed,
             self._flags() | (_lib.ANTITHETIC if anti else 0), self.device, _stream_handle(self.device),
@@ -328,7 +329,7 @@ class Option:
             if not self._has_anti:
                 raise NotImplementedError("Option instance has no implemented anti_payoff method")
             ar |= _lib.ANTITHETIC
-        p = self._params()
+        p = self._params((int(l),))
         st = _stream_handle(self.device)
         if self._model == GBM:
             Z = torch.as_tensor(np.ascontiguousarray(draws, dtype=np.float64), device=dev)
@@ -503,19 +504,59 @@ def sqrt_boundary(c=0.8):
 
 class Amer_GBM(GBM_Option):
     """American put under GBM (reference Amer_GBM :1483-1632, Amer_payoff :138-158): barrier-crossing
-    probabilities between grid points, M must be 2 (:1524).  `exerciseBoundary` is `sqrt_boundary(c)`
-    or just the number c; an arbitrary Python callable cannot be evaluated inside the kernel and is
-    rejected (NotImplementedError) rather than silently run on the host."""
+    probabilities between grid points, M must be 2 (:1524).  `exerciseBoundary` is what the reference takes -
+    any callable `b(self, t)` (:1495-1497, called as `exerciseBoundary(self, t)` :1561) - or `sqrt_boundary(c)` /
+    the number c for the demo notebook's family K(1 - c sqrt(T-t)), which the library tabulates on the device.
+    A general callable is evaluated HERE, on the host, once per level, at exactly the times the reference
+    evaluates it (grid points :1561/:1568, fine mid-points :1565, coarse mid-points :1593), and only the values
+    travel to the library (mlmcb_params.amer_boundary); the path simulation stays on the GPU."""
     _payoff_kind = AMERICAN
 
     def __init__(self, exerciseBoundary=0.8, **kwargs):
         super().__init__(**kwargs)
         c = getattr(exerciseBoundary, "mlmcb_c", exerciseBoundary)
+        self._boundary_tables = {}
         if callable(c):
-            raise NotImplementedError(
-                "Amer_GBM on the GPU supports the boundary family K*(1-c*sqrt(T-t)): pass sqrt_boundary(c) or c")
-        self.boundary_c = float(c)
-        self.exerciseBoundary = exerciseBoundary if callable(exerciseBoundary) else sqrt_boundary(self.boundary_c)
+            self.boundary_c = 0.0
+            self.exerciseBoundary = exerciseBoundary
+            self._tabulated = True
+        else:
+            self.boundary_c = float(c)
+            self.exerciseBoundary = sqrt_boundary(self.boundary_c)
+            self._tabulated = False
+
+    def _boundary_values(self, l):
+        """b on the grid | fine mid-points | coarse mid-points of level l (M = 2), as float64, cached per level
+        and parameter set."""
+        key = (int(l), float(self.T), float(self.K), float(self.X0), float(self.r), float(self.sig))
+        tab = self._boundary_tables.get(key)
+        if tab is None:
+            n, M = 2 ** int(l), 2
+            dt = self.T / n                                              # :1529
+            b = self.exerciseBoundary
+            grid = [b(self, j * dt) for j in range(n + 1)]               # t_ = (j-1)*dt :1546, j*dt :1568
+            fmid = [b(self, (j - 1) * dt + dt / 2) for j in range(1, n + 1)]                 # :1562
+            cmid = [b(self, (j - M) * dt + M * dt / 2) for j in range(2, n + 1, 2)]          # :1580, :1590
+            tab = np.ascontiguousarray(np.array(grid + fmid + cmid, dtype=np.float64).reshape(-1))
+            if tab.size != 2 * n + 1 + n // 2:
+                raise ValueError("exerciseBoundary(self, t) must return one number per call")
+            self._boundary_tables[key] = tab
+        return tab
+
+    def _params(self, levels=()):
+        p = super()._params(levels)
+        if self._tabulated and levels:
+            top = max(levels)
+            ptrs = (C.c_void_p * (top + 1))()
+            keep = []
+            for l in set(levels):
+                tab = self._boundary_values(l)
+                keep.append(tab)
+                ptrs[l] = tab.ctypes.data
+            p.amer_boundary = C.cast(ptrs, C.POINTER(C.c_void_p))
+            p.amer_levels = top + 1
+            p._keep_alive = (ptrs, keep)                                 # host memory the library reads during the call
+        return p
 
 
 class Euro_Merton(Merton_Option):

@@ -383,13 +383,37 @@ def closed_forms(ref):
     return out
 
 
+def amer_callable_cases(ref):
+    """Amer_GBM with exercise boundaries outside the square-root family (oracle/boundaries.py): what the
+    host-tabulated boundary path of the library has to reproduce."""
+    from oracle.boundaries import BOUNDARIES
+    out = {}
+    idx = 0
+    for bname, fn in BOUNDARIES.items():
+        for kw_name, kw in (("default", {}), ("alt2", ALT_GBM2)):
+            for l in (0, 1, 2, 4, 6):
+                n = 96 if l <= 4 else 32
+                seed = 9700 + idx
+                opt = ref.Amer_GBM(exerciseBoundary=fn, **kw)
+                np.random.seed(seed)
+                Pf, Pc = opt.payoff(n, l, 2)
+                out[f"c{idx}_meta"] = np.array(["Amer_GBM", kw_name, str(l), "2", str(n), str(seed), bname])
+                out[f"c{idx}_Pf"] = np.asarray(Pf, dtype=np.float64)
+                out[f"c{idx}_Pc"] = np.asarray(Pc, dtype=np.float64) * np.ones(n)
+                idx += 1
+    out["n_cases"] = np.array(idx)
+    return out
+
+
 def main():
     ref = load_reference()
     os.makedirs(OUT, exist_ok=True)
     for name, fn in (("payoffs_gbm", gbm_cases), ("payoffs_merton", merton_cases), ("payoffs_anti", anti_cases),
                      ("payoffs_milstein", milstein_cases), ("payoffs_amer", amer_cases),
-                     ("looper", looper_cases),
+                     ("payoffs_amer_callable", amer_callable_cases), ("looper", looper_cases),
                      ("mlmc_trace", mlmc_traces), ("closed_forms", closed_forms)):
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:       # python oracle/make_golden.py [file ...]
+            continue
         d = fn(ref)
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **d)

@@ -199,6 +199,45 @@ def test_american_put_replay(golden, cuda_lib, c_oracle):
         mm.Amer_GBM().payoff_replay(np.zeros((16, 4)), 2, 4)
 
 
+def test_american_put_with_tabulated_boundary_matches_reference(cuda_lib, golden):
+    """Amer_GBM(exerciseBoundary=<any callable>), the reference's contract (:1495-1497): the callable is evaluated
+    on the host at the reference's times and only the values enter the library.  Fixtures: the reference run with
+    the two boundaries of oracle/boundaries.py (neither is of the square-root family)."""
+    from oracle.boundaries import BOUNDARIES
+    n = 0
+    g = golden["payoffs_amer_callable"]
+    for i in range(int(g["n_cases"])):
+        cname, kw_name, l, M, npaths, seed, bname = [str(x) for x in g[f"c{i}_meta"]]
+        c = dict(l=int(l), M=int(M), n=int(npaths), seed=int(seed), Z=None)
+        kw = case_kwargs("Euro_GBM", kw_name)
+        p = O.Params(**kw)
+        opt = mm.Amer_GBM(exerciseBoundary=BOUNDARIES[bname], **kw)
+        Z = regen_Z(c)
+        for arith in ("exact", "fast"):
+            Pf, Pc = opt.payoff_replay(Z, c["l"], 2, arith=arith)
+            assert np.all(np.abs(Pf - g[f"c{i}_Pf"]) <= payoff_tol(p, g[f"c{i}_Pf"])), (i, arith, np.abs(Pf - g[f"c{i}_Pf"]).max())
+            assert np.all(np.abs(Pc - g[f"c{i}_Pc"]) <= payoff_tol(p, g[f"c{i}_Pc"])), (i, arith, np.abs(Pc - g[f"c{i}_Pc"]).max())
+        n += 1
+    assert n == 20
+    # the tabulated path and the device-tabulated family agree when the callable IS the family
+    fam = lambda self, t: np.maximum(self.K * (1 - 0.8 * np.sqrt(self.T - t)), 0)       # the notebook's exb, unwrapped
+    Z = np.random.RandomState(3).randn(2 ** 5, 200)
+    a = mm.Amer_GBM(exerciseBoundary=fam).payoff_replay(Z, 5, 2, arith="exact")
+    b = mm.Amer_GBM(exerciseBoundary=0.8).payoff_replay(Z, 5, 2, arith="exact")
+    for x, y in zip(a, b):
+        assert np.all(np.abs(x - y) <= payoff_tol(O.Params(), y))
+    # production kernels: sums, per-path payoffs, paths and a sweep all take the table
+    opt = mm.Amer_GBM(exerciseBoundary=BOUNDARIES["power"], seed=5)
+    s = opt.looper(200_000, 4, 2, False)
+    opt2 = mm.Amer_GBM(exerciseBoundary=BOUNDARIES["power"], seed=5)
+    Pf, Pc = opt2.payoff(200_000, 4, 2)
+    np.testing.assert_allclose(s, O.seven_sums(Pf, Pc, 4), rtol=1e-12)
+    sw = mm.Amer_GBM(exerciseBoundary=BOUNDARIES["linear"], seed=6).level_sweep(Lmax=3, Nsamples=20_000, M=2)
+    assert sw.shape == (7, 4) and np.isfinite(sw).all() and sw[2, 0] > 0
+    F, Cc = mm.Amer_GBM(exerciseBoundary=BOUNDARIES["linear"], seed=6).path(1000, 3, 2)
+    assert F.shape == (1000, 3) and Cc.shape == (1000, 3)
+
+
 def test_randomised_parameters_bit_exact_against_c_oracle(cuda_lib, c_oracle):
     """40 seeded random parameter sets / shapes (odd path counts, M in 2..6, every GBM product, plain,
     Milstein and antithetic): the reference-order policy must equal the pinned C restatement bit for bit,

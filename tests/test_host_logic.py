@@ -31,7 +31,8 @@ def test_params_struct_layout_matches_header():
     body = re.search(r"typedef struct mlmcb_params \{(.*?)\} mlmcb_params;", text, re.S).group(1)
     fields = re.findall(r"\b([A-Za-z_0-9]+)\s*[,;]", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
     assert fields == [f for f, _ in _lib.Params._fields_]
-    assert ctypes.sizeof(_lib.Params) == 8 * len(fields)
+    # 13 doubles, one pointer, two ints
+    assert ctypes.sizeof(_lib.Params) == 13 * 8 + 8 + 2 * 4 and len(fields) == 16
 
 
 def test_philox_known_answers():
@@ -168,8 +169,20 @@ def test_amer_gbm_surface():
     assert a.boundary_c == 0.7 and a._params().boundary_c == 0.7
     assert a.exerciseBoundary(a, 0.5) == max(95 * (1 - 0.7 * np.sqrt(0.5)), 0)
     assert mm.Amer_GBM().boundary_c == 0.8 and mm.Amer_GBM(0.6).boundary_c == 0.6
-    with pytest.raises(NotImplementedError):
-        mm.Amer_GBM(exerciseBoundary=lambda self, t: 90.0)       # arbitrary callbacks cannot enter the kernel
+    assert a._params((3,)).amer_levels == 0                      # the family is tabulated on the device
+    # any other callable (the reference's contract, :1495-1497) is evaluated on the host, once per level, at the
+    # reference's times: grid points, fine mid-points, coarse mid-points
+    calls = []
+    g = mm.Amer_GBM(exerciseBoundary=lambda self, t: calls.append(t) or self.K * (0.8 + 0.1 * t), K=90, T=2.0)
+    p = g._params((0, 2))
+    assert p.amer_levels == 3 and not p.amer_boundary[1] and p.amer_boundary[0] and p.amer_boundary[2]
+    tab = g._boundary_values(2)
+    dt = 2.0 / 4
+    want_t = [j * dt for j in range(5)] + [(j - 1) * dt + dt / 2 for j in range(1, 5)] + [(j - 2) * dt + 2 * dt / 2 for j in (2, 4)]
+    assert np.array_equal(tab, [90 * (0.8 + 0.1 * t) for t in want_t])
+    n_calls = len(calls)
+    g._params((2,))
+    assert len(calls) == n_calls                                 # cached per level
 
 
 def test_path_ids_advance_per_level(monkeypatch):
