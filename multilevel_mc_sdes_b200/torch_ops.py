@@ -4,7 +4,8 @@ of a torch program, current stream, no host synchronisation).  A thin registrati
 
     import multilevel_mc_sdes_b200.torch_ops        # registers the op
     out = torch.ops.mlmcb.level_sums(params, model, payoff, l, M, n_paths, seed, path_offset, flags, device)
-    # params: the 13 doubles of struct mlmcb_params in order; out: float64[7] on cuda:device
+    # params: the 13 doubles of struct mlmcb_params in order (a tabulated American boundary is not supported
+    # through this op); out: float64[7] on cuda:device
 """
 import ctypes as C
 
@@ -33,4 +34,4 @@ def _(params, model, payoff, l, M, n_paths, seed, path_offset, flags, device):
 def option_params(opt):
     """The `params` list of an Option from this package."""
     p = opt._params()
-    return [getattr(p, name) for name, _ in _lib.Params._fields_]
+    return [getattr(p, name) for name, ctype in _lib.Params._fields_ if ctype is C.c_double]
