@@ -155,7 +155,7 @@ int mlmcb_launch_geometry(int model, int payoff, int M, int flags, int device,
 
 void mlmcb_params_fill_derived(mlmcb_params* p);   /* disc = exp(-r*T), J_bar = exp(m+s^2/2)-1 */
 const char* mlmcb_last_error(void);
-int mlmcb_version(void);
+int mlmcb_version(void);                            /* 101 (100: mlmcb_params without amer_boundary/amer_levels) */
 
 #ifdef __cplusplus
 }

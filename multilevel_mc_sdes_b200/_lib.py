@@ -14,6 +14,7 @@ ANTITHETIC = 0x20
 MILSTEIN = 0x40
 ARITH_FAST, ARITH_EXACT = 0, 1
 OK, EINVAL, ECUDA, ENOTIMPL = 0, -1, -2, -3
+ABI_VERSION = 101
 
 
 class Params(C.Structure):
@@ -77,6 +78,8 @@ def load():
         fn = getattr(lib, name)      # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
+    if lib.mlmcb_version() != ABI_VERSION:      # a stale build would read struct mlmcb_params with another layout
+        raise MlmcbError(f"{LIB_PATH} has ABI version {lib.mlmcb_version()}, this package needs {ABI_VERSION}: rebuild it")
     _lib = lib
     return lib
 

@@ -387,7 +387,7 @@ int host_side(int dev, HostSide** out) {
 extern "C" {
 
 const char* mlmcb_last_error(void) { return g_err; }
-int mlmcb_version(void) { return 100; }
+int mlmcb_version(void) { return 101; }      // 101: mlmcb_params grew amer_boundary / amer_levels
 
 void mlmcb_params_fill_derived(mlmcb_params* p) {
     if (!p) return;
