@@ -24,6 +24,8 @@ def test_integration_stub_runs_against_the_reference():
         original = ref.Option.looper
         ns = {}
         exec(code, ns)
+        import ctypes
+        assert ctypes.sizeof(ns["_P"]) == ctypes.sizeof(_lib.Params)      # the stub's struct is the header's
         want = {"Euro_GBM": (0, 0), "Asian_GBM": (0, 1), "Lookback_GBM": (0, 2), "Digital_GBM": (0, 3),
                 "Euro_Merton": (1, 0), "Asian_Merton": (1, 1), "Lookback_Merton": (1, 2), "Digital_Merton": (1, 3)}
         import torch
