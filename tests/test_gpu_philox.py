@@ -456,6 +456,48 @@ def test_philox_mode_equals_replay_of_its_own_draws_gbm(cuda_lib, sampler):
     np.testing.assert_allclose(Pc, Rc, rtol=1e-13, atol=1e-11)
 
 
+def test_philox_mode_equals_replay_of_its_own_draws_gbm_random_parameters(cuda_lib):
+    """The same with random model parameters, path-id offsets and levels: the packed kernel (1-2 steps), the
+    level kernel, and the American-put kernel with a host-tabulated boundary (T != 1 moves every table time)."""
+    import torch
+    from oracle.boundaries import BOUNDARIES
+    rng = np.random.default_rng(31415)
+    classes = (mm.Euro_GBM, mm.Asian_GBM, mm.Lookback_GBM, mm.Digital_GBM)
+    levels = ((0, 2), (1, 2), (0, 4), (2, 2), (1, 4), (1, 3), (3, 2), (2, 4), (2, 5), (6, 2), (3, 4))
+    for it in range(22):
+        kw = dict(X0=float(rng.uniform(5, 400)), T=float(rng.uniform(0.1, 4.0)), r=float(rng.uniform(-0.01, 0.12)),
+                  sig=float(rng.uniform(0.02, 0.8)))
+        kw["K"] = kw["X0"] * float(rng.uniform(0.6, 1.4))
+        cls = classes[it % 4]
+        l, M = levels[it % len(levels)]
+        n, off, seed = 500, int(rng.integers(0, 2 ** 44)), int(rng.integers(0, 2 ** 31))
+        opt = cls(seed=seed, **kw)
+        opt._next_path[l] = off
+        Pf, Pc = opt.payoff(n, l, M)
+        nsteps = M ** l
+        if nsteps <= 2:
+            out = torch.empty(nsteps * n, dtype=torch.float64, device="cuda")
+            _lib.check(cuda_lib.mlmcb_packed_probe(_lib.SAMPLER_F32BM, seed, l, nsteps, off, n, 0, 0, out.data_ptr()))
+            torch.cuda.synchronize()
+            Z = out.cpu().numpy().reshape(nsteps, n)
+        else:
+            Z = _probe_normals(cuda_lib, _lib.SAMPLER_F32BM, seed, l, off, n, nsteps)
+        Rf, Rc = cls(**kw).payoff_replay(Z, l, M, arith="fast")
+        scale = 1e-12 * max(kw["X0"], kw["K"])
+        np.testing.assert_allclose(Pf, Rf, rtol=1e-12, atol=scale)
+        np.testing.assert_allclose(Pc, Rc, rtol=1e-12, atol=scale)
+    for bname, l in (("power", 3), ("linear", 6), ("power", 0)):
+        kw = dict(X0=float(rng.uniform(50, 150)), T=float(rng.uniform(0.3, 2.5)), r=0.04, sig=float(rng.uniform(0.1, 0.5)))
+        kw["K"] = kw["X0"] * 1.05
+        opt = mm.Amer_GBM(exerciseBoundary=BOUNDARIES[bname], seed=12, **kw)
+        opt._next_path[l] = 9000
+        Pf, Pc = opt.payoff(400, l, 2)
+        Z = _probe_normals(cuda_lib, _lib.SAMPLER_F32BM, 12, l, 9000, 400, 2 ** l)
+        Rf, Rc = mm.Amer_GBM(exerciseBoundary=BOUNDARIES[bname], **kw).payoff_replay(Z, l, 2, arith="fast")
+        np.testing.assert_allclose(Pf, Rf, rtol=1e-12, atol=1e-10)
+        np.testing.assert_allclose(Pc, Rc, rtol=1e-12, atol=1e-10)
+
+
 def _merton_own_draws_case(cuda_lib, cls, kw, l, M, n=600, off=999, seed=17, K=64):
     """Per-path payoffs of the production Merton kernel against the replay of its own draws: grid normals
     from the sampler probe, jump records from the jump probe, interleaved on the host in the order the
