@@ -52,14 +52,17 @@ enum { MLMCB_EURO = 0, MLMCB_ASIAN = 1, MLMCB_LOOKBACK = 2, MLMCB_DIGITAL = 3,  
 
 /* flags for the Philox-mode level function */
 enum {
-    MLMCB_SAMPLER_F32BM = 0,   /* default: 32-bit uniforms, fp32 Box-Muller, promoted to fp64      */
-    MLMCB_SAMPLER_F64BM = 1,   /* canonical: 53-bit uniforms, fp64 Box-Muller (log/sqrt/sincospi)  */
+    MLMCB_SAMPLER_F64BM = 0,   /* default: 52-bit uniforms, fp64 Box-Muller (table-driven log, Newton sqrt,
+                                  table + polynomial sin/cos, <= 1 ulp) - the precision of the reference's
+                                  numpy normals                                                        */
+    MLMCB_SAMPLER_F32BM = 1,   /* opt-in: 32-bit uniforms, fp32 Box-Muller (MUFU log/sqrt), promoted to fp64;
+                                  about twice the throughput, fp32-grade draws (Merton: fp32 Exp() gaps)  */
     MLMCB_SAMPLER_MASK  = 0xF,
-    MLMCB_FP32_PATHS    = 0x10,/* opt-in: path arithmetic in fp32 (sums stay fp64); F32BM sampler  */
+    MLMCB_FP32_PATHS    = 0x10,/* opt-in: path arithmetic in fp32 (sums stay fp64), Euler-Maruyama only       */
     MLMCB_MILSTEIN      = 0x40,/* Milstein instead of Euler-Maruyama increments: the reference's demo
                                   notebook swaps `sde` for milstein_GBM / milstein_Merton
-                                  (ExampleUsages.ipynb cell 1: + 0.5*X*sig**2*(dW**2-dt)).  fp64 paths and
-                                  the default sampler only, not with MLMCB_ANTITHETIC -> MLMCB_ENOTIMPL.
+                                  (ExampleUsages.ipynb cell 1: + 0.5*X*sig**2*(dW**2-dt)).  Every sampler, with or
+                                  without MLMCB_ANTITHETIC; fp64 paths only (with MLMCB_FP32_PATHS -> MLMCB_ENOTIMPL).
                                   May also be ORed into `arith` of the replay entry points.          */
     MLMCB_ANTITHETIC    = 0x20 /* antithetic estimator (looper(anti=True) :941-942): GBM Euro/Asian
                                   only (anti_EA_payoff :292-317, diffusion_anti_path(_avg) :162-290),
@@ -105,11 +108,22 @@ int mlmcb_level_sums_host(const mlmcb_params* p, int model, int payoff, int l, i
                           int device, void* cuda_stream, double* h_out7);
 
 /* One sweep of Option.mlmc's inner `for l in range(L+1)` (:994-997): n_levels independent
- * level calls issued concurrently (internal side streams), one D2H of h_out[n_levels][7].
+ * level calls in one launch (see mlmcb_level_sweep), one D2H of h_out[n_levels][7].
  * levels[i] is the level index, n_paths[i] may be 0 (row left zero).                        */
 int mlmcb_level_sweep_host(const mlmcb_params* p, int model, int payoff, int M, int n_levels,
                            const int* levels, const uint64_t* n_paths, const uint64_t* path_offsets,
                            uint64_t seed, int flags, int device, void* cuda_stream, double* h_out);
+
+/* The same sweep without the host hop: rows of EIGHT doubles (seven sums + one pad) into d_out[n_levels][8]
+ * on the device, asynchronous on `cuda_stream`.  A multi-GPU caller all-reduces d_out in place (NCCL) and
+ * copies it back once.  Plain estimator on fp64 paths (either scheme, either sampler): ONE
+ * kernel launch for all levels - the grid is cut into per-level block ranges, deepest level first - on a
+ * persistent workspace (no allocation, no memset); other requests (antithetic, fp32 paths, American put, more
+ * than 20 non-empty levels) run as concurrent per-level launches.  Consecutive sweeps on one device are
+ * ordered among themselves, whatever streams they are issued on.                                         */
+int mlmcb_level_sweep(const mlmcb_params* p, int model, int payoff, int M, int n_levels,
+                      const int* levels, const uint64_t* n_paths, const uint64_t* path_offsets,
+                      uint64_t seed, int flags, int device, void* cuda_stream, double* d_out);
 
 /* ---- replay mode (parity check (a) of the north star) ------------------------------------
  * Feeds the reference's own draws.  GBM: d_Z[step*n_paths + path] is the np.random.randn(N_loop)
@@ -155,7 +169,7 @@ int mlmcb_launch_geometry(int model, int payoff, int M, int flags, int device,
 
 void mlmcb_params_fill_derived(mlmcb_params* p);   /* disc = exp(-r*T), J_bar = exp(m+s^2/2)-1 */
 const char* mlmcb_last_error(void);
-int mlmcb_version(void);                            /* 101 (100: mlmcb_params without amer_boundary/amer_levels) */
+int mlmcb_version(void);                            /* 102 (101: flags == 0 meant the fp32 sampler; 100: mlmcb_params without amer_boundary/amer_levels) */
 
 #ifdef __cplusplus
 }

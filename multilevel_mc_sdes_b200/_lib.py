@@ -8,13 +8,13 @@ LIB_PATH = os.environ.get("MLMCB_LIB") or os.path.join(_HERE, "csrc", "libmlmcb.
 
 GBM, MERTON = 0, 1
 EURO, ASIAN, LOOKBACK, DIGITAL, AMERICAN = 0, 1, 2, 3, 4
-SAMPLER_F32BM, SAMPLER_F64BM = 0, 1
+SAMPLER_F64BM, SAMPLER_F32BM = 0, 1      # flags == 0: the fp64 sampler; fp32 is the opt-in
 FP32_PATHS = 0x10
 ANTITHETIC = 0x20
 MILSTEIN = 0x40
 ARITH_FAST, ARITH_EXACT = 0, 1
 OK, EINVAL, ECUDA, ENOTIMPL = 0, -1, -2, -3
-ABI_VERSION = 101
+ABI_VERSION = 102
 
 
 class Params(C.Structure):
@@ -45,6 +45,9 @@ SIGNATURES = {
     "mlmcb_level_sweep_host": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(C.c_int), C.POINTER(_u64), C.POINTER(_u64), _u64,
                                          C.c_int, C.c_int, _vp, _dp]),
+    "mlmcb_level_sweep": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(C.c_int), C.POINTER(_u64), C.POINTER(_u64), _u64,
+                                    C.c_int, C.c_int, _vp, _vp]),
     "mlmcb_replay_gbm": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.c_int, _u64, _vp, C.c_int, C.c_int,
                                    _vp, _vp, _vp, _vp]),
     "mlmcb_replay_merton": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.c_int, _u64, _vp, _vp, _vp, _vp,

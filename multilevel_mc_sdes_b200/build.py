@@ -7,9 +7,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmlmcb.so")
-# one translation unit per kernel family, compiled side by side
-SOURCES = ["mlmcb_api.cu", "mlmcb_gbm.cu", "mlmcb_merton_uniform.cu", "mlmcb_merton_flat.cu"]
-HEADERS = ["mlmcb_kernels.cuh", "mlmcb_pick.cuh", os.path.join("..", "..", "include", "mlmcb.h")]
+# one translation unit per (kernel family, sampler), compiled side by side: (source, object name, extra -D flags)
+UNITS = [("mlmcb_api.cu", "api.o", [])] + [
+    ("mlmcb_family.cu", f"family{fam}_s{samp}.o", [f"-DMLMCB_TU_FAMILY={fam}", f"-DMLMCB_TU_SAMP={samp}"])
+    for fam in (0, 1, 2, 3, 4) for samp in (0, 1)]
+SOURCES = ["mlmcb_api.cu", "mlmcb_family.cu"]
+HEADERS = ["mlmcb_kernels.cuh", "mlmcb_pick.cuh", "mlmcb_f64tab.inc", os.path.join("..", "..", "include", "mlmcb.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -38,9 +41,9 @@ def compile_lib(out, extra=(), verbose=False):
     os.makedirs(objdir, exist_ok=True)
     flags = NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else [])
     procs = []
-    for src in SOURCES:
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        procs.append((obj, subprocess.Popen([nvcc_path()] + flags + ["-c", "-o", obj, src], cwd=CSRC,
+    for src, objname, defs in UNITS:
+        obj = os.path.join(objdir, objname)
+        procs.append((obj, subprocess.Popen([nvcc_path()] + flags + defs + ["-c", "-o", obj, src], cwd=CSRC,
                                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log, ok = "", True
     for obj, p in procs:

@@ -6,7 +6,9 @@
 #include "mlmcb_pick.cuh"
 
 #include <math.h>
+#include <algorithm>
 #include <map>
+#include <stddef.h>
 #include <mutex>
 #include <stdarg.h>
 #include <stdio.h>
@@ -45,7 +47,7 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-struct DeviceInfo { int sms = 0; bool pool_ready = false; };
+struct DeviceInfo { int sms = 0; cudaMemPool_t pool = nullptr; };
 DeviceInfo g_dev[64];
 std::mutex g_dev_mu;               // first-use initialisation of g_dev / g_host entries
 
@@ -56,10 +58,16 @@ int device_info(int dev, DeviceInfo** out) {
     if (!d.sms) {
         int sms = 0;
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        cudaMemPool_t pool;
-        CU(cudaDeviceGetDefaultMemPool(&pool, dev));
-        unsigned long long keep = ~0ull;   // keep freed workspace blocks cached in the pool
-        CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        // a pool of the library's own for the stream-ordered workspace: its release threshold keeps freed
+        // blocks cached without changing the trimming behaviour of the process's default pool
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        CU(cudaMemPoolCreate(&d.pool, &props));
+        unsigned long long keep = ~0ull;
+        CU(cudaMemPoolSetAttribute(d.pool, cudaMemPoolAttrReleaseThreshold, &keep));
         d.sms = sms;
     }
     *out = &d;
@@ -135,6 +143,14 @@ int make_consts(const mlmcb_params* p, int model, int payoff, int l, int M, ull 
                                  2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
                                  1.479819860511658591e-01};
     memcpy(C->dq, dq, sizeof dq); memcpy(C->dc, dc, sizeof dc); memcpy(C->lg, lg, sizeof lg);
+    // table-driven fp64 Box-Muller (tools/gen_f64bm_tables.py): G(x) = x + x^2 Q(x); sin(pi d)/d and (cos(pi d) - 1)/d^2 in d^2
+    static const double lq[5] = {0x1.0000000000000p-2, 0x1.55555555279e5p-4, 0x1.ffffffffafffbp-6, 0x1.999b07519179fp-7,
+                                 0x1.5556955655562p-8};
+    static const double ts[3] = {0x1.921fb54442d18p+1, -0x1.4abbce625a8c0p+2, 0x1.466ba9b398947p+1};
+    static const double tc[2] = {-0x1.3bd3cc9be3b30p+2, 0x1.03c1db247a00ep+2};
+    memcpy(C->lq, lq, sizeof lq); memcpy(C->ts, ts, sizeof ts); memcpy(C->tc, tc, sizeof tc);
+    C->neg2ln2 = -0x1.62e42fefa39efp+0;
+    C->one_hi = 0x3ff00000u;
     C->amer_vals = (payoff == MLMCB_AMERICAN && p->amer_boundary && l < p->amer_levels) ? p->amer_boundary[l] : nullptr;
     C->ln2_hi = 6.93147180369123816490e-01; C->ln2_lo = 1.90821492927058770002e-10;
     { double f = 1.0; for (int k = 2; k <= 13; ++k) { f *= (double)k; C->ex[k - 2] = 1.0 / f; } }
@@ -174,8 +190,15 @@ uint32_t run_blocks_for(ull nsteps) {
 
 LevelKernel pick_kernel(int model, int payoff, int M, int flags, ull nsteps) {
     const int fn = fn_of(payoff), mt = mt_of(M);
-    if (model == MLMCB_GBM) return nsteps <= 2 ? pick_gbm_packed(fn, flags) : pick_gbm(fn, mt, flags);
-    return nsteps < flat_below() ? pick_merton_flat(fn, mt, flags) : pick_merton_uniform(fn, mt, flags);
+    const bool f64 = (flags & MLMCB_SAMPLER_MASK) == MLMCB_SAMPLER_F64BM;
+    if (model == MLMCB_GBM) {
+        // the coarsest levels have kernels of their own: 1 or 2 fine steps, and 4 (M = 4, l = 1 / M = 2, l = 2)
+        const int packed = nsteps <= 2 ? 1 : (nsteps == 4 && M == 4) ? 4 : (nsteps == 4 && M == 2) ? -4 : 0;
+        if (packed) return f64 ? pick_gbm_packed_s<1>(fn, flags, packed) : pick_gbm_packed_s<0>(fn, flags, packed);
+        return f64 ? pick_gbm_s<1>(fn, mt, flags) : pick_gbm_s<0>(fn, mt, flags);
+    }
+    if (nsteps < flat_below()) return f64 ? pick_merton_flat_s<1>(fn, mt, flags) : pick_merton_flat_s<0>(fn, mt, flags);
+    return f64 ? pick_merton_uniform_s<1>(fn, mt, flags) : pick_merton_uniform_s<0>(fn, mt, flags);
 }
 
 // Launch geometry: a grid-stride loop over paths.  The grid never exceeds the number of
@@ -221,9 +244,16 @@ struct Workspace {
     void* base = nullptr;
 };
 
-int ws_alloc(int grid, cudaStream_t st, Workspace* w) {
+int pool_alloc(void** ptr, size_t bytes, int device, cudaStream_t st) {
+    DeviceInfo* d;
+    if (int rc = device_info(device, &d)) return rc;
+    CU(cudaMallocFromPoolAsync(ptr, bytes, d->pool, st));
+    return 0;
+}
+
+int ws_alloc(int grid, int device, cudaStream_t st, Workspace* w) {
     const size_t bytes = (size_t)grid * 8 * sizeof(double) + 256;
-    CU(cudaMallocAsync(&w->base, bytes, st));
+    if (int rc = pool_alloc(&w->base, bytes, device, st)) return rc;
     w->ticket = (unsigned*)w->base;
     w->partials = (double*)((char*)w->base + 256);
     CU(cudaMemsetAsync(w->ticket, 0, sizeof(unsigned), st));
@@ -239,10 +269,9 @@ int check_flags(int flags) {
     if (samp != MLMCB_SAMPLER_F32BM && samp != MLMCB_SAMPLER_F64BM) return fail(MLMCB_EINVAL, "unknown sampler %d", samp);
     if (flags & ~(MLMCB_SAMPLER_MASK | MLMCB_FP32_PATHS | MLMCB_ANTITHETIC | MLMCB_MILSTEIN))
         return fail(MLMCB_EINVAL, "unknown flag bits 0x%x", flags);
-    if ((flags & MLMCB_MILSTEIN) && ((flags & (MLMCB_FP32_PATHS | MLMCB_ANTITHETIC)) || samp != MLMCB_SAMPLER_F32BM))
-        return fail(MLMCB_ENOTIMPL, "Milstein is built for fp64 paths with the default sampler, without the antithetic estimator");
-    if ((flags & MLMCB_FP32_PATHS) && samp != MLMCB_SAMPLER_F32BM)
-        return fail(MLMCB_ENOTIMPL, "fp32 path arithmetic is built with the default (fp32) sampler only");
+    // every sampler x scheme x estimator combination is built for fp64 paths; the fp32 opt-in covers Euler-Maruyama
+    if ((flags & MLMCB_MILSTEIN) && (flags & MLMCB_FP32_PATHS))
+        return fail(MLMCB_ENOTIMPL, "Milstein is built for fp64 path arithmetic only");
     return 0;
 }
 
@@ -255,32 +284,28 @@ int check_anti(int model, int payoff, int M) {
     return 0;
 }
 
-template <typename R, int SAMP>
-LevelKernel pick_anti_fn(int fn, int mt) {
-    if (fn == FN_AVG)
-        return mt == 2 ? level_anti_kernel<R, FN_AVG, 2, SAMP> : mt == 4 ? level_anti_kernel<R, FN_AVG, 4, SAMP>
-                                                                         : level_anti_kernel<R, FN_AVG, 0, SAMP>;
-    return mt == 2 ? level_anti_kernel<R, FN_FINAL, 2, SAMP> : mt == 4 ? level_anti_kernel<R, FN_FINAL, 4, SAMP>
-                                                                       : level_anti_kernel<R, FN_FINAL, 0, SAMP>;
-}
 LevelKernel pick_anti_kernel(int payoff, int M, int flags) {
-    const int fn = fn_of(payoff), mt = mt_of(M), samp = flags & MLMCB_SAMPLER_MASK;
-    if (flags & MLMCB_FP32_PATHS) return pick_anti_fn<float, SAMP_F32BM>(fn, mt);      // check_flags: default sampler only
-    return samp == MLMCB_SAMPLER_F64BM ? pick_anti_fn<double, SAMP_F64BM>(fn, mt) : pick_anti_fn<double, SAMP_F32BM>(fn, mt);
+    const int fn = fn_of(payoff), mt = mt_of(M);
+    return (flags & MLMCB_SAMPLER_MASK) == MLMCB_SAMPLER_F64BM ? pick_gbm_anti_s<1>(fn, mt, flags) : pick_gbm_anti_s<0>(fn, mt, flags);
 }
 
 // American put: tabulate the per-step scalars, then run the path kernel (Philox or replay).
 constexpr ull kAmerMaxSteps = 1ull << 22;
 
-int amer_table(const LevelConsts& C, cudaStream_t st, AmerRow** tab) {
+// host staging of a tabulated boundary: freed by the stream once the copy that reads it has run
+void CUDART_CB free_host_rows(void* p) { free(p); }
+
+int amer_table(const LevelConsts& C, int device, cudaStream_t st, AmerRow** tab) {
     if (C.nsteps > kAmerMaxSteps) return fail(MLMCB_EINVAL, "American put: M**l above 2^22 fine steps is not supported");
-    CU(cudaMallocAsync((void**)tab, (size_t)(C.nsteps + 1) * sizeof(AmerRow), st));
+    *tab = nullptr;
+    if (int rc = pool_alloc((void**)tab, (size_t)(C.nsteps + 1) * sizeof(AmerRow), device, st)) return rc;
     if (C.amer_vals) {
         // tabulated boundary: the same rows as amer_table_kernel, built here from the caller's values
         // (b on the grid | at the fine mid-points | at the coarse mid-points), same operation order
         const ull n = C.nsteps;
         const double *bg = C.amer_vals, *bf = bg + n + 1, *bc = bf + n;
-        std::vector<AmerRow> rows(n + 1);
+        AmerRow* rows = (AmerRow*)malloc((n + 1) * sizeof(AmerRow));
+        if (!rows) { cudaFreeAsync(*tab, st); *tab = nullptr; return fail(MLMCB_ECUDA, "out of host memory for the boundary table"); }
         for (ull j = 0; j <= n; ++j) {
             AmerRow row = {0, 0, 0, 0, 0, 0, 0, 0};
             row.bR = bg[j];
@@ -297,14 +322,28 @@ int amer_table(const LevelConsts& C, cudaStream_t st, AmerRow** tab) {
             }
             rows[j] = row;
         }
-        CU(cudaMemcpyAsync(*tab, rows.data(), rows.size() * sizeof(AmerRow), cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));          // `rows` must outlive the copy
+        // pageable source: the copy is staged by the runtime before the call returns for small tables and
+        // otherwise ordered on the stream; the staging block is released by a host callback AFTER the copy,
+        // so the entry point stays asynchronous (no cudaStreamSynchronize)
+        cudaError_t e = cudaMemcpyAsync(*tab, rows, (n + 1) * sizeof(AmerRow), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaLaunchHostFunc(st, free_host_rows, rows);
+        if (e != cudaSuccess) {
+            cudaStreamSynchronize(st);
+            free(rows);
+            cudaFreeAsync(*tab, st);
+            *tab = nullptr;
+            return fail(MLMCB_ECUDA, "boundary table upload failed: %s", cudaGetErrorString(e));
+        }
         return 0;
     }
     const int threads = 128;
     const int blocks = (int)((C.nsteps + 1 + threads - 1) / threads);
     amer_table_kernel<<<blocks, threads, 0, st>>>(C, *tab);
-    CU(cudaGetLastError());
+    if (cudaError_t e = cudaGetLastError()) {
+        cudaFreeAsync(*tab, st);
+        *tab = nullptr;
+        return fail(MLMCB_ECUDA, "amer_table_kernel launch failed: %s", cudaGetErrorString(e));
+    }
     return 0;
 }
 
@@ -317,13 +356,15 @@ int amer_level_sums(const LevelConsts& C, int flags, int device, cudaStream_t st
     int grid = 1;
     if (int rc = geometry(k, device, C.n_paths, &grid, nullptr)) return rc;
     AmerRow* tab = nullptr;
-    if (int rc = amer_table(C, st, &tab)) return rc;
+    if (int rc = amer_table(C, device, st, &tab)) return rc;
     Workspace w;
-    if (int rc = ws_alloc(grid, st, &w)) return rc;
+    if (int rc = ws_alloc(grid, device, st, &w)) { cudaFreeAsync(tab, st); return rc; }
     k<<<grid, kThreads, 0, st>>>(C, tab, w.partials, w.ticket, d_out7, d_Pf, d_Pc);
-    CU(cudaGetLastError());
-    CU(cudaFreeAsync(tab, st));
-    return ws_free(&w, st);
+    const cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(tab, st);
+    if (int rc = ws_free(&w, st)) return rc;
+    if (e != cudaSuccess) return fail(MLMCB_ECUDA, "amer_level_kernel launch failed: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 int level_sums_impl(const mlmcb_params* p, int model, int payoff, int l, int M, ull n_paths, ull seed,
@@ -348,7 +389,7 @@ int level_sums_impl(const mlmcb_params* p, int model, int payoff, int l, int M, 
     int grid = 1;
     if (int rc = geometry(k, device, n_paths, &grid, nullptr)) return rc;
     Workspace w;
-    if (int rc = ws_alloc(grid, st, &w)) return rc;
+    if (int rc = ws_alloc(grid, device, st, &w)) return rc;
     k<<<grid, kThreads, 0, st>>>(C, w.partials, w.ticket, d_out7, d_Pf, d_Pc);
     CU(cudaGetLastError());
     return ws_free(&w, st);
@@ -360,9 +401,16 @@ struct HostSide {
     double* dev = nullptr;         // same shape on the device
     cudaStream_t side[8] = {};
     cudaEvent_t fork = nullptr, join[8] = {};
+    // persistent workspace of the one-launch sweep: partial rows, the ticket (the kernel leaves it zero) and an
+    // event that orders consecutive sweeps issued on different streams
+    double* sweep_partials = nullptr;
+    unsigned* sweep_ticket = nullptr;
+    cudaEvent_t sweep_done = nullptr;
+    bool sweep_pending = false;
     bool ready = false;
 };
 constexpr int kMaxSweep = 64;
+constexpr int kSweepRows = 8192;   // upper bound on the grid of a sweep launch
 HostSide g_host[64];
 std::mutex g_host_mu[64];          // the staging buffers of a device serve one _host call at a time
 
@@ -372,6 +420,10 @@ int host_side(int dev, HostSide** out) {
         CU(cudaHostAlloc((void**)&h.pinned, kMaxSweep * 8 * sizeof(double), cudaHostAllocDefault));
         CU(cudaMalloc((void**)&h.dev, kMaxSweep * 8 * sizeof(double)));
         CU(cudaEventCreateWithFlags(&h.fork, cudaEventDisableTiming));
+        CU(cudaMalloc((void**)&h.sweep_partials, (size_t)kSweepRows * 8 * sizeof(double)));
+        CU(cudaMalloc((void**)&h.sweep_ticket, 256));
+        CU(cudaMemset(h.sweep_ticket, 0, 256));
+        CU(cudaEventCreateWithFlags(&h.sweep_done, cudaEventDisableTiming));
         for (int i = 0; i < 8; ++i) {
             CU(cudaStreamCreateWithFlags(&h.side[i], cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&h.join[i], cudaEventDisableTiming));
@@ -382,12 +434,138 @@ int host_side(int dev, HostSide** out) {
     return 0;
 }
 
+// ---- one launch per sweep ----------------------------------------------------------------------
+// Relative cost of one path in SMSP cycles per warp (profiles/r0*_gbm_levels.txt, r0*_merton_levels.txt): only the
+// proportions matter - they decide how many blocks of the launch each level gets; the block scheduler evens
+// out what the model gets wrong because the grid is several waves deep.
+double path_cost(int model, bool f64, ull nsteps, double lamT) {
+    const double step = f64 ? 80.0 : 38.0, n = (double)nsteps;
+    if (model == MLMCB_GBM) {
+        if (nsteps == 1) return f64 ? 260.0 : 130.0;
+        if (nsteps == 2) return f64 ? 520.0 : 265.0;
+        return (f64 ? 400.0 : 230.0) + step * n;
+    }
+    const double event = (f64 ? 1600.0 : 800.0) * (lamT + 1.0);
+    if (nsteps == 1) return event;
+    if (nsteps < flat_below()) return 1.3 * event + 2.5 * step * n;
+    return 6.0 * event + 1.05 * step * n;
+}
+
+// Tries to run the sweep as ONE kernel; *done = false (and nothing launched) if this request is not covered
+// (antithetic, fp32 paths, American put, more than kSweepMax non-empty levels).  d_out: [n_levels][8] on the device.
+int sweep_fused(const mlmcb_params* p, int model, int payoff, int M, int n_levels, const int* levels,
+                const uint64_t* n_paths, const uint64_t* path_offsets, uint64_t seed, int flags, int device,
+                cudaStream_t st, HostSide* h, double* d_out, bool* done) {
+    *done = false;
+    static const bool off = getenv("MLMCB_NO_FUSED_SWEEP") != nullptr;      // A/B timing and the agreement test
+    if (off || payoff == MLMCB_AMERICAN || (flags & (MLMCB_ANTITHETIC | MLMCB_FP32_PATHS))) return 0;
+    int live = 0;
+    for (int i = 0; i < n_levels; ++i) live += n_paths[i] != 0;
+    if (live == 0 || live > kSweepMax) return 0;
+    if (int rc = check_flags(flags)) return rc;
+    const bool f64 = (flags & MLMCB_SAMPLER_MASK) == MLMCB_SAMPLER_F64BM;
+    const int fn = fn_of(payoff), mt = mt_of(M);
+    SweepKernel k = model == MLMCB_GBM ? (f64 ? pick_gbm_sweep_s<1>(fn, mt, flags) : pick_gbm_sweep_s<0>(fn, mt, flags))
+                                       : (f64 ? pick_merton_sweep_s<1>(fn, mt, flags) : pick_merton_sweep_s<0>(fn, mt, flags));
+    static thread_local SweepConsts S;            // 25 KB: too big for comfort on the stack
+    memset(&S, 0, offsetof(SweepConsts, lv));
+    S.n_levels = live;
+    S.n_rows = n_levels;
+    // deepest level first (longest serial path); ties keep the caller's order
+    std::vector<int> order;
+    for (int i = 0; i < n_levels; ++i) if (n_paths[i]) order.push_back(i);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return levels[a] > levels[b]; });
+    double cost[kSweepMax], total = 0.0;
+    ull cap[kSweepMax];
+    for (int j = 0; j < live; ++j) {
+        const int i = order[j];
+        LevelConsts* C = &S.lv[j];
+        if (int rc = make_consts(p, model, payoff, levels[i], M, n_paths[i], seed, path_offsets[i], C)) return rc;
+        S.row[j] = i;
+        ull per_thread = 1;
+        if (model == MLMCB_GBM) {
+            if (C->nsteps <= 2) { S.kind[j] = SK_PACKED; per_thread = C->nsteps == 1 ? 4 : 2; }
+            else if (C->nsteps == 4 && mt != 0) S.kind[j] = SK_FOUR;
+            else S.kind[j] = SK_LONG;
+        } else {
+            S.kind[j] = C->nsteps < flat_below() ? SK_MJD_FLAT : SK_MJD_UNIFORM;
+        }
+        cost[j] = (double)n_paths[i] * path_cost(model, f64, C->nsteps, model == MLMCB_MERTON ? p->lam * p->T : 0.0);
+        total += cost[j];
+        const ull threads = (n_paths[i] + per_thread - 1) / per_thread + (per_thread > 1 ? 1 : 0);
+        cap[j] = (threads + kThreads - 1) / kThreads;                   // more blocks than this would idle
+    }
+    int grid0 = 0, resident = 0;
+    if (int rc = geometry(k, device, ~0ull >> 16, &grid0, &resident)) return rc;
+    const double budget = (double)(resident * 4 < kSweepRows - kSweepMax ? resident * 4 : kSweepRows - kSweepMax);   // four waves
+    unsigned first = 0;
+    for (int j = 0; j < live; ++j) {
+        ull b = (ull)(budget * cost[j] / total + 0.5);
+        if (b < 1) b = 1;
+        if (b > cap[j]) b = cap[j];
+        S.first[j] = first;
+        first += (unsigned)b;
+    }
+    S.first[live] = first;
+    if (h->sweep_pending) CU(cudaStreamWaitEvent(st, h->sweep_done, 0));     // the workspace serves one sweep at a time
+    k<<<first, kThreads, 0, st>>>(S, h->sweep_partials, h->sweep_ticket, d_out);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->sweep_done, st));
+    h->sweep_pending = true;
+    *done = true;
+    return 0;
+}
+
+// the sweep as concurrent per-level launches on the side streams, rows of 8 doubles into d_out
+int sweep_per_level(const mlmcb_params* p, int model, int payoff, int M, int n_levels, const int* levels,
+                    const uint64_t* n_paths, const uint64_t* path_offsets, uint64_t seed, int flags, int device,
+                    cudaStream_t st, HostSide* h, double* d_out) {
+    // fork: side streams wait for whatever precedes on the caller's stream (and the zero-fill)
+    CU(cudaMemsetAsync(d_out, 0, (size_t)n_levels * 8 * sizeof(double), st));
+    CU(cudaEventRecord(h->fork, st));
+    bool used[8] = {};
+    // deepest level first: it is the longest-running launch of the sweep
+    for (int i = n_levels - 1, slot = 0; i >= 0; --i) {
+        if (n_paths[i] == 0) continue;
+        cudaStream_t s = h->side[slot & 7];
+        if (!used[slot & 7]) { CU(cudaStreamWaitEvent(s, h->fork, 0)); used[slot & 7] = true; }
+        if (int rc = level_sums_impl(p, model, payoff, levels[i], M, n_paths[i], seed, path_offsets[i], flags,
+                                     device, s, d_out + (size_t)i * 8, nullptr, nullptr)) {
+            cudaDeviceSynchronize();      // launches already issued on side streams must not outlive the call
+            return rc;
+        }
+        ++slot;
+    }
+    for (int s = 0; s < 8; ++s) {
+        if (!used[s]) continue;
+        CU(cudaEventRecord(h->join[s], h->side[s]));
+        CU(cudaStreamWaitEvent(st, h->join[s], 0));
+    }
+    return 0;
+}
+
+int sweep_impl(const mlmcb_params* p, int model, int payoff, int M, int n_levels, const int* levels,
+               const uint64_t* n_paths, const uint64_t* path_offsets, uint64_t seed, int flags, int device,
+               cudaStream_t st, HostSide* h, double* d_out) {
+    if (n_levels == 0) return 0;
+    bool done = false;
+    int live = 0;
+    for (int i = 0; i < n_levels; ++i) live += n_paths[i] != 0;
+    // a single level keeps its own kernel (one wave, equal paths per thread); two or more share one launch
+    if (live >= 2)
+    if (int rc = sweep_fused(p, model, payoff, M, n_levels, levels, n_paths, path_offsets, seed, flags, device, st, h,
+                             d_out, &done))
+        return rc;
+    if (done) return 0;
+    return sweep_per_level(p, model, payoff, M, n_levels, levels, n_paths, path_offsets, seed, flags, device, st, h, d_out);
+}
+
 }  // namespace
 
 extern "C" {
 
 const char* mlmcb_last_error(void) { return g_err; }
-int mlmcb_version(void) { return 101; }      // 101: mlmcb_params grew amer_boundary / amer_levels
+int mlmcb_version(void) { return 102; }      // 102: flags == 0 selects the fp64 sampler (fp32 is the opt-in); 101: mlmcb_params grew amer_boundary / amer_levels
 
 void mlmcb_params_fill_derived(mlmcb_params* p) {
     if (!p) return;
@@ -458,31 +636,27 @@ int mlmcb_level_sweep_host(const mlmcb_params* p, int model, int payoff, int M, 
     HostSide* h;
     if (int rc = host_side(device, &h)) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    // fork: side streams wait for whatever precedes on the caller's stream (and the zero-fill)
-    CU(cudaMemsetAsync(h->dev, 0, (size_t)n_levels * 8 * sizeof(double), st));
-    CU(cudaEventRecord(h->fork, st));
-    bool used[8] = {};
-    // deepest level first: it is the longest-running launch of the sweep
-    for (int i = n_levels - 1, slot = 0; i >= 0; --i) {
-        if (n_paths[i] == 0) continue;
-        cudaStream_t s = h->side[slot & 7];
-        if (!used[slot & 7]) { CU(cudaStreamWaitEvent(s, h->fork, 0)); used[slot & 7] = true; }
-        if (int rc = level_sums_impl(p, model, payoff, levels[i], M, n_paths[i], seed, path_offsets[i], flags,
-                                     device, s, h->dev + (size_t)i * 8, nullptr, nullptr)) {
-            cudaDeviceSynchronize();      // launches already issued on side streams must not outlive the call
-            return rc;
-        }
-        ++slot;
-    }
-    for (int s = 0; s < 8; ++s) {
-        if (!used[s]) continue;
-        CU(cudaEventRecord(h->join[s], h->side[s]));
-        CU(cudaStreamWaitEvent(st, h->join[s], 0));
-    }
+    if (int rc = sweep_impl(p, model, payoff, M, n_levels, levels, n_paths, path_offsets, seed, flags, device, st, h, h->dev))
+        return rc;
     CU(cudaMemcpyAsync(h->pinned, h->dev, (size_t)n_levels * 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     for (int i = 0; i < n_levels; ++i) memcpy(h_out + (size_t)i * 7, h->pinned + (size_t)i * 8, 7 * sizeof(double));
     return 0;
+}
+
+int mlmcb_level_sweep(const mlmcb_params* p, int model, int payoff, int M, int n_levels,
+                      const int* levels, const uint64_t* n_paths, const uint64_t* path_offsets,
+                      uint64_t seed, int flags, int device, void* cuda_stream, double* d_out) {
+    if (!levels || !n_paths || !path_offsets || !d_out) return fail(MLMCB_EINVAL, "NULL array argument");
+    if (n_levels < 0 || n_levels > kMaxSweep) return fail(MLMCB_EINVAL, "n_levels=%d out of range (max %d)", n_levels, kMaxSweep);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    if (device < 0 || device >= 64) return fail(MLMCB_EINVAL, "device %d out of range", device);
+    std::lock_guard<std::mutex> lock(g_host_mu[device]);
+    HostSide* h;
+    if (int rc = host_side(device, &h)) return rc;
+    return sweep_impl(p, model, payoff, M, n_levels, levels, n_paths, path_offsets, seed, flags, device,
+                      (cudaStream_t)cuda_stream, h, d_out);
 }
 
 int mlmcb_replay_gbm(const mlmcb_params* p, int payoff, int l, int M, uint64_t n_paths, const double* d_Z,
@@ -492,7 +666,6 @@ int mlmcb_replay_gbm(const mlmcb_params* p, int payoff, int l, int M, uint64_t n
     arith &= ~(MLMCB_ANTITHETIC | MLMCB_MILSTEIN);
     if (arith != MLMCB_ARITH_FAST && arith != MLMCB_ARITH_EXACT) return fail(MLMCB_EINVAL, "unknown arith %d", arith);
     if (anti) {
-        if (mil) return fail(MLMCB_ENOTIMPL, "Milstein is not built with the antithetic estimator");
         if (int rc = check_anti(MLMCB_GBM, payoff, M)) return rc;
     }
     DeviceGuard g(device);
@@ -504,11 +677,11 @@ int mlmcb_replay_gbm(const mlmcb_params* p, int payoff, int l, int M, uint64_t n
     if (payoff == MLMCB_AMERICAN) {
         if (anti || mil) return fail(MLMCB_ENOTIMPL, "the American put is built for Euler-Maruyama without the antithetic estimator");
         AmerRow* tab = nullptr;
-        if (int rc = amer_table(C, st, &tab)) return rc;
+        if (int rc = amer_table(C, device, st, &tab)) return rc;
         int grid = (int)((n_paths + kThreads - 1) / kThreads);
         if (grid > 65535) grid = 65535;
         Workspace w;
-        if (int rc = ws_alloc(grid + 1, st, &w)) return rc;
+        if (int rc = ws_alloc(grid + 1, device, st, &w)) { cudaFreeAsync(tab, st); return rc; }
         double* out = d_out7 ? d_out7 : w.partials;
         if (arith == MLMCB_ARITH_EXACT)
             replay_amer_kernel<AR_EXACT><<<grid, kThreads, 0, st>>>(C, tab, d_Z, w.partials + 8, w.ticket, out, d_Pf, d_Pc);
@@ -527,14 +700,16 @@ int mlmcb_replay_gbm(const mlmcb_params* p, int payoff, int l, int M, uint64_t n
         {replay_gbm_kernel<FN_FINAL, AR_FAST, 1>, replay_gbm_kernel<FN_FINAL, AR_EXACT, 1>},
         {replay_gbm_kernel<FN_AVG, AR_FAST, 1>, replay_gbm_kernel<FN_AVG, AR_EXACT, 1>},
         {replay_gbm_kernel<FN_MIN, AR_FAST, 1>, replay_gbm_kernel<FN_MIN, AR_EXACT, 1>}};
-    static const K anti_table[2][2] = {
-        {replay_gbm_anti_kernel<FN_FINAL, AR_FAST>, replay_gbm_anti_kernel<FN_FINAL, AR_EXACT>},
-        {replay_gbm_anti_kernel<FN_AVG, AR_FAST>, replay_gbm_anti_kernel<FN_AVG, AR_EXACT>}};
-    K k = anti ? anti_table[fn_of(payoff)][arith] : mil ? mil_table[fn_of(payoff)][arith] : table[fn_of(payoff)][arith];
+    static const K anti_table[2][2][2] = {
+        {{replay_gbm_anti_kernel<FN_FINAL, AR_FAST, 0>, replay_gbm_anti_kernel<FN_FINAL, AR_EXACT, 0>},
+         {replay_gbm_anti_kernel<FN_AVG, AR_FAST, 0>, replay_gbm_anti_kernel<FN_AVG, AR_EXACT, 0>}},
+        {{replay_gbm_anti_kernel<FN_FINAL, AR_FAST, 1>, replay_gbm_anti_kernel<FN_FINAL, AR_EXACT, 1>},
+         {replay_gbm_anti_kernel<FN_AVG, AR_FAST, 1>, replay_gbm_anti_kernel<FN_AVG, AR_EXACT, 1>}}};
+    K k = anti ? anti_table[mil ? 1 : 0][fn_of(payoff)][arith] : mil ? mil_table[fn_of(payoff)][arith] : table[fn_of(payoff)][arith];
     int grid = (int)((n_paths + kThreads - 1) / kThreads);
     if (grid > 65535) grid = 65535;
     Workspace w;
-    if (int rc = ws_alloc(grid + 1, st, &w)) return rc;
+    if (int rc = ws_alloc(grid + 1, device, st, &w)) return rc;
     double* out = d_out7 ? d_out7 : w.partials;   // sums are always formed; row 0 is scratch if unwanted
     k<<<grid, kThreads, 0, st>>>(C, d_Z, w.partials + 8, w.ticket, out, d_Pf, d_Pc);
     CU(cudaGetLastError());
@@ -570,7 +745,7 @@ int mlmcb_replay_merton(const mlmcb_params* p, int payoff, int l, int M, uint64_
     int grid = (int)((n_paths + kThreads - 1) / kThreads);
     if (grid > 65535) grid = 65535;
     Workspace w;
-    if (int rc = ws_alloc(grid + 1, st, &w)) return rc;
+    if (int rc = ws_alloc(grid + 1, device, st, &w)) return rc;
     double* out = d_out7 ? d_out7 : w.partials;
     k<<<grid, kThreads, 0, st>>>(C, d_zW, (const long long*)d_offW, d_zQ, (const long long*)d_offQ, d_E,
                                  (const long long*)d_offE, w.partials + 8, w.ticket, out, d_Pf, d_Pc);

@@ -48,7 +48,13 @@
 #define MLMCB_UNROLL_MJD 2
 #endif
 #ifndef MLMCB_MINBLOCKS_F64
-#define MLMCB_MINBLOCKS_F64 1
+#define MLMCB_MINBLOCKS_F64 6       // fp64-sampler kernels: <= 80 registers -> 6 blocks of 128 threads per SM
+#endif
+#ifndef MLMCB_MINBLOCKS_F64_MJD
+#define MLMCB_MINBLOCKS_F64_MJD 4   // Merton kernels with the fp64 sampler: <= 128 registers
+#endif
+#ifndef MLMCB_F64BM_TABLES
+#define MLMCB_F64BM_TABLES 1        // 0: the round-1 table-free fp64 Box-Muller (fdlibm log, degree-8 sin/cos) for A/B runs
 #endif
 #ifndef MLMCB_PHILOX_ROUNDS
 #define MLMCB_PHILOX_ROUNDS 10      // experiments only; the shipped library is Philox4x32-10
@@ -98,6 +104,8 @@ struct LevelConsts {
     float poly_q4, poly_c4;         // leading sin/cos coefficients as uniform operands (no per-block MOV)
     // fp64 sampler constants, read straight from the constant bank by DFMA (no 64-bit immediates exist)
     double dq[9], dc[9], lg[7], ln2_hi, ln2_lo;
+    double lq[5], neg2ln2, ts[3], tc[2];   // table-driven fp64 Box-Muller (tools/gen_f64bm_tables.py)
+    uint32_t one_hi;                // 0x3ff00000 as a run-time value: (x & mask) | one_hi then is ONE LOP3 (register operand)
     double ex[12];                  // 1/k!, k = 2..13 (exp_bounded)
     const double* amer_vals;        // HOST pointer (never read on the device): tabulated exercise boundary of this level, or null
 };
@@ -307,10 +315,96 @@ __device__ __forceinline__ void sincos_half(const LevelConsts& C, double h, doub
     sn_over_h = q; cs = c;
 }
 
+// ---- table-driven form of the same pair (MLMCB_F64BM_TABLES, the shipped one) -------------------
+// The stream is unchanged (same words -> same normals to ~1 ulp); what changes is the instruction
+// count: 29 FP64-pipe instructions per pair instead of 53.  Two tables (6 KB) sit in shared memory:
+//   lg[128]  -2 ln u = k(-2 ln2) + B_i + G(x),  u = 2^k m,  x = fma(m, A_i, 2) = -2(m/c_i - 1),
+//            G(x) = x + x^2 Q(x), |x| <= 2^-7.  The interval that holds m = 1 is centred on it
+//            (c = 1, A = -2, B = 0): x is exact there, so u -> 1 keeps full relative accuracy.
+//   tr[256]  (cos, sin)(pi h_j), h_j = (j + 1/2)/256 - 1/2; the remaining angle pi*d, |d| <= 2^-9,
+//            by three-/two-term polynomials and one rotation.
+// tools/gen_f64bm_tables.py generates tables and coefficients and checks the pair against 60-digit
+// values (worst |z - exact| 1.3e-15 at |z| = 8.6, i.e. <= 1 ulp).
+// (x & MASK) | c in one LOP3: MASK is the instruction's immediate, c must come from a register
+template <uint32_t MASK>
+__device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "n"(MASK), "r"(c));
+    return r;
+}
+struct F64Tab { double2 lg[128]; double2 tr[256]; };
+static __device__ const F64Tab g_f64tab = {
+#include "mlmcb_f64tab.inc"
+};
+__device__ __forceinline__ F64Tab& f64tab() {
+    __shared__ F64Tab t;
+    return t;
+}
+// every thread of the block, before the first fp64 draw
+template <int SAMP>
+__device__ __forceinline__ void sampler_init() {
+#if MLMCB_F64BM_TABLES
+    if (SAMP == SAMP_F64BM) {
+        const double2* src = reinterpret_cast<const double2*>(&g_f64tab);
+        double2* dst = reinterpret_cast<double2*>(&f64tab());
+        for (int i = threadIdx.x; i < (int)(sizeof(F64Tab) / sizeof(double2)); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+#endif
+}
+__device__ __forceinline__ double neg2_log_tab(const LevelConsts& C, double u) {
+    const int ix = __double2hiint(u);
+    const int tmp = ix - 0x3fe6b000;
+    const int k = tmp >> 20;
+    int mh;                                                                              // ix - (k << 20) as ONE IMAD
+    asm("mad.lo.s32 %0, %1, -1048576, %2;" : "=r"(mh) : "r"(k), "r"(ix));
+    const double m = __hiloint2double(mh, __double2loint(u));                            // [0.70898, 1.41797)
+    const double2 e = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(f64tab().lg) + ((tmp >> 9) & 0x7f0));
+    const double x = fma(m, e.x, 2.0);
+    const double x2 = x * x;
+    double q = fma(x, C.lq[4], C.lq[3]);
+    q = fma(q, x, C.lq[2]);
+    q = fma(q, x, C.lq[1]);
+    q = fma(q, x, C.lq[0]);
+    const double t = fma((double)k, C.neg2ln2, e.y);
+    return t + fma(x2, q, x);
+}
+// sqrt(s): reciprocal-root seed y (2^-22), then two residual corrections g += (s - g*g)*(y/2); the half-seed's own
+// error only scales the correction, so the second pass lands at e*e1 ~ 2^-62 before the final rounding.
+__device__ __forceinline__ double sqrt_pos2(double s) {
+    const double y = rsqrt64_seed(s);
+    double g = s * y;
+    const double hy = 0.5 * y;
+    g = fma(fma(-g, g, s), hy, g);
+    return fma(fma(-g, g, s), hy, g);
+}
+__device__ __forceinline__ void bm_pair_f64_tab(const LevelConsts& C, uint32_t a, uint32_t b, uint32_t c, uint32_t d, double& z0, double& z1) {
+    const double u = __hiloint2double((int)and_or<0x000FFFFFu>(a, C.one_hi), (int)b) - (1.0 - 0x1p-53);    // u52(a, b)
+    double rad = sqrt_pos2(neg2_log_tab(C, u));
+    rad = __hiloint2double(__double2hiint(rad) | (int)(c & 0x80000000u), __double2loint(rad));
+    const double2 cs = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(f64tab().tr) + ((c >> 8) & 0xff0));
+    const double dl = __hiloint2double((int)and_or<0x00000FFFu>(c, C.one_hi), (int)d) - (1.0 + 0x1p-9);
+    const double D = dl * dl;
+    const double sd = fma(fma(D, C.ts[2], C.ts[1]), D, C.ts[0]) * dl;          // sin(pi d)
+    const double cm = fma(D, C.tc[1], C.tc[0]) * D;                             // cos(pi d) - 1
+    z0 = rad * fma(-cs.y, sd, fma(cs.x, cm, cs.x));
+    z1 = rad * fma(cs.x, sd, fma(cs.y, cm, cs.y));
+}
+
+__device__ __forceinline__ double neg2_log_u(const LevelConsts& C, double u) {
+#if MLMCB_F64BM_TABLES
+    return neg2_log_tab(C, u);
+#else
+    return neg2_log(C, u);
+#endif
+}
+
 // One Philox block (a,b,c,d) -> two N(0,1): radius from u52(a,b), angle pi*h with h = u52-like
 // from (c,d) shifted to [-1/2,1/2), half-plane from the top bit of c.
 __device__ __forceinline__ void bm_pair_f64(const LevelConsts& C, uint32_t a, uint32_t b, uint32_t c, uint32_t d, double& z0, double& z1) {
-#if MLMCB_F64BM_LIBDEVICE
+#if MLMCB_F64BM_TABLES
+    bm_pair_f64_tab(C, a, b, c, d, z0, z1);
+#elif MLMCB_F64BM_LIBDEVICE
     double rad = sqrt(-2.0 * log(u53(a, b)));
     double sn, cs;
     sincospi(2.0 * u53(c, d), &sn, &cs);
@@ -428,7 +522,7 @@ struct Sums7 {
 // payoff formula (average -> EA payoff, minimum -> lookback, final value -> Euro or Digital), so only
 // the last distinction is a run-time test.  (Hoisting the "any per-path output requested" test out of the
 // path loop was measured: it costs the 4096-step loop 1 % through register allocation.)
-template <int FN>
+template <int FN, bool MAYBE_L0 = true>
 __device__ __forceinline__ void emit_t(const LevelConsts& C, ull i, double vf, double vc, double gf, double gc,
                                        Sums7& acc, double* Pf_out, double* Pc_out) {
     double Pf, Pc;
@@ -442,8 +536,8 @@ __device__ __forceinline__ void emit_t(const LevelConsts& C, ull i, double vf, d
         Pf = vf > C.K ? C.discK : 0.0;
         Pc = vc > C.K ? C.discK : 0.0;
     }
-    if (C.is_l0) Pc = vc;                                                // l==0: raw coarse output :82
-    acc.add(Pf, Pc, C.is_l0);
+    if (MAYBE_L0 && C.is_l0) Pc = vc;                                    // l==0: raw coarse output :82
+    acc.add(Pf, Pc, MAYBE_L0 && C.is_l0);
     if (Pf_out || Pc_out || C.raw) {
         if (Pf_out) Pf_out[i] = Pf;
         if (Pc_out) Pc_out[i] = Pc;
@@ -644,10 +738,10 @@ __device__ __forceinline__ void gbm_path_exact(const LevelConsts& C, const doubl
 // diffusion_anti_path_avg :219-290.  The antithetic path swaps the two Brownian increments of
 // every pair of fine steps; M must be even (:178).  FN is FN_FINAL or FN_AVG.
 // ------------------------------------------------------------------------------------------
-template <typename R, int FN, int MT, typename Source>
+template <typename R, int FN, int MT, int SCH, typename Source>
 __device__ __forceinline__ void gbm_anti_path_fast(const LevelConsts& C, const Source& src,
                                                    double& vf, double& va, double& vc) {
-    const R af = (R)C.a_f, bf = (R)C.b_f, ac = (R)C.a_c;
+    const StepCoef<R, SCH> co(C);
     R Xf = (R)C.X0, Xa = (R)C.X0, Xc = (R)C.X0, sz = (R)0;
     R Ff = (R)0, Fa = (R)0, Fc = (R)0;
     int cm = 0;
@@ -655,7 +749,7 @@ __device__ __forceinline__ void gbm_anti_path_fast(const LevelConsts& C, const S
     if (C.is_l0) {                                                       // :213-215 / :282-285
         R z[4];
         src.load4(0, z);
-        R t_ = fma_<R>(bf, z[0], af);
+        R t_ = co.t(z[0]);
         Xf = fma_<R>(Xf, t_, Xf);
         vf = va = FN == FN_AVG ? C.avg_wf * (0.5 * C.X0 + 0.5 * (double)Xf) : (double)Xf;
         vc = C.X0;
@@ -663,7 +757,7 @@ __device__ __forceinline__ void gbm_anti_path_fast(const LevelConsts& C, const S
     }
 #define MLMCB_PAIR(zo, ze)                                               \
     {                                                                    \
-        R to_ = fma_<R>(bf, (zo), af), te_ = fma_<R>(bf, (ze), af);      \
+        R to_ = co.t(zo), te_ = co.t(ze);                                \
         Xf = fma_<R>(Xf, to_, Xf); Xa = fma_<R>(Xa, te_, Xa);            \
         if (FN == FN_AVG) { Ff += Xf; Fa += Xa; }                        \
         Xf = fma_<R>(Xf, te_, Xf); Xa = fma_<R>(Xa, to_, Xa);            \
@@ -672,7 +766,7 @@ __device__ __forceinline__ void gbm_anti_path_fast(const LevelConsts& C, const S
     }
 #define MLMCB_COARSE()                                                   \
     {                                                                    \
-        R t_ = fma_<R>(bf, sz, ac);                                      \
+        R t_ = co.tc(sz);                                                \
         Xc = fma_<R>(Xc, t_, Xc);                                        \
         sz = (R)0;                                                       \
         if (FN == FN_AVG) Fc += Xc;                                      \
@@ -708,11 +802,17 @@ __device__ __forceinline__ void gbm_anti_path_fast(const LevelConsts& C, const S
 }
 
 // reference expression order (replay, bit-exact vs numpy)
-template <int FN>
+template <int FN, int SCH>
+__device__ __forceinline__ double anti_inc(const LevelConsts& C, double X, double h, double dW) {
+    double inc = __dadd_rn(__dmul_rn(__dmul_rn(C.mu, X), h), __dmul_rn(__dmul_rn(C.sig, X), dW));
+    if (SCH) inc = __dadd_rn(inc, milstein_term(C, X, h, dW));           // whatever `self.sde` is bound to (:200-210)
+    return inc;
+}
+template <int FN, int SCH>
 __device__ __forceinline__ void gbm_anti_path_exact(const LevelConsts& C, const double* Z, ull n, ull i,
                                                     double& vf, double& va, double& vc) {
-    const double dt = C.dt, Mdt = C.Mdt, mu = C.mu, sig = C.sig, Md = C.Md;
-#define MLMCB_INC(X, h, dW) __dadd_rn(__dmul_rn(__dmul_rn(mu, (X)), (h)), __dmul_rn(__dmul_rn(sig, (X)), (dW)))
+    const double dt = C.dt, Mdt = C.Mdt, Md = C.Md;
+#define MLMCB_INC(X, h, dW) anti_inc<FN, SCH>(C, (X), (h), (dW))
     double Xf = C.X0, Xa = C.X0, Xc = C.X0, dWc = 0.0;
     double Af = __dmul_rn(__dmul_rn(0.5, dt), Xf), Aa = __dmul_rn(__dmul_rn(0.5, dt), Xa);      // :247-248
     double Ac = __dmul_rn(__dmul_rn(__dmul_rn(0.5, Md), dt), Xc);                               // :249
@@ -919,7 +1019,7 @@ __device__ __forceinline__ void jump_draws(const LevelConsts& C, ull pid, uint32
         zq = (R)a; zw = (R)b;
     } else {
         U4 r = philox_at(C, pid, STREAM_JUMP, 2 * jk), s = philox_at(C, pid, STREAM_JUMP, 2 * jk + 1);
-        gap = neg2_log(C, u52(r.x, r.y)) * (0.5 * C.inv_lam);        // Exp(lam) inter-arrival time :454/:474
+        gap = neg2_log_u(C, u52(r.x, r.y)) * (0.5 * C.inv_lam);        // Exp(lam) inter-arrival time :454/:474
         double a, b;
         bm_pair_f64(C, s.x, s.y, s.z, s.w, a, b);
         zq = (R)a; zw = (R)b;
@@ -1243,14 +1343,13 @@ struct MjdFlat {
     }
 };
 
+// Body of the event-driven Merton kernel for block `bid` of the `nblk` blocks that share this level's paths
+// (a whole grid for a level call, a slice of the grid inside a sweep).
 template <typename R, int FN, int MT, int SAMP, int SCH>
-__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64 : MLMCB_MINBLOCKS_FLAT)
-mjd_flat_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
-                double* out7, double* Pf_out, double* Pc_out) {
-    Sums7 acc;
-    acc.clear();
-    const ull stride = (ull)gridDim.x * blockDim.x;
-    ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void mjd_flat_body(const LevelConsts& C, unsigned bid, unsigned nblk, Sums7& acc,
+                                              double* Pf_out, double* Pc_out) {
+    const ull stride = (ull)nblk * blockDim.x;
+    ull i = (ull)bid * blockDim.x + threadIdx.x;
     if (C.nsteps == 1) {
         // l = 0: a path is its jumps and one closing step, every one of them "draw a record, step to
         // min(jump time, T)".  Each lane runs that loop over its own queue of paths, so the warp never
@@ -1287,7 +1386,6 @@ mjd_flat_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigne
                 }
             }
         }
-        grid_finish(acc, partials, ticket, out7);
         return;
     }
     bool active = i < C.n_paths;
@@ -1319,6 +1417,16 @@ mjd_flat_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigne
             }
         }
     }
+}
+
+template <typename R, int FN, int MT, int SAMP, int SCH>
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64_MJD : MLMCB_MINBLOCKS_FLAT)
+mjd_flat_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
+                double* out7, double* Pf_out, double* Pc_out) {
+    sampler_init<SAMP>();
+    Sums7 acc;
+    acc.clear();
+    mjd_flat_body<R, FN, MT, SAMP, SCH>(C, blockIdx.x, gridDim.x, acc, Pf_out, Pc_out);
     grid_finish(acc, partials, ticket, out7);
 }
 
@@ -1469,6 +1577,7 @@ template <int SAMP>
 __global__ void __launch_bounds__(kThreads)
 amer_level_kernel(const __grid_constant__ LevelConsts C, const AmerRow* tab, double* partials, unsigned* ticket,
                   double* out7, double* Pf_out, double* Pc_out) {
+    sampler_init<SAMP>();
     Sums7 acc;
     acc.clear();
     const ull stride = (ull)gridDim.x * blockDim.x;
@@ -1574,13 +1683,47 @@ struct JumpRecStore<1> {
 
 // GBM paths of one or two fine steps (l = 0; M = 2, l = 1), a kernel of their own so that the long-path
 // kernel's register allocation and code placement do not move when this one is tuned.
-template <typename R, int FN, int SAMP, int SCH>
-__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64 : MLMCB_MINBLOCKS)
-gbm_packed_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
-                  double* out7, double* Pf_out, double* Pc_out) {
-    Sums7 acc;
-    acc.clear();
-    const ull stride = (ull)gridDim.x * blockDim.x;
+// NS = 0: one or two fine steps per path (several paths share a Philox block);  NS = 4 / -4: four fine steps
+// with M = 4 (l = 1) / M = 2 (l = 2) - one draw block IS the path, so there is no block loop, the coarse steps
+// sit at compile-time places and the payoff is the compile-time one of the path functional.  Same draws as
+// the long-path kernel would use (STREAM_GRID block 0 of the path), so results do not depend on which runs.
+template <typename R, int FN, int SAMP, int SCH, int NS>
+__device__ __forceinline__ void gbm_packed_body(const LevelConsts& C, unsigned bid, unsigned nblk, Sums7& acc,
+                                                double* Pf_out, double* Pc_out) {
+    const ull stride = (ull)nblk * blockDim.x;
+    const ull tid = (ull)bid * blockDim.x + threadIdx.x;
+    if (NS != 0) {
+        const StepCoef<R, SCH> co(C);
+        const R X0 = (R)C.X0;
+        const double h0 = 0.5 * C.X0;
+        for (ull i = tid; i < C.n_paths; i += stride) {
+            R z[4];
+            PhiloxSource<R, SAMP>{C, C.path_offset + i}.load4(0, z);
+            R Xf = X0, Xc = X0;
+            R Ff = FN == FN_MIN ? X0 : (R)0, Fc = Ff;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                Xf = fma_<R>(Xf, co.t(z[k]), Xf);
+                if (FN == FN_AVG) Ff += Xf;
+                if (FN == FN_MIN) Ff = min_<R>(Ff, Xf);
+                if (NS == -4 ? (k & 1) : k == 3) {
+                    const R s = NS == -4 ? z[k - 1] + z[k] : (z[0] + z[1]) + (z[2] + z[3]);
+                    Xc = fma_<R>(Xc, co.tc(s), Xc);
+                    if (FN == FN_AVG) Fc += Xc;
+                    if (FN == FN_MIN) Fc = min_<R>(Fc, Xc);
+                }
+            }
+            double vf, vc, gf = 0.0, gc = 0.0;
+            if (FN == FN_AVG) {          // trapezoid :369-386
+                vf = C.avg_wf * ((double)Ff + fma(-0.5, (double)Xf, h0));
+                vc = C.avg_wc * ((double)Fc + fma(-0.5, (double)Xc, h0));
+            } else {
+                vf = (double)Xf; vc = (double)Xc; gf = (double)Ff; gc = (double)Fc;
+            }
+            emit_t<FN, false>(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
+        }
+        return;
+    }
     // The coarsest levels (1 or 2 fine steps per path) are where MLMC puts most of its samples and
     // a path needs fewer normals than one Philox block holds: 4 (or 2) consecutive global path ids
     // share one block (stream STREAM_PACK, counter = id / paths-per-block), each taking its own
@@ -1594,7 +1737,7 @@ gbm_packed_kernel(const __grid_constant__ LevelConsts C, double* partials, unsig
         const R X0 = (R)C.X0;
         const double h0 = 0.5 * C.X0, vc0 = FN == FN_AVG ? 0.0 : C.X0, gc0 = FN == FN_MIN ? C.X0 : 0.0;
         double s0 = 0.0, s1 = 0.0;
-        for (ull c = first + (ull)blockIdx.x * blockDim.x + threadIdx.x; c <= last; c += stride) {
+        for (ull c = first + tid; c <= last; c += stride) {
             R z[4];
             PhiloxSource<R, SAMP>{C, c}.load4_stream(STREAM_PACK, 0, z);
             const ull p0 = c << 2;
@@ -1623,8 +1766,9 @@ gbm_packed_kernel(const __grid_constant__ LevelConsts C, double* partials, unsig
         }
         acc.s[0] = acc.s[2] = s0;
         acc.s[1] = acc.s[3] = s1;
+        acc.s[4] = acc.s[5] = acc.s[6] = 0.0;
     } else {
-        for (ull c = first + (ull)blockIdx.x * blockDim.x + threadIdx.x; c <= last; c += stride) {
+        for (ull c = first + tid; c <= last; c += stride) {
             PhiloxSource<R, SAMP> quad{C, c};
             PackedSource<R> src;
             quad.load4_stream(STREAM_PACK, 0, src.z);
@@ -1639,18 +1783,26 @@ gbm_packed_kernel(const __grid_constant__ LevelConsts C, double* partials, unsig
             }
         }
     }
+}
+
+template <typename R, int FN, int SAMP, int SCH, int NS>
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64 : MLMCB_MINBLOCKS)
+gbm_packed_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
+                  double* out7, double* Pf_out, double* Pc_out) {
+    sampler_init<SAMP>();
+    Sums7 acc;
+    acc.clear();
+    gbm_packed_body<R, FN, SAMP, SCH, NS>(C, blockIdx.x, gridDim.x, acc, Pf_out, Pc_out);
     grid_finish(acc, partials, ticket, out7);
 }
 
+
 template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH>
-__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64 : (MODEL == 0 ? MLMCB_MINBLOCKS : MLMCB_MINBLOCKS_MJD))
-level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
-             double* out7, double* Pf_out, double* Pc_out) {
-    Sums7 acc;
-    acc.clear();
-    const ull stride = (ull)gridDim.x * blockDim.x;
+__device__ __forceinline__ void level_body(const LevelConsts& C, unsigned bid, unsigned nblk, Sums7& acc,
+                                           double* Pf_out, double* Pc_out) {
+    const ull stride = (ull)nblk * blockDim.x;
     double* const rec = JumpRecStore<MODEL>::column();
-    for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
+    for (ull i = (ull)bid * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
         const ull pid = C.path_offset + i;
         double vf, vc, gf, gc;
         if (MODEL == 0) {
@@ -1661,7 +1813,82 @@ level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* 
         }
         emit_t<FN>(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
     }
+}
+
+template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH>
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? (MODEL == 0 ? MLMCB_MINBLOCKS_F64 : MLMCB_MINBLOCKS_F64_MJD)
+                                                                : (MODEL == 0 ? MLMCB_MINBLOCKS : MLMCB_MINBLOCKS_MJD))
+level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
+             double* out7, double* Pf_out, double* Pc_out) {
+    sampler_init<SAMP>();
+    Sums7 acc;
+    acc.clear();
+    level_body<R, MODEL, FN, MT, SAMP, SCH>(C, blockIdx.x, gridDim.x, acc, Pf_out, Pc_out);
     grid_finish(acc, partials, ticket, out7);
+}
+
+// ------------------------------------------------------------------------------------------
+// One launch for a whole sweep of Option.mlmc's `for l in range(L+1)` loop (:994-997).
+// The grid is cut into consecutive block ranges, one per requested level (deepest first: it has the
+// longest serial path and must start first); a block looks its range up, runs the body of the kernel
+// that level would get on its own - packed / four-step / long GBM paths, event-driven / block-uniform
+// Merton walk - on that level's constants, and leaves one row of partial sums.  The last block to
+// arrive folds every level's rows in block order into out[row][8] and clears the ticket, so the
+// persistent workspace needs neither a memset nor an allocation between launches.  The per-level
+// constants sit in the kernel's parameter block (indexed by a block-uniform level number).
+// ------------------------------------------------------------------------------------------
+constexpr int kSweepMax = 20;
+enum { SK_PACKED = 0, SK_FOUR = 1, SK_LONG = 2, SK_MJD_FLAT = 3, SK_MJD_UNIFORM = 4 };
+struct SweepConsts {
+    int n_levels, n_rows;
+    unsigned first[kSweepMax + 1];      // blocks [first[k], first[k+1]) simulate entry k
+    int kind[kSweepMax], row[kSweepMax];
+    LevelConsts lv[kSweepMax];
+};
+static_assert(sizeof(SweepConsts) <= 32764, "kernel parameters are limited to 32764 bytes");
+
+template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH>
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? (MODEL == 0 ? MLMCB_MINBLOCKS_F64 - 1 : MLMCB_MINBLOCKS_F64_MJD)
+                                                                : (MODEL == 0 ? MLMCB_MINBLOCKS - 2 : MLMCB_MINBLOCKS_FLAT - 1))
+sweep_kernel(const __grid_constant__ SweepConsts S, double* partials, unsigned* ticket, double* out) {
+    sampler_init<SAMP>();
+    int k = 0;
+    while (k + 1 < S.n_levels && blockIdx.x >= S.first[k + 1]) ++k;
+    const LevelConsts& C = S.lv[k];
+    const unsigned bid = blockIdx.x - S.first[k], nblk = S.first[k + 1] - S.first[k];
+    Sums7 acc;
+    acc.clear();
+    if (MODEL == 0) {
+        const int kind = S.kind[k];
+        if (kind == SK_PACKED) gbm_packed_body<R, FN, SAMP, SCH, 0>(C, bid, nblk, acc, nullptr, nullptr);
+        else if (MT != 0 && kind == SK_FOUR) gbm_packed_body<R, FN, SAMP, SCH, MT == 4 ? 4 : -4>(C, bid, nblk, acc, nullptr, nullptr);
+        else level_body<R, 0, FN, MT, SAMP, SCH>(C, bid, nblk, acc, nullptr, nullptr);
+    } else {
+        if (S.kind[k] == SK_MJD_FLAT) mjd_flat_body<R, FN, MT, SAMP, SCH>(C, bid, nblk, acc, nullptr, nullptr);
+        else level_body<R, 1, FN, MT, SAMP, SCH>(C, bid, nblk, acc, nullptr, nullptr);
+    }
+    __shared__ double sm[(kThreads / 32) * 8];
+    __shared__ unsigned last;
+    const double mine = block_fold(acc, sm);
+    if (threadIdx.x < 7) partials[(size_t)blockIdx.x * 8 + threadIdx.x] = mine;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int t = threadIdx.x; t < S.n_rows * 8; t += blockDim.x) out[t] = 0.0;      // rows of empty requests
+    for (int j = 0; j < S.n_levels; ++j) {
+        Sums7 t;
+        t.clear();
+        for (unsigned r = S.first[j] + threadIdx.x; r < S.first[j + 1]; r += blockDim.x) {
+#pragma unroll
+            for (int q = 0; q < 7; ++q) t.s[q] += __ldcg(&partials[(size_t)r * 8 + q]);
+        }
+        const double tot = block_fold(t, sm);
+        if (threadIdx.x < 7) out[S.row[j] * 8 + threadIdx.x] = tot;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
 }
 
 template <int FN, int AR, int SCH>
@@ -1684,23 +1911,24 @@ replay_gbm_kernel(const __grid_constant__ LevelConsts C, const double* Z, double
     grid_finish(acc, partials, ticket, out7);
 }
 
-template <typename R, int FN, int MT, int SAMP>
+template <typename R, int FN, int MT, int SAMP, int SCH>
 __global__ void __launch_bounds__(kThreads)
 level_anti_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
                   double* out7, double* Pf_out, double* Pc_out) {
+    sampler_init<SAMP>();
     Sums7 acc;
     acc.clear();
     const ull stride = (ull)gridDim.x * blockDim.x;
     for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
         PhiloxSource<R, SAMP> src{C, C.path_offset + i};
         double vf, va, vc;
-        gbm_anti_path_fast<R, FN, MT>(C, src, vf, va, vc);
+        gbm_anti_path_fast<R, FN, MT, SCH>(C, src, vf, va, vc);
         emit_anti(C, i, vf, va, vc, acc, Pf_out, Pc_out);
     }
     grid_finish(acc, partials, ticket, out7);
 }
 
-template <int FN, int AR>
+template <int FN, int AR, int SCH>
 __global__ void __launch_bounds__(kThreads)
 replay_gbm_anti_kernel(const __grid_constant__ LevelConsts C, const double* Z, double* partials, unsigned* ticket,
                        double* out7, double* Pf_out, double* Pc_out) {
@@ -1710,10 +1938,10 @@ replay_gbm_anti_kernel(const __grid_constant__ LevelConsts C, const double* Z, d
     for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < C.n_paths; i += stride) {
         double vf, va, vc;
         if (AR == AR_EXACT) {
-            gbm_anti_path_exact<FN>(C, Z, C.n_paths, i, vf, va, vc);
+            gbm_anti_path_exact<FN, SCH>(C, Z, C.n_paths, i, vf, va, vc);
         } else {
             ReplaySource src{Z, C.n_paths, i, C.nsteps};
-            gbm_anti_path_fast<double, FN, 0>(C, src, vf, va, vc);
+            gbm_anti_path_fast<double, FN, 0, SCH>(C, src, vf, va, vc);
         }
         emit_anti(C, i, vf, va, vc, acc, Pf_out, Pc_out);
     }
@@ -1757,6 +1985,7 @@ replay_mjd_kernel(const __grid_constant__ LevelConsts C, const double* zW, const
 // divided by lam), the jump-size normal and the Brownian normal of the sub-step that ends at the jump.
 template <int SAMP>
 __global__ void jump_probe_kernel(const __grid_constant__ LevelConsts C, ull n_records, double* out) {
+    sampler_init<SAMP>();
     const ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C.n_paths) return;
     for (ull k = 0; k < n_records; ++k) {
@@ -1772,6 +2001,7 @@ __global__ void jump_probe_kernel(const __grid_constant__ LevelConsts C, ull n_r
 // path ids share one Philox block of the STREAM_PACK stream: out[step*n_paths + path].
 template <int SAMP>
 __global__ void packed_probe_kernel(const __grid_constant__ LevelConsts C, int nsteps, double* out) {
+    sampler_init<SAMP>();
     const ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C.n_paths) return;
     const int per = nsteps == 1 ? 4 : 2;
@@ -1787,6 +2017,7 @@ __global__ void packed_probe_kernel(const __grid_constant__ LevelConsts C, int n
 
 template <int SAMP>
 __global__ void sampler_probe_kernel(const __grid_constant__ LevelConsts C, ull n_steps, double* out) {
+    sampler_init<SAMP>();
     const ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C.n_paths) return;
     PhiloxSource<double, SAMP> src{C, C.path_offset + i};

@@ -1,7 +1,8 @@
 // libmlmcb - selecting one instantiation of a level-kernel family from run-time codes.
-// The families live in separate translation units (mlmcb_gbm.cu, mlmcb_merton_uniform.cu,
-// mlmcb_merton_flat.cu; antithetic, replay, American and probe kernels stay in mlmcb_api.cu) so that
-// nvcc compiles them side by side.
+// A family x sampler pair is one translation unit: mlmcb_family.cu compiled with
+// -DMLMCB_TU_FAMILY={0 GBM, 1 Merton block-uniform, 2 Merton event-driven, 3 GBM sweep, 4 Merton sweep} -DMLMCB_TU_SAMP={0 f32bm, 1 f64bm}
+// (build.py), so nvcc compiles the ten of them side by side; replay, American and probe kernels stay in
+// mlmcb_api.cu.
 #pragma once
 #include "../../include/mlmcb.h"
 #include "mlmcb_kernels.cuh"
@@ -9,6 +10,7 @@
 namespace mlmcb {
 
 typedef void (*LevelKernel)(const LevelConsts, double*, unsigned*, double*, double*, double*);
+typedef void (*SweepKernel)(const SweepConsts, double*, unsigned*, double*);
 
 // Fam::get<R, FN, MT, SAMP, SCH>() returns the kernel
 template <class Fam, typename R, int FN, int SAMP, int SCH>
@@ -27,18 +29,40 @@ LevelKernel pick_fn(int fn, int mt) {
     default: return pick_mt<Fam, R, FN_FINAL, SAMP, SCH>(mt);
     }
 }
-// fn: FN_*; mt: 2, 4 or 0 (generic M); flags: sampler, MLMCB_FP32_PATHS, MLMCB_MILSTEIN - 36 kernels per family
-template <class Fam>
+// fn: FN_*; mt: 2, 4 or 0 (generic M); flags: MLMCB_FP32_PATHS, MLMCB_MILSTEIN.  Per sampler: fp64 paths with
+// either scheme, fp32 paths with Euler-Maruyama (check_flags refuses Milstein in fp32) - 27 kernels.
+template <class Fam, int SAMP>
 LevelKernel pick_family(int fn, int mt, int flags) {
-    const int samp = flags & MLMCB_SAMPLER_MASK;
-    if (flags & MLMCB_MILSTEIN) return pick_fn<Fam, double, SAMP_F32BM, SCH_MILSTEIN>(fn, mt);
-    if (flags & MLMCB_FP32_PATHS) return pick_fn<Fam, float, SAMP_F32BM>(fn, mt);      // default sampler only (check_flags)
-    return samp == MLMCB_SAMPLER_F64BM ? pick_fn<Fam, double, SAMP_F64BM>(fn, mt) : pick_fn<Fam, double, SAMP_F32BM>(fn, mt);
+    if (flags & MLMCB_MILSTEIN) return pick_fn<Fam, double, SAMP, SCH_MILSTEIN>(fn, mt);
+    if (flags & MLMCB_FP32_PATHS) return pick_fn<Fam, float, SAMP>(fn, mt);
+    return pick_fn<Fam, double, SAMP>(fn, mt);
 }
 
-LevelKernel pick_gbm(int fn, int mt, int flags);              // mlmcb_gbm.cu
-LevelKernel pick_gbm_packed(int fn, int flags);               // mlmcb_gbm.cu: paths of one or two fine steps
-LevelKernel pick_merton_uniform(int fn, int mt, int flags);   // mlmcb_merton_uniform.cu
-LevelKernel pick_merton_flat(int fn, int mt, int flags);      // mlmcb_merton_flat.cu
+// the sweep kernels: fp64 paths, plain estimator, either scheme (anything else takes the per-level launches)
+template <int MODEL, int FN, int SAMP, int SCH>
+SweepKernel pick_sweep_mt(int mt) {
+    switch (mt) {
+    case 2: return sweep_kernel<double, MODEL, FN, 2, SAMP, SCH>;
+    case 4: return sweep_kernel<double, MODEL, FN, 4, SAMP, SCH>;
+    default: return sweep_kernel<double, MODEL, FN, 0, SAMP, SCH>;
+    }
+}
+template <int MODEL, int SAMP>
+SweepKernel pick_sweep(int fn, int mt, int flags) {
+    if (flags & MLMCB_MILSTEIN)
+        return fn == FN_AVG ? pick_sweep_mt<MODEL, FN_AVG, SAMP, SCH_MILSTEIN>(mt)
+             : fn == FN_MIN ? pick_sweep_mt<MODEL, FN_MIN, SAMP, SCH_MILSTEIN>(mt) : pick_sweep_mt<MODEL, FN_FINAL, SAMP, SCH_MILSTEIN>(mt);
+    return fn == FN_AVG ? pick_sweep_mt<MODEL, FN_AVG, SAMP, SCH_EM>(mt)
+         : fn == FN_MIN ? pick_sweep_mt<MODEL, FN_MIN, SAMP, SCH_EM>(mt) : pick_sweep_mt<MODEL, FN_FINAL, SAMP, SCH_EM>(mt);
+}
+
+// defined (as explicit specialisations) by the translation unit of that family and sampler
+template <int SAMP> LevelKernel pick_gbm_s(int fn, int mt, int flags);
+template <int SAMP> LevelKernel pick_gbm_packed_s(int fn, int flags, int nsteps);   // paths of 1, 2 or 4 fine steps
+template <int SAMP> LevelKernel pick_gbm_anti_s(int fn, int mt, int flags);         // antithetic triple (Euro/Asian)
+template <int SAMP> LevelKernel pick_merton_uniform_s(int fn, int mt, int flags);
+template <int SAMP> LevelKernel pick_merton_flat_s(int fn, int mt, int flags);
+template <int SAMP> SweepKernel pick_gbm_sweep_s(int fn, int mt, int flags);         // MLMCB_TU_FAMILY 3
+template <int SAMP> SweepKernel pick_merton_sweep_s(int fn, int mt, int flags);      // MLMCB_TU_FAMILY 4
 
 }  // namespace mlmcb

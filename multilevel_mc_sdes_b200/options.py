@@ -12,7 +12,9 @@ global MT19937, so each Option carries a seed and a per-level path-offset counte
 call consumes fresh ids).  `mlmc` is the reference driver restated line by line
 (host code; it only decides how many samples each level gets), None-safe for alpha_0/beta_0.
 
-Extra constructor kwargs (keyword-only, all optional): seed, device, sampler ("f32bm"|"f64bm"),
+Extra constructor kwargs (keyword-only, all optional): seed, device, sampler ("f64bm" - the default: 52-bit
+uniforms and an fp64 Box-Muller, i.e. the precision of the reference's numpy normals - or "f32bm": the opt-in fast
+sampler, 32-bit uniforms and fp32 Box-Muller normals promoted to fp64, about twice the throughput),
 fp32 (path arithmetic in fp32, opt-in), scheme ("em" | "milstein": the time-stepper the demo notebook
 swaps in through `opt.sde`, ExampleUsages.ipynb cells 1 and 6), distributed (shard each level call over the
 torch.distributed world and all-reduce the 7 sums).
@@ -108,7 +110,7 @@ class Option:
     _has_anti = False             # Euro_GBM / Asian_GBM bind anti_payoff + anti_path (:1379-1381, :1406-1408)
 
     def __init__(self, alpha_0=None, beta_0=None, X0=100, K=100, T=1, r=0.05, *,
-                 seed=0, device=0, sampler="f32bm", fp32=False, scheme="em", distributed=False, verbose=True):
+                 seed=0, device=0, sampler="f64bm", fp32=False, scheme="em", distributed=False, verbose=True):
         self.alpha_0 = alpha_0
         self.beta_0 = beta_0
         self.X0 = X0
@@ -225,15 +227,23 @@ class Option:
         lo, hi = (g * n) // G, ((g + 1) * n) // G
         return hi - lo, start + lo
 
+    def _nccl(self):
+        """True when the all-reduce of the sums runs on the device (torch.distributed over NCCL)."""
+        if not self.distributed:
+            return False
+        import torch.distributed as dist
+        return dist.get_backend() == "nccl"
+
     def _allreduce(self, rows):
-        """Sum rows (k,7) over the world: the only message of the method."""
+        """Sum host rows (k,7) over the world (gloo: the CPU test path; NCCL sweeps never leave the device,
+        see _sweep)."""
         if not self.distributed:
             return rows
         import torch
         import torch.distributed as dist
-        backend = dist.get_backend()
-        dev = f"cuda:{self.device}" if backend == "nccl" else "cpu"
-        t = torch.as_tensor(np.ascontiguousarray(rows), dtype=torch.float64, device=dev)
+        t = torch.as_tensor(np.ascontiguousarray(rows), dtype=torch.float64)
+        if dist.get_backend() == "nccl":
+            t = t.to(f"cuda:{self.device}")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t.cpu().numpy()
 
@@ -288,8 +298,8 @@ class Option:
         return out
 
     def _sweep(self, requests, M, anti=False):
-        """requests: [(Nl, l), ...] -> list of 7-vectors.  All launches of one sweep run
-        concurrently on the device; one D2H copy brings every row back."""
+        """requests: [(Nl, l), ...] -> list of 7-vectors.  The whole sweep is one kernel launch (per-level
+        block ranges); one D2H copy brings every row back."""
         self._check_product()
         if anti and not self._has_anti:
             raise NotImplementedError("Option instance has no implemented anti_payoff method")   # :844
@@ -305,12 +315,24 @@ class Option:
             offsets.append(start_loc)
         n_arr = (C.c_uint64 * k)(*counts)
         o_arr = (C.c_uint64 * k)(*offsets)
-        out = np.zeros((k, 7))
         p = self._params(tuple(int(l) for _, l in requests))
+        flags = self._flags() | (_lib.ANTITHETIC if anti else 0)
+        if self._nccl():
+            # multi-GPU: the kernel writes its rows into the buffer NCCL reduces in place; one D2H after it
+            import torch
+            import torch.distributed as dist
+            dev = torch.device("cuda", self.device)
+            buf = torch.empty((k, 8), dtype=torch.float64, device=dev)
+            _lib.check(_lib.load().mlmcb_level_sweep(
+                C.byref(p), self._model, self._payoff_kind, int(M), k, levels, n_arr, o_arr, self.seed, flags,
+                self.device, _stream_handle(self.device), buf.data_ptr()))
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            out = buf.cpu().numpy()[:, :7]
+            return [out[i].copy() for i in range(k)]
+        out = np.zeros((k, 7))
         _lib.check(_lib.load().mlmcb_level_sweep_host(
-            C.byref(p), self._model, self._payoff_kind, int(M), k, levels, n_arr, o_arr, self.seed,
-            self._flags() | (_lib.ANTITHETIC if anti else 0), self.device, _stream_handle(self.device),
-            out.ctypes.data_as(C.POINTER(C.c_double))))
+            C.byref(p), self._model, self._payoff_kind, int(M), k, levels, n_arr, o_arr, self.seed, flags,
+            self.device, _stream_handle(self.device), out.ctypes.data_as(C.POINTER(C.c_double))))
         out = self._allreduce(out)
         return [out[i].copy() for i in range(k)]
 
@@ -514,15 +536,25 @@ class Amer_GBM(GBM_Option):
 
     def __init__(self, exerciseBoundary=0.8, **kwargs):
         super().__init__(**kwargs)
-        c = getattr(exerciseBoundary, "mlmcb_c", exerciseBoundary)
+        self.exerciseBoundary = exerciseBoundary
+
+    @property
+    def exerciseBoundary(self):
+        return self._exercise_boundary
+
+    @exerciseBoundary.setter
+    def exerciseBoundary(self, b):
+        """The reference lets a user rebind `opt.exerciseBoundary` at any time: every assignment re-derives how the
+        boundary reaches the kernel and drops the tabulated values of the previous one."""
+        c = getattr(b, "mlmcb_c", b)
         self._boundary_tables = {}
         if callable(c):
             self.boundary_c = 0.0
-            self.exerciseBoundary = exerciseBoundary
+            self._exercise_boundary = b
             self._tabulated = True
         else:
             self.boundary_c = float(c)
-            self.exerciseBoundary = sqrt_boundary(self.boundary_c)
+            self._exercise_boundary = sqrt_boundary(self.boundary_c)
             self._tabulated = False
 
     def _boundary_values(self, l):

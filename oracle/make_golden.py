@@ -9,6 +9,8 @@ Files
   payoffs_gbm.npz     per-path (Pf,Pc) of `opt.payoff(N,l,M)` for the 4 GBM products, with the
                       seed; small cases also carry the literal normals Z[step,path] the
                       reference consumed (np.random.randn wrapped while the reference ran)
+  payoffs_anti_milstein.npz  anti_payoff with the notebook's Milstein stepper bound over `sde`
+  payoffs_merton_deep.npz    the 4 Merton products at 128 / 256 fine steps (l=7,8 M=2; l=4 M=4)
   payoffs_merton.npz  same for the 4 Merton products with the three ragged draw streams
                       (dW normals, jump-size normals, inter-arrival times) in CSR layout
   looper.npz          `opt.looper(Nl,l,M,False,Npl)` 7-vectors for seeds
@@ -280,6 +282,87 @@ def milstein_cases(ref):
     return out
 
 
+def anti_milstein_cases(ref):
+    """anti_payoff (:292-317) with the notebook's milstein_GBM bound over `sde`: diffusion_anti_path(_avg)
+    calls whatever `self.sde` is (:200-210), so the antithetic estimator composes with the Milstein stepper."""
+    import types
+    out = {}
+    idx = 0
+    for cname in ("Euro_GBM", "Asian_GBM"):
+        for kw_name, kw in (("default", {}), ("alt2", ALT_GBM2)):
+            for M in (2, 4, 6):
+                for l in (0, 1, 2, 3, 5):
+                    if M == 6 and l > 2:
+                        continue
+                    steps = M ** l
+                    n = 64 if steps <= 64 else 24
+                    seed = 7300 + idx
+                    opt = getattr(ref, cname)(**kw)
+                    opt.sde = types.MethodType(milstein_GBM, opt)
+                    np.random.seed(seed)
+                    Pf, Pc = opt.anti_payoff(n, l, M)
+                    key = f"c{idx}"
+                    out[key + "_meta"] = np.array([cname, kw_name, str(l), str(M), str(n), str(seed)])
+                    out[key + "_Pf"] = np.asarray(Pf, dtype=np.float64)
+                    out[key + "_Pc"] = np.asarray(Pc, dtype=np.float64) * np.ones(n)
+                    idx += 1
+    opt = ref.Asian_GBM()
+    opt.sde = types.MethodType(milstein_GBM, opt)
+    np.random.seed(7399)
+    out["l0_meta"] = np.array(["Asian_GBM", "2", "4", "600", "250", "7399"])
+    out["l0_sums"] = opt.looper(600, 2, 4, True, 250)
+    out["n_cases"] = np.array(idx)
+    out["n_looper"] = np.array(1)
+    return out
+
+
+def merton_deep_cases(ref):
+    """JD_path* (:428-651) at 128 and 256 fine steps - the regime the block-uniform Merton walk serves
+    (l = 7, 8 with M = 2; l = 4 with M = 4).  Same layout as payoffs_merton.npz."""
+    out = {}
+    idx = 0
+    for cname in MJD_CLASSES:
+        for kw_name, kw in (("default", {}), ("alt", ALT_MJD)):
+            for (l, M) in ((7, 2), (8, 2), (4, 4)):
+                if kw_name == "alt" and l == 8:
+                    continue
+                n = 24
+                seed = 5600 + idx
+                kw2 = dict(kw)
+                if cname == "Lookback_Merton":
+                    kw2.pop("K", None)
+                opt = getattr(ref, cname)(**kw2)
+                np.random.seed(seed)
+                Pf_all, Pc_all, zw, zq, ex = [], [], [], [], []
+                for _ in range(n):
+                    with Tap() as tap:
+                        tap.wrap_jumptime(opt)
+                        Pf, Pc = opt.payoff(1, l, M)
+                        opt.jumptime = np.random.exponential
+                    Pf_all.append(float(Pf[0]))
+                    Pc_all.append(float(np.asarray(Pc).reshape(-1)[0]))
+                    zw.append([float(v) for v in tap.randn_calls])
+                    zq.append(tap.stdn)
+                    ex.append(tap.expo)
+
+                def csr(rows):
+                    off = np.zeros(len(rows) + 1, dtype=np.int64)
+                    off[1:] = np.cumsum([len(r) for r in rows])
+                    return np.array([v for r in rows for v in r], dtype=np.float64), off
+
+                key = f"c{idx}"
+                out[key + "_meta"] = np.array([cname, kw_name, str(l), str(M), str(n), str(seed)])
+                out[key + "_Pf"] = np.array(Pf_all)
+                out[key + "_Pc"] = np.array(Pc_all)
+                for nm, rows in (("W", zw), ("Q", zq), ("E", ex)):
+                    flat, off = csr(rows)
+                    out[key + "_z" + nm] = flat
+                    out[key + "_off" + nm] = off
+                idx += 1
+    out["n_cases"] = np.array(idx)
+    return out
+
+
 def amer_cases(ref):
     """Amer_GBM (:1483-1632) with the demo notebook's exercise boundary `exb` (cell 1):
     np.maximum(self.K*(1-0.8*np.sqrt(self.T-t)),0); c = 0.8 and one other value."""
@@ -409,6 +492,7 @@ def main():
     ref = load_reference()
     os.makedirs(OUT, exist_ok=True)
     for name, fn in (("payoffs_gbm", gbm_cases), ("payoffs_merton", merton_cases), ("payoffs_anti", anti_cases),
+                     ("payoffs_anti_milstein", anti_milstein_cases), ("payoffs_merton_deep", merton_deep_cases),
                      ("payoffs_milstein", milstein_cases), ("payoffs_amer", amer_cases),
                      ("payoffs_amer_callable", amer_callable_cases), ("looper", looper_cases),
                      ("mlmc_trace", mlmc_traces), ("closed_forms", closed_forms)):

@@ -37,7 +37,7 @@ def pytest_sessionstart(session):
 @pytest.fixture(scope="session")
 def golden():
     return {n: np.load(os.path.join(GOLDEN, n + ".npz"), allow_pickle=False)
-            for n in ("payoffs_gbm", "payoffs_merton", "payoffs_anti", "payoffs_milstein", "payoffs_amer", "payoffs_amer_callable", "looper", "mlmc_trace", "closed_forms")}
+            for n in ("payoffs_gbm", "payoffs_merton", "payoffs_merton_deep", "payoffs_anti", "payoffs_anti_milstein", "payoffs_milstein", "payoffs_amer", "payoffs_amer_callable", "looper", "mlmc_trace", "closed_forms")}
 
 
 @pytest.fixture(scope="session")

@@ -64,5 +64,5 @@ def test_two_rank_sharding_and_allreduce():
         np.testing.assert_allclose(r1, _fake_row(3, 1001, 0), rtol=1e-12, atol=1e-9)
         np.testing.assert_allclose(r2, _fake_row(3, 500, 1001), rtol=1e-12, atol=1e-9)
         for l in range(3):
-            np.testing.assert_allclose(sw[:, l], _fake_row(l, 77, 1501 if l == 3 else 0), rtol=1e-12, atol=1e-9)
+            np.testing.assert_allclose(sw[:, l], _fake_row(l, 77, 0), rtol=1e-12, atol=1e-9)
     assert (res[0][4], res[0][5]) == (5, 100) and (res[1][4], res[1][5]) == (5, 105)

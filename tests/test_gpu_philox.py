@@ -202,7 +202,9 @@ def test_looper_host_call_and_sweep(cuda_lib):
     opt2 = mm.Lookback_GBM(seed=77)
     sw = opt2.level_sweep(Lmax=4, Nsamples=200_000, M=4)
     assert sw.shape == (7, 5)
-    assert np.array_equal(sw[:, 2], s)                             # same ids, same sums, sweep or single
+    # same ids, same paths, sweep or single call; the sweep kernel cuts the paths into other block ranges, so
+    # the sums agree to summation order
+    np.testing.assert_allclose(sw[:, 2], s, rtol=1e-13)
     # second call on the same object uses fresh ids
     assert not np.array_equal(opt.looper(200_000, 2, 4, False), s)
     Pf, Pc = mm.Euro_GBM().payoff(1000, 0, 2)
@@ -260,9 +262,7 @@ def test_milstein_level_moments(cuda_lib, c_oracle, cname):
             v.append(s[1] / 2e6 - (s[0] / 2e6) ** 2)
         assert 10 < v[0] / v[1] < 24 and 10 < v[1] / v[2] < 24
     with pytest.raises(NotImplementedError):
-        mm.Euro_GBM(scheme="milstein").looper(100, 2, 2, True)        # not built with the antithetic estimator
-    with pytest.raises(NotImplementedError):
-        mm.Euro_GBM(scheme="milstein", sampler="f64bm").looper(100, 2, 2, False)
+        mm.Euro_GBM(scheme="milstein", fp32=True).looper(100, 2, 2, False)      # Milstein: fp64 path arithmetic only
 
 
 def test_f64bm_stream_matches_float64_recomputation(cuda_lib):
@@ -425,10 +425,9 @@ def test_philox_mode_equals_replay_of_its_own_draws_gbm(cuda_lib, sampler):
     (sampler probe) pushed through the replay entry point reproduce its per-path payoffs."""
     code = _lib.SAMPLER_F32BM if sampler == "f32bm" else _lib.SAMPLER_F64BM
     for cls, scheme in ((mm.Euro_GBM, "em"), (mm.Asian_GBM, "em"), (mm.Lookback_GBM, "em"), (mm.Digital_GBM, "em"),
-                        (mm.Asian_GBM, "milstein")):
-        if scheme == "milstein" and sampler == "f64bm":
-            continue                      # Milstein is built for the default sampler only
-        for l, M in ((2, 2), (3, 4), (2, 3), (5, 2)):
+                        (mm.Asian_GBM, "milstein"), (mm.Lookback_GBM, "milstein")):
+        # (1,4) and (2,2): the four-step kernels; (6,4): the headline level (4096 steps)
+        for l, M in ((2, 2), (1, 4), (3, 4), (2, 3), (5, 2), (6, 4)):
             n, off, seed = 1000, 12345, 31
             opt = cls(seed=seed, sampler=sampler, scheme=scheme)
             opt._next_path[l] = off
@@ -446,21 +445,25 @@ def test_philox_mode_equals_replay_of_its_own_draws_gbm(cuda_lib, sampler):
         Rf, Rc = mm.Amer_GBM().payoff_replay(Z, l, 2, arith="fast")
         np.testing.assert_allclose(Pf, Rf, rtol=1e-12, atol=1e-10)
         np.testing.assert_allclose(Pc, Rc, rtol=1e-12, atol=1e-10)
-    # antithetic
-    opt = mm.Asian_GBM(seed=5, sampler=sampler)
-    opt._next_path[3] = 77
-    Pf, Pc = opt.anti_payoff(500, 3, 4)
-    Z = _probe_normals(cuda_lib, code, 5, 3, 77, 500, 64)
-    Rf, Rc = mm.Asian_GBM().payoff_replay(Z, 3, 4, arith="fast", anti=True)
-    np.testing.assert_allclose(Pf, Rf, rtol=1e-13, atol=1e-11)
-    np.testing.assert_allclose(Pc, Rc, rtol=1e-13, atol=1e-11)
+    # antithetic, with either time-stepper
+    for scheme in ("em", "milstein"):
+        for cls in (mm.Asian_GBM, mm.Euro_GBM):
+            opt = cls(seed=5, sampler=sampler, scheme=scheme)
+            opt._next_path[3] = 77
+            Pf, Pc = opt.anti_payoff(500, 3, 4)
+            Z = _probe_normals(cuda_lib, code, 5, 3, 77, 500, 64)
+            Rf, Rc = cls(scheme=scheme).payoff_replay(Z, 3, 4, arith="fast", anti=True)
+            np.testing.assert_allclose(Pf, Rf, rtol=1e-13, atol=1e-11)
+            np.testing.assert_allclose(Pc, Rc, rtol=1e-13, atol=1e-11)
 
 
-def test_philox_mode_equals_replay_of_its_own_draws_gbm_random_parameters(cuda_lib):
+@pytest.mark.parametrize("sampler", ["f32bm", "f64bm"])
+def test_philox_mode_equals_replay_of_its_own_draws_gbm_random_parameters(cuda_lib, sampler):
     """The same with random model parameters, path-id offsets and levels: the packed kernel (1-2 steps), the
     level kernel, and the American-put kernel with a host-tabulated boundary (T != 1 moves every table time)."""
     import torch
     from oracle.boundaries import BOUNDARIES
+    code = _lib.SAMPLER_F32BM if sampler == "f32bm" else _lib.SAMPLER_F64BM
     rng = np.random.default_rng(31415)
     classes = (mm.Euro_GBM, mm.Asian_GBM, mm.Lookback_GBM, mm.Digital_GBM)
     levels = ((0, 2), (1, 2), (0, 4), (2, 2), (1, 4), (1, 3), (3, 2), (2, 4), (2, 5), (6, 2), (3, 4))
@@ -471,17 +474,17 @@ def test_philox_mode_equals_replay_of_its_own_draws_gbm_random_parameters(cuda_l
         cls = classes[it % 4]
         l, M = levels[it % len(levels)]
         n, off, seed = 500, int(rng.integers(0, 2 ** 44)), int(rng.integers(0, 2 ** 31))
-        opt = cls(seed=seed, **kw)
+        opt = cls(seed=seed, sampler=sampler, **kw)
         opt._next_path[l] = off
         Pf, Pc = opt.payoff(n, l, M)
         nsteps = M ** l
         if nsteps <= 2:
             out = torch.empty(nsteps * n, dtype=torch.float64, device="cuda")
-            _lib.check(cuda_lib.mlmcb_packed_probe(_lib.SAMPLER_F32BM, seed, l, nsteps, off, n, 0, 0, out.data_ptr()))
+            _lib.check(cuda_lib.mlmcb_packed_probe(code, seed, l, nsteps, off, n, 0, 0, out.data_ptr()))
             torch.cuda.synchronize()
             Z = out.cpu().numpy().reshape(nsteps, n)
         else:
-            Z = _probe_normals(cuda_lib, _lib.SAMPLER_F32BM, seed, l, off, n, nsteps)
+            Z = _probe_normals(cuda_lib, code, seed, l, off, n, nsteps)
         Rf, Rc = cls(**kw).payoff_replay(Z, l, M, arith="fast")
         scale = 1e-12 * max(kw["X0"], kw["K"])
         np.testing.assert_allclose(Pf, Rf, rtol=1e-12, atol=scale)
@@ -489,28 +492,29 @@ def test_philox_mode_equals_replay_of_its_own_draws_gbm_random_parameters(cuda_l
     for bname, l in (("power", 3), ("linear", 6), ("power", 0)):
         kw = dict(X0=float(rng.uniform(50, 150)), T=float(rng.uniform(0.3, 2.5)), r=0.04, sig=float(rng.uniform(0.1, 0.5)))
         kw["K"] = kw["X0"] * 1.05
-        opt = mm.Amer_GBM(exerciseBoundary=BOUNDARIES[bname], seed=12, **kw)
+        opt = mm.Amer_GBM(exerciseBoundary=BOUNDARIES[bname], seed=12, sampler=sampler, **kw)
         opt._next_path[l] = 9000
         Pf, Pc = opt.payoff(400, l, 2)
-        Z = _probe_normals(cuda_lib, _lib.SAMPLER_F32BM, 12, l, 9000, 400, 2 ** l)
+        Z = _probe_normals(cuda_lib, code, 12, l, 9000, 400, 2 ** l)
         Rf, Rc = mm.Amer_GBM(exerciseBoundary=BOUNDARIES[bname], **kw).payoff_replay(Z, l, 2, arith="fast")
         np.testing.assert_allclose(Pf, Rf, rtol=1e-12, atol=1e-10)
         np.testing.assert_allclose(Pc, Rc, rtol=1e-12, atol=1e-10)
 
 
-def _merton_own_draws_case(cuda_lib, cls, kw, l, M, n=600, off=999, seed=17, K=64):
+def _merton_own_draws_case(cuda_lib, cls, kw, l, M, n=600, off=999, seed=17, K=64, sampler="f64bm"):
     """Per-path payoffs of the production Merton kernel against the replay of its own draws: grid normals
     from the sampler probe, jump records from the jump probe, interleaved on the host in the order the
     reference consumes them (:454-479)."""
     import torch
-    opt = cls(seed=seed, **kw)
+    code = _lib.SAMPLER_F32BM if sampler == "f32bm" else _lib.SAMPLER_F64BM
+    opt = cls(seed=seed, sampler=sampler, **kw)
     opt._next_path[l] = off
     Pf, Pc = opt.payoff(n, l, M)
     nsteps = M ** l
     # grid normals: the coarsest GBM-style packing does not apply to Merton; block-addressed stream
-    Z = _probe_normals(cuda_lib, _lib.SAMPLER_F32BM, seed, l, off, n, max(nsteps, 1))
+    Z = _probe_normals(cuda_lib, code, seed, l, off, n, max(nsteps, 1))
     rec = torch.empty(3 * K * n, dtype=torch.float64, device="cuda")
-    _lib.check(cuda_lib.mlmcb_jump_probe(_lib.SAMPLER_F32BM, seed, l, opt.lam, off, n, K, 0, 0, rec.data_ptr()))
+    _lib.check(cuda_lib.mlmcb_jump_probe(code, seed, l, opt.lam, off, n, K, 0, 0, rec.data_ptr()))
     torch.cuda.synchronize()
     rec = rec.cpu().numpy().reshape(3, K, n)
     zW, zQ, E, oW, oQ, oE = [], [], [], [0], [0], [0]
@@ -538,17 +542,19 @@ def _merton_own_draws_case(cuda_lib, cls, kw, l, M, n=600, off=999, seed=17, K=6
     np.testing.assert_allclose(Pc, Rc, rtol=1e-12, atol=100 * scale)
 
 
+@pytest.mark.parametrize("sampler", ["f32bm", "f64bm"])
 @pytest.mark.parametrize("lam", [1.0, 6.0])
-def test_philox_mode_equals_replay_of_its_own_draws_merton(cuda_lib, lam):
+def test_philox_mode_equals_replay_of_its_own_draws_merton(cuda_lib, lam, sampler):
     """Exercises the jump-free run length agreement, the jump blocks and the tail of the block-uniform kernel,
     the event-driven kernel and the l = 0 loop against the straightforward replay loop."""
     for cls in (mm.Euro_Merton, mm.Asian_Merton, mm.Lookback_Merton):
         # 1 step: lane-queue loop; 2, 8, 9, 32, 64: event-driven kernel; 128, 256: block-uniform kernel
         for l, M in ((0, 2), (1, 2), (3, 2), (3, 4), (2, 3), (5, 2), (7, 2), (4, 4)):
-            _merton_own_draws_case(cuda_lib, cls, dict(lam=lam), l, M)
+            _merton_own_draws_case(cuda_lib, cls, dict(lam=lam), l, M, sampler=sampler)
 
 
-def test_philox_mode_equals_replay_of_its_own_draws_merton_random_parameters(cuda_lib):
+@pytest.mark.parametrize("sampler", ["f32bm", "f64bm"])
+def test_philox_mode_equals_replay_of_its_own_draws_merton_random_parameters(cuda_lib, sampler):
     """The same with every model parameter drawn at random - in particular T != 1, on which the step search,
     the block index of a jump and the end-of-path test of the three walks depend."""
     rng = np.random.default_rng(2718)
@@ -562,7 +568,7 @@ def test_philox_mode_equals_replay_of_its_own_draws_merton_random_parameters(cud
         cls = classes[it % 4]
         l, M = levels[it % len(levels)]
         _merton_own_draws_case(cuda_lib, cls, kw, l, M, n=300, off=int(rng.integers(0, 2 ** 40)), seed=int(rng.integers(0, 2 ** 31)),
-                               K=128)
+                               K=128, sampler=sampler)
 
 
 def test_merton_walks_agree_per_path(cuda_lib, tmp_path):

@@ -146,6 +146,38 @@ def test_antithetic_replay(golden, cuda_lib, c_oracle):
         mm.Lookback_GBM().payoff_replay(np.zeros((4, 4)), 2, 2, anti=True)
 
 
+def test_antithetic_replay_with_milstein_stepper(golden, cuda_lib):
+    """scheme="milstein" + anti=True (the reference composes them: diffusion_anti_path calls whatever self.sde is
+    bound to, :200-210; the demo notebook binds milstein_GBM): reference-order policy bit-exact, production 1e-12."""
+    n = 0
+    for c in anti_cases(golden["payoffs_anti_milstein"]):
+        p = oracle_params(c["cname"], c["kw_name"])
+        opt = getattr(mm, c["cname"])(scheme="milstein", **case_kwargs(c["cname"], c["kw_name"]))
+        Z = regen_Z(c)
+        Pf, Pc = opt.payoff_replay(Z, c["l"], c["M"], arith="exact", anti=True)
+        assert np.array_equal(Pf, c["Pf"]) and np.array_equal(Pc, c["Pc"]), (c["cname"], c["l"], c["M"])
+        Pf, Pc = opt.payoff_replay(Z, c["l"], c["M"], arith="fast", anti=True)
+        assert np.all(np.abs(Pf - c["Pf"]) <= payoff_tol(p, c["Pf"])) and np.all(np.abs(Pc - c["Pc"]) <= payoff_tol(p, c["Pc"]))
+        n += 1
+    assert n > 40
+
+
+def test_merton_replay_deep_levels(golden, cuda_lib):
+    """Reference fixtures at 128 and 256 fine steps (l = 7, 8 at M = 2; l = 4 at M = 4), both policies."""
+    n = 0
+    for c in merton_cases(golden["payoffs_merton_deep"]):
+        p = oracle_params(c["cname"], c["kw_name"])
+        for arith in ("exact", "fast"):
+            Pf, Pc = _opt(c["cname"], c["kw_name"]).payoff_replay(c["packed"], c["l"], c["M"], arith=arith)
+            if c["cname"] == "Digital_Merton":
+                assert np.array_equal(Pf, c["Pf"]) and np.array_equal(Pc, c["Pc"])
+            else:
+                assert np.all(np.abs(Pf - c["Pf"]) <= payoff_tol(p, c["Pf"])), (c["idx"], arith, np.abs(Pf - c["Pf"]).max())
+                assert np.all(np.abs(Pc - c["Pc"]) <= payoff_tol(p, c["Pc"])), (c["idx"], arith, np.abs(Pc - c["Pc"]).max())
+        n += 1
+    assert n == 20
+
+
 def test_milstein_replay(golden, cuda_lib):
     """scheme="milstein": GBM reference-order policy bit-exact, everything else within 1e-12."""
     g = golden["payoffs_milstein"]

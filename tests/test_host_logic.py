@@ -230,6 +230,7 @@ def test_flag_combinations_are_checked_before_the_device():
     t, b = C.c_int(), C.c_int()
     geo = lambda flags: lib.mlmcb_launch_geometry(0, 0, 4, flags, 0, C.byref(t), C.byref(b))
     assert geo(0x1000) == _lib.EINVAL
-    assert geo(_lib.FP32_PATHS | _lib.SAMPLER_F64BM) == _lib.ENOTIMPL          # fp32 paths: default sampler only
-    assert geo(_lib.MILSTEIN | _lib.ANTITHETIC) == _lib.ENOTIMPL
-    assert b"sampler" in lib.mlmcb_last_error() or b"Milstein" in lib.mlmcb_last_error()
+    assert geo(0xE) == _lib.EINVAL                                              # unknown sampler code
+    assert geo(_lib.FP32_PATHS | _lib.MILSTEIN) == _lib.ENOTIMPL               # Milstein: fp64 path arithmetic only
+    assert b"Milstein" in lib.mlmcb_last_error()
+    assert _lib.SAMPLER_F64BM == 0                                              # flags == 0 is the all-fp64 kernel

@@ -123,6 +123,42 @@ def test_oracles_antithetic_bit_exact(golden, c_oracle):
     assert "odd coarseness factor" in str(g["odd_M_message"])
 
 
+def test_oracles_antithetic_with_milstein_stepper(golden, c_oracle):
+    """anti_payoff with milstein_GBM bound over sde (diffusion_anti_path calls self.sde, :200-210)."""
+    g = golden["payoffs_anti_milstein"]
+    n = 0
+    for c in anti_cases(g):
+        _, pay = CLASS_CODES[c["cname"]]
+        p = oracle_params(c["cname"], c["kw_name"], scheme="milstein")
+        Z = regen_Z(c)
+        Pf, Pc = O.anti_level_payoffs(p, pay, c["l"], c["M"], Z=Z.copy())
+        assert np.array_equal(Pf, c["Pf"]) and np.array_equal(np.asarray(Pc, dtype=float) * np.ones(c["n"]), c["Pc"])
+        Pf, Pc = c_oracle.gbm_anti_replay(p, pay, c["l"], c["M"], Z)
+        assert np.array_equal(Pf, c["Pf"]) and np.array_equal(Pc, c["Pc"]), c["idx"]
+        n += 1
+    assert n > 40
+    cname, l, M, Nl, Npl, seed = [str(x) for x in g["l0_meta"]]
+    np.random.seed(int(seed))
+    s = O.looper(O.Params(scheme="milstein"), O.GBM, CLASS_CODES[cname][1], int(Nl), int(l), int(M), Npl=int(Npl), anti=True)
+    assert np.array_equal(s, g["l0_sums"])
+
+
+def test_oracles_merton_deep_levels(golden, c_oracle):
+    """128 / 256 fine steps (l = 7, 8 at M = 2; l = 4 at M = 4): numpy restatement bit-exact, C port to libm's exp."""
+    n = 0
+    for c in merton_cases(golden["payoffs_merton_deep"]):
+        model, pay = CLASS_CODES[c["cname"]]
+        p = oracle_params(c["cname"], c["kw_name"])
+        Pf, Pc = O.level_payoffs(p, model, pay, c["l"], c["M"], n=c["n"], draws=O.ReplayDraws(c["packed"]))
+        assert np.array_equal(Pf, c["Pf"]), c["idx"]
+        assert np.array_equal(np.asarray(Pc, dtype=float) * np.ones(c["n"]), c["Pc"]), c["idx"]
+        Pf, Pc = c_oracle.merton_replay(p, pay, c["l"], c["M"], c["packed"])
+        np.testing.assert_allclose(Pf, c["Pf"], rtol=0, atol=2e-13 * p.X0)
+        np.testing.assert_allclose(Pc, c["Pc"], rtol=0, atol=2e-13 * p.X0)
+        n += 1
+    assert n == 20
+
+
 def test_oracles_milstein(golden, c_oracle):
     """The notebook's Milstein time-steppers bound over the reference's sde (ExampleUsages.ipynb cells 1, 6)."""
     g = golden["payoffs_milstein"]
