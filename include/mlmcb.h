@@ -160,7 +160,9 @@ int mlmcb_jump_probe(int sampler, uint64_t seed, int l, double lam, uint64_t pat
 /* Host-side Philox4x32-10 (same code the kernels use), for known-answer tests; no GPU needed. */
 void mlmcb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* Pipe micro-benchmarks used for the roofline denominators.  which: 0 DFMA, 1 DADD, 2 FFMA,
- * 3 IMAD.WIDE (mul.wide.u32+add), 4 LOP3, 5 MUFU.LG2, 6 I2F.U32, 7 F2F.F64.F32, 8 MUFU.SIN.
+ * 3 IMAD.WIDE (mul.wide.u32+add), 4 LOP3, 5 MUFU.LG2, 6 I2F.U32, 7 F2F.F64.F32, 8 MUFU.SIN; two-instruction
+ * mixes on independent chains: 9 DFMA+LOP3, 10 DFMA+IMAD.WIDE, 11 IMAD.WIDE+LOP3, 12 FFMA+LOP3, 13 DFMA+FFMA,
+ * 14 DFMA+IMAD (the table behind "an INT32 instruction holds the dispatch port two cycles").
  * Returns warp-level instructions per second per GPU in *inst_per_s and the elapsed ms.      */
 int mlmcb_pipe_probe(int which, int device, double* inst_per_s, float* ms);
 /* Steps/sec the kernel's launch geometry: threads per block and resident blocks used.       */

@@ -875,6 +875,26 @@ __global__ void __launch_bounds__(256) pipe_probe_kernel(float seed, unsigned* s
                 else if (WHICH == 6) asm volatile("cvt.rn.f32.u32 %0, %1;" : "=f"(f[c]) : "r"(__float_as_uint(f[c])));
                 else if (WHICH == 7) asm volatile("{ .reg .f64 t; cvt.f64.f32 t, %0; cvt.rn.f32.f64 %0, t; }" : "+f"(f[c]));
                 else if (WHICH == 8) asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(f[c]));
+                // two-instruction mixes (independent chains): what a pair costs when both kinds are in flight
+                else if (WHICH == 9) {       // DFMA + LOP3
+                    d[c] = fma(d[c], da, db);
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[c]) : "r"(tid), "r"(0x9E3779B9u + it));
+                } else if (WHICH == 10) {    // DFMA + IMAD.WIDE
+                    d[c] = fma(d[c], da, db);
+                    asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"((unsigned)w[c]), "r"(0xD2511F53u));
+                } else if (WHICH == 11) {    // IMAD.WIDE + LOP3
+                    asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"((unsigned)w[c]), "r"(0xD2511F53u));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[c]) : "r"(tid), "r"(0x9E3779B9u + it));
+                } else if (WHICH == 12) {    // FFMA + LOP3
+                    f[c] = fmaf(f[c], fa, fb);
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[c]) : "r"(tid), "r"(0x9E3779B9u + it));
+                } else if (WHICH == 13) {    // DFMA + FFMA
+                    d[c] = fma(d[c], da, db);
+                    f[c] = fmaf(f[c], fa, fb);
+                } else if (WHICH == 14) {    // IMAD (32-bit multiply-add, not wide) + DFMA
+                    d[c] = fma(d[c], da, db);
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(u[c]) : "r"(0x9E3779B1u), "r"(tid));
+                }
             }
         }
     }
@@ -896,6 +916,12 @@ ProbeKernel probe_of(int which) {
     case 6: return pipe_probe_kernel<6>;
     case 7: return pipe_probe_kernel<7>;
     case 8: return pipe_probe_kernel<8>;
+    case 9: return pipe_probe_kernel<9>;
+    case 10: return pipe_probe_kernel<10>;
+    case 11: return pipe_probe_kernel<11>;
+    case 12: return pipe_probe_kernel<12>;
+    case 13: return pipe_probe_kernel<13>;
+    case 14: return pipe_probe_kernel<14>;
     default: return nullptr;
     }
 }
@@ -909,23 +935,30 @@ extern "C" int mlmcb_pipe_probe(int which, int device, double* inst_per_s, float
     if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
     DeviceInfo* d;
     if (int rc = device_info(device, &d)) return rc;
-    unsigned* sink;
-    CU(cudaMalloc((void**)&sink, 4));
-    const int grid = d->sms * 8, threads = 256;
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
-    k<<<grid, threads>>>(1e-7f, sink);   // warm-up
-    CU(cudaEventRecord(e0));
-    k<<<grid, threads>>>(1e-7f, sink);
-    CU(cudaEventRecord(e1));
-    CU(cudaEventSynchronize(e1));
+    unsigned* sink = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     float ms = 0;
-    CU(cudaEventElapsedTime(&ms, e0, e1));
-    CU(cudaGetLastError());
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
-    // F2F probe issues two conversions per chain step
-    const double per_step = which == 7 ? 2.0 : 1.0;
+    const int grid = d->sms * 8, threads = 256;
+    cudaError_t e = cudaMalloc((void**)&sink, 4);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) {
+        k<<<grid, threads>>>(1e-7f, sink);   // warm-up
+        e = cudaEventRecord(e0);
+    }
+    if (e == cudaSuccess) {
+        k<<<grid, threads>>>(1e-7f, sink);
+        e = cudaEventRecord(e1);
+    }
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (sink) cudaFree(sink);
+    if (e != cudaSuccess) return fail(MLMCB_ECUDA, "pipe probe failed: %s", cudaGetErrorString(e));
+    // F2F probe issues two conversions per chain step, the mixes two instructions
+    const double per_step = (which == 7 || which >= 9) ? 2.0 : 1.0;
     const double warp_insts = (double)grid * (threads / 32) * kProbeIters * kProbeUnroll * kProbeChains * per_step;
     if (inst_per_s) *inst_per_s = warp_insts / (ms * 1e-3);
     if (ms_out) *ms_out = ms;
