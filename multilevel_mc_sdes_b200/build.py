@@ -35,25 +35,31 @@ def is_stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def compile_lib(out, extra=(), verbose=False):
-    """nvcc -c every source (in parallel), then link them into the shared library `out`."""
+def compile_lib(out, extra=(), verbose=False, only=None):
+    """nvcc -c every unit (in parallel), then link them into the shared library `out`.
+    `only`: object names (e.g. ["family0_s1.o"]) to compile with `extra`; the other objects are taken from the
+    main build's object directory (csrc/libmlmcb.so.obj) - how a kernel experiment rebuilds one family in seconds."""
     objdir = out + ".obj"
     os.makedirs(objdir, exist_ok=True)
-    flags = NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else [])
-    procs = []
+    main_objdir = LIB + ".obj"
+    flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    procs, objs = [], []
     for src, objname, defs in UNITS:
         obj = os.path.join(objdir, objname)
-        procs.append((obj, subprocess.Popen([nvcc_path()] + flags + defs + ["-c", "-o", obj, src], cwd=CSRC,
+        if only is not None and objname not in only:
+            objs.append(os.path.join(main_objdir, objname))
+            continue
+        objs.append(obj)
+        procs.append((obj, subprocess.Popen([nvcc_path()] + flags + list(extra) + defs + ["-c", "-o", obj, src], cwd=CSRC,
                                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log, ok = "", True
     for obj, p in procs:
         log += p.communicate()[0]
         ok = ok and p.returncode == 0
     if ok:
-        r = subprocess.run([nvcc_path(), "-shared", "-o", out] + [o for o, _ in procs], cwd=CSRC, capture_output=True, text=True)
+        r = subprocess.run([nvcc_path(), "-shared", "-o", out] + objs, cwd=CSRC, capture_output=True, text=True)
         log += r.stdout + r.stderr
         ok = r.returncode == 0
-    shutil.rmtree(objdir, ignore_errors=True)
     if not ok:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building " + os.path.basename(out))

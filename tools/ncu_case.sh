@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: exp/ncu_case.sh <tag> <kernel-regex> <time_lib args...>
+# usage: tools/ncu_case.sh <tag> <kernel-regex> <time_lib args...>
 tag=$1; kr=$2; shift 2
 python tools/time_lib.py "$@" --reps 1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:$kr -c 1 -f -o gpurun_out/$tag python tools/time_lib.py "$@" --reps 1 > gpurun_out/ncu_$tag.log 2>&1
