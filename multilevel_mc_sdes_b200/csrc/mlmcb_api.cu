@@ -133,16 +133,6 @@ int make_consts(const mlmcb_params* p, int model, int payoff, int l, int M, ull 
     C->poly_q4 = MLMCB_Q4; C->poly_c4 = MLMCB_C4;
     C->inv_blk_dt = 1.0 / (4.0 * C->dt);
     C->run_blocks = run_blocks_for(C->nsteps);
-    // fp64 sampler: sin(pi h)/h and cos(pi h) in h^2 (tools/gen_trig_poly.py), fdlibm log coefficients
-    static const double dq[9] = {0x1.921fb54442d18p+1, -0x1.4abbce625be52p+2, 0x1.466bc6775aa7dp+1, -0x1.32d2cce627c86p-1,
-                                 0x1.5078348551854p-4, -0x1.e3074dfaf87afp-8, 0x1.e8f3675ee37ddp-12, -0x1.6f7acdb8f6580p-16,
-                                 0x1.9d462020fcc78p-21};
-    static const double dc[9] = {1.0, -0x1.3bd3cc9be45dbp+2, 0x1.03c1f081b5992p+2, -0x1.55d3c7e3bfbf5p+0, 0x1.e1f506813a321p-3,
-                                 -0x1.a6d1efc8c38bep-6, 0x1.f9d254582ac30p-10, -0x1.b6957b54dd389p-14, 0x1.1678f9078a9b3p-18};
-    static const double lg[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
-                                 2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
-                                 1.479819860511658591e-01};
-    memcpy(C->dq, dq, sizeof dq); memcpy(C->dc, dc, sizeof dc); memcpy(C->lg, lg, sizeof lg);
     // table-driven fp64 Box-Muller (tools/gen_f64bm_tables.py): G(x) = x + x^2 Q(x); sin(pi d)/d and (cos(pi d) - 1)/d^2 in d^2
     static const double lq[5] = {0x1.0000000000000p-2, 0x1.55555555279e5p-4, 0x1.ffffffffafffbp-6, 0x1.999b07519179fp-7,
                                  0x1.5556955655562p-8};

@@ -29,9 +29,6 @@
 #ifndef MLMCB_MINBLOCKS
 #define MLMCB_MINBLOCKS 8           // GBM/f32bm kernels: cap at 64 registers -> 8 blocks of 128 threads per SM
 #endif
-#ifndef MLMCB_F64BM_LIBDEVICE
-#define MLMCB_F64BM_LIBDEVICE 0     // 1: the first-cut canonical sampler on CUDA's log/sqrt/sincospi
-#endif
 #ifndef MLMCB_MINBLOCKS_MJD
 #define MLMCB_MINBLOCKS_MJD 6
 #endif
@@ -48,13 +45,14 @@
 #define MLMCB_UNROLL_MJD 2
 #endif
 #ifndef MLMCB_MINBLOCKS_F64
-#define MLMCB_MINBLOCKS_F64 6       // fp64-sampler kernels: <= 80 registers -> 6 blocks of 128 threads per SM
+#define MLMCB_MINBLOCKS_F64 4       // fp64-sampler GBM kernels: eight step factors and three Philox blocks in flight want ~126
+                                    // registers; 4 to 6 blocks per SM time the same (profiles/r02_f64bm_variants.txt)
+#endif
+#ifndef MLMCB_UNROLL_F64
+#define MLMCB_UNROLL_F64 1          // fp64 sampler: draw blocks (two Philox calls, four normals) in flight per thread
 #endif
 #ifndef MLMCB_MINBLOCKS_F64_MJD
 #define MLMCB_MINBLOCKS_F64_MJD 4   // Merton kernels with the fp64 sampler: <= 128 registers
-#endif
-#ifndef MLMCB_F64BM_TABLES
-#define MLMCB_F64BM_TABLES 1        // 0: the round-1 table-free fp64 Box-Muller (fdlibm log, degree-8 sin/cos) for A/B runs
 #endif
 #ifndef MLMCB_PHILOX_ROUNDS
 #define MLMCB_PHILOX_ROUNDS 10      // experiments only; the shipped library is Philox4x32-10
@@ -103,7 +101,7 @@ struct LevelConsts {
     double sig2, half_sig2, a_fm, a_cm, c_mil;
     float poly_q4, poly_c4;         // leading sin/cos coefficients as uniform operands (no per-block MOV)
     // fp64 sampler constants, read straight from the constant bank by DFMA (no 64-bit immediates exist)
-    double dq[9], dc[9], lg[7], ln2_hi, ln2_lo;
+    double ln2_hi, ln2_lo;
     double lq[5], neg2ln2, ts[3], tc[2];   // table-driven fp64 Box-Muller (tools/gen_f64bm_tables.py)
     uint32_t one_hi;                // 0x3ff00000 as a run-time value: (x & mask) | one_hi then is ONE LOP3 (register operand)
     double ex[12];                  // 1/k!, k = 2..13 (exp_bounded)
@@ -220,20 +218,29 @@ __device__ __forceinline__ void bm_quad_f32(const LevelConsts& C, U4 w, float z[
 #endif
 }
 
-__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {   // (0,1), 53 random bits
-    ull v = ((ull)hi << 21) | (ull)(lo >> 11);
-    return ((double)v + 0.5) * 0x1p-53;
-}
+// ---- the fp64 Box-Muller sampler (`f64bm`, the default) --------------------------------------------
+// One pair of N(0,1) from THREE Philox words (a, b, c):
+//   radius  u = ((a & 0xFFFFF)*2^32 + b + 1/2) * 2^-52 in (0,1): 52 random bits; r = sqrt(-2 ln u), tail to 8.57 sigma
+//   angle   theta = pi*h, h = h_j + d in [-1/2,1/2): j = bits 30..23 of a (h_j = (j + 1/2)/256 - 1/2),
+//           d = c*2^-40 - 2^-9 (32 bits), and bit 31 of a picks the half-plane (sign of r): 41 angle bits
+//   (z0, z1) = (r cos theta, r sin theta)
+// so three Philox4x32-10 blocks give four pairs = eight normals.  All arithmetic is fp64, about 1 ulp:
+//   -2 ln u = k(-2 ln2) + B_i + G(x),  u = 2^k m,  x = fma(m, A_i, 2) = -2(m/c_i - 1), G(x) = x + x^2 Q(x), |x| <= 2^-7,
+//             128-entry table (A_i, B_i); the interval that holds m = 1 is centred on it (c = 1, A = -2, B = 0), so
+//             x is exact there and u -> 1 keeps full relative accuracy;
+//   sqrt      reciprocal-root seed (MUFU.RSQ64H) and two residual corrections;
+//   sin/cos   256-entry table (cos, sin)(pi h_j), the remainder pi*d by three-/two-term polynomials, one rotation.
+// 30 FP64-pipe instructions per pair (the round-1 table-free form - fdlibm log, degree-8 sin/cos - took 53).  The two
+// tables (6 KB) are copied to shared memory by every kernel that draws fp64 normals.  tools/gen_f64bm_tables.py
+// generates tables and coefficients and checks the pair against 60-digit values (worst |z - exact| 1.3e-15 at
+// |z| = 8.6); tests/test_gpu_philox.py recomputes the device stream from the Philox words in numpy float64.
 
-// ---- canonical fp64 Box-Muller, hand-scheduled for B200's dispatch costs -------------------
-// All transcendental work is FP64-pipe instructions (1 dispatch cycle each) seeded by one MUFU
-// each; integer work is kept to the few bit operations that build the uniforms and split the
-// exponent.  Accuracy: |error| < 4e-16 absolute on each normal (tests/test_gpu_philox.py checks
-// the stream against a float64 recomputation from the same Philox words).
-
-// (0,1) uniform from 52 random bits (low 20 of `hi`, all of `lo`) plus a half-ulp offset.
-__device__ __forceinline__ double u52(uint32_t hi, uint32_t lo) {
-    return __hiloint2double((int)((hi & 0x000FFFFFu) | 0x3FF00000u), (int)lo) - (1.0 - 0x1p-53);
+// (x & MASK) | c in one LOP3: MASK is the instruction's immediate, c must come from a register
+template <uint32_t MASK>
+__device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "n"(MASK), "r"(c));
+    return r;
 }
 __device__ __forceinline__ double rcp64_seed(double x) {
     double y;
@@ -245,38 +252,86 @@ __device__ __forceinline__ double rsqrt64_seed(double x) {
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));      // MUFU.RSQ64H, ~2^-22
     return y;
 }
-// -2*ln(u) for a normal double u in (0,1): fdlibm's log (Sun, e_log.c) with the division done
-// by a reciprocal seed and two Newton steps.  Relative error < 2e-16.
-__device__ __forceinline__ double neg2_log(const LevelConsts& C, double u) {
-    const int ix = __double2hiint(u) + 0x00095F62;               // 0x3ff00000 - 0x3fe6a09e
-    const int k = (ix >> 20) - 0x3ff;
-    const double m = __hiloint2double((ix & 0x000fffff) + 0x3fe6a09e, __double2loint(u));   // [sqrt(1/2), sqrt(2))
-    const double f = m - 1.0, g = m + 1.0;
-    double y = rcp64_seed(g);
-    y = fma(y, fma(-g, y, 1.0), y);
-    y = fma(y, fma(-g, y, 1.0), y);
-    const double s = f * y;                                      // y is 1/g to ~1 ulp: no refinement needed
-    const double z = s * s;
-    double R = fma(z, C.lg[6], C.lg[5]);
-    R = fma(R, z, C.lg[4]);
-    R = fma(R, z, C.lg[3]);
-    R = fma(R, z, C.lg[2]);
-    R = fma(R, z, C.lg[1]);
-    R = fma(R, z, C.lg[0]);
-    R *= z;
-    const double hfsq = 0.5 * f * f, dk = (double)k;
-    // ln u = k*ln2_hi - ((hfsq - (s*(hfsq+R) + k*ln2_lo)) - f)
-    const double lg = fma(dk, C.ln2_hi, f - (hfsq - fma(s, hfsq + R, dk * C.ln2_lo)));
-    return -2.0 * lg;
+struct F64TabSrc { double2 lg[128]; double2 tr[256]; };
+static __device__ const F64TabSrc g_f64tab = {
+#include "mlmcb_f64tab.inc"
+};
+// In shared memory the 4 KB table comes first and the block is 4 KB-aligned: both tables then sit on a multiple of
+// their own size, and "base + masked byte offset" is "base | masked offset" - folded into the LOP3 that masks.
+struct F64Tab { double2 tr[256]; double2 lg[128]; };
+__device__ __forceinline__ F64Tab& f64tab() {
+    __shared__ __align__(4096) F64Tab t;
+    return t;
 }
-// sqrt(s), s in [2e-16, 74]: reciprocal-root seed (2^-22), one coupled Newton (Goldschmidt) step
-// (2^-44) and one residual correction g + (s - g*g)*h, which squares the error again.  <= 1 ulp.
+__device__ __forceinline__ uint32_t f64tab_tr() { return (uint32_t)__cvta_generic_to_shared(f64tab().tr); }
+__device__ __forceinline__ uint32_t f64tab_lg() { return (uint32_t)__cvta_generic_to_shared(f64tab().lg); }
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+// every thread of the block, before the first fp64 draw
+template <int SAMP>
+__device__ __forceinline__ void sampler_init() {
+    if (SAMP == SAMP_F64BM) {
+        F64Tab& t = f64tab();
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) t.tr[i] = g_f64tab.tr[i];
+        for (int i = threadIdx.x; i < 128; i += blockDim.x) t.lg[i] = g_f64tab.lg[i];
+        __syncthreads();
+    }
+}
+// (0,1) uniform from 52 random bits (low 20 of `hi`, all of `lo`) plus a half-ulp offset
+__device__ __forceinline__ double u52(const LevelConsts& C, uint32_t hi, uint32_t lo) {
+    return __hiloint2double((int)and_or<0x000FFFFFu>(hi, C.one_hi), (int)lo) - (1.0 - 0x1p-53);
+}
+// -2 ln u for a normal double u in (0,1)
+__device__ __forceinline__ double neg2_log_u(const LevelConsts& C, double u) {
+    const int ix = __double2hiint(u);
+    const int tmp = ix - 0x3fe6b000;
+    const int k = tmp >> 20;
+    int mh;                                                                              // ix - (k << 20) as ONE IMAD
+    asm("mad.lo.s32 %0, %1, -1048576, %2;" : "=r"(mh) : "r"(k), "r"(ix));
+    const double m = __hiloint2double(mh, __double2loint(u));                            // [0.70898, 1.41797)
+    const double2 e = lds_f64x2(and_or<0x7f0u>((uint32_t)tmp >> 9, f64tab_lg()));                    // lg[(tmp >> 13) & 127]
+    const double x = fma(m, e.x, 2.0);
+    const double x2 = x * x;
+    double q = fma(x, C.lq[4], C.lq[3]);
+    q = fma(q, x, C.lq[2]);
+    q = fma(q, x, C.lq[1]);
+    q = fma(q, x, C.lq[0]);
+    const double t = fma((double)k, C.neg2ln2, e.y);
+    return t + fma(x2, q, x);
+}
+// sqrt(s), s > 0 normal: reciprocal-root seed y (2^-22), then two residual corrections g += (s - g*g)*(y/2); the
+// half-seed's own error only scales the correction, so the second pass lands at e*e1 ~ 2^-62 before the final rounding.
 __device__ __forceinline__ double sqrt_pos(double s) {
     const double y = rsqrt64_seed(s);
-    double g = s * y, h = 0.5 * y;
-    const double r = fma(-g, h, 0.5);
-    g = fma(g, r, g); h = fma(h, r, h);
-    return fma(fma(-g, g, s), h, g);
+    double g = s * y;
+    const double hy = 0.5 * y;
+    g = fma(fma(-g, g, s), hy, g);
+    return fma(fma(-g, g, s), hy, g);
+}
+// AFFINE = false: (z0, z1);  AFFINE = true: (a0 + b0*z0, a0 + b0*z1) - the Euler-Maruyama step factor, one multiply
+// per pair instead of one FMA per normal
+template <bool AFFINE>
+__device__ __forceinline__ void bm_pair_f64(const LevelConsts& C, uint32_t a, uint32_t b, uint32_t c, double& z0, double& z1,
+                                            double a0 = 0.0, double b0 = 1.0) {
+    double rad = sqrt_pos(neg2_log_u(C, u52(C, a, b)));
+    rad = __hiloint2double(__double2hiint(rad) | (int)(a & 0x80000000u), __double2loint(rad));
+    const double2 cs = lds_f64x2(and_or<0xff0u>(a >> 19, f64tab_tr()));        // tr[(a >> 23) & 255]
+    const double dl = fma(__uint2double_rn(c), 0x1p-40, -0x1p-9);              // d in [-2^-9, 2^-9), exact
+    const double D = dl * dl;
+    const double sd = fma(fma(D, C.ts[2], C.ts[1]), D, C.ts[0]) * dl;          // sin(pi d)
+    const double cm = fma(D, C.tc[1], C.tc[0]) * D;                             // cos(pi d) - 1
+    const double cc = fma(-cs.y, sd, fma(cs.x, cm, cs.x)), ss = fma(cs.x, sd, fma(cs.y, cm, cs.y));
+    if (AFFINE) {
+        const double br = b0 * rad;
+        z0 = fma(br, cc, a0);
+        z1 = fma(br, ss, a0);
+    } else {
+        z0 = rad * cc;
+        z1 = rad * ss;
+    }
 }
 
 // max(x, 0) by masking with the sign: one shift and two logic operations.  (fp64 fmax - which is also what
@@ -305,122 +360,6 @@ __device__ __forceinline__ double exp_bounded(const LevelConsts& C, double x) {
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
-// sin(pi h)/h and cos(pi h) on |h| <= 1/2 as degree-8 polynomials in h^2 (tools/gen_trig_poly.py,
-// max abs error 3e-17 / 1e-16 including coefficient rounding)
-__device__ __forceinline__ void sincos_half(const LevelConsts& C, double h, double& sn_over_h, double& cs) {
-    const double T = h * h;
-    double q = fma(T, C.dq[8], C.dq[7]), c = fma(T, C.dc[8], C.dc[7]);
-#pragma unroll
-    for (int i = 6; i >= 0; --i) { q = fma(q, T, C.dq[i]); c = fma(c, T, C.dc[i]); }
-    sn_over_h = q; cs = c;
-}
-
-// ---- table-driven form of the same pair (MLMCB_F64BM_TABLES, the shipped one) -------------------
-// The stream is unchanged (same words -> same normals to ~1 ulp); what changes is the instruction
-// count: 29 FP64-pipe instructions per pair instead of 53.  Two tables (6 KB) sit in shared memory:
-//   lg[128]  -2 ln u = k(-2 ln2) + B_i + G(x),  u = 2^k m,  x = fma(m, A_i, 2) = -2(m/c_i - 1),
-//            G(x) = x + x^2 Q(x), |x| <= 2^-7.  The interval that holds m = 1 is centred on it
-//            (c = 1, A = -2, B = 0): x is exact there, so u -> 1 keeps full relative accuracy.
-//   tr[256]  (cos, sin)(pi h_j), h_j = (j + 1/2)/256 - 1/2; the remaining angle pi*d, |d| <= 2^-9,
-//            by three-/two-term polynomials and one rotation.
-// tools/gen_f64bm_tables.py generates tables and coefficients and checks the pair against 60-digit
-// values (worst |z - exact| 1.3e-15 at |z| = 8.6, i.e. <= 1 ulp).
-// (x & MASK) | c in one LOP3: MASK is the instruction's immediate, c must come from a register
-template <uint32_t MASK>
-__device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t c) {
-    uint32_t r;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "n"(MASK), "r"(c));
-    return r;
-}
-struct F64Tab { double2 lg[128]; double2 tr[256]; };
-static __device__ const F64Tab g_f64tab = {
-#include "mlmcb_f64tab.inc"
-};
-__device__ __forceinline__ F64Tab& f64tab() {
-    __shared__ F64Tab t;
-    return t;
-}
-// every thread of the block, before the first fp64 draw
-template <int SAMP>
-__device__ __forceinline__ void sampler_init() {
-#if MLMCB_F64BM_TABLES
-    if (SAMP == SAMP_F64BM) {
-        const double2* src = reinterpret_cast<const double2*>(&g_f64tab);
-        double2* dst = reinterpret_cast<double2*>(&f64tab());
-        for (int i = threadIdx.x; i < (int)(sizeof(F64Tab) / sizeof(double2)); i += blockDim.x) dst[i] = src[i];
-        __syncthreads();
-    }
-#endif
-}
-__device__ __forceinline__ double neg2_log_tab(const LevelConsts& C, double u) {
-    const int ix = __double2hiint(u);
-    const int tmp = ix - 0x3fe6b000;
-    const int k = tmp >> 20;
-    int mh;                                                                              // ix - (k << 20) as ONE IMAD
-    asm("mad.lo.s32 %0, %1, -1048576, %2;" : "=r"(mh) : "r"(k), "r"(ix));
-    const double m = __hiloint2double(mh, __double2loint(u));                            // [0.70898, 1.41797)
-    const double2 e = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(f64tab().lg) + ((tmp >> 9) & 0x7f0));
-    const double x = fma(m, e.x, 2.0);
-    const double x2 = x * x;
-    double q = fma(x, C.lq[4], C.lq[3]);
-    q = fma(q, x, C.lq[2]);
-    q = fma(q, x, C.lq[1]);
-    q = fma(q, x, C.lq[0]);
-    const double t = fma((double)k, C.neg2ln2, e.y);
-    return t + fma(x2, q, x);
-}
-// sqrt(s): reciprocal-root seed y (2^-22), then two residual corrections g += (s - g*g)*(y/2); the half-seed's own
-// error only scales the correction, so the second pass lands at e*e1 ~ 2^-62 before the final rounding.
-__device__ __forceinline__ double sqrt_pos2(double s) {
-    const double y = rsqrt64_seed(s);
-    double g = s * y;
-    const double hy = 0.5 * y;
-    g = fma(fma(-g, g, s), hy, g);
-    return fma(fma(-g, g, s), hy, g);
-}
-__device__ __forceinline__ void bm_pair_f64_tab(const LevelConsts& C, uint32_t a, uint32_t b, uint32_t c, uint32_t d, double& z0, double& z1) {
-    const double u = __hiloint2double((int)and_or<0x000FFFFFu>(a, C.one_hi), (int)b) - (1.0 - 0x1p-53);    // u52(a, b)
-    double rad = sqrt_pos2(neg2_log_tab(C, u));
-    rad = __hiloint2double(__double2hiint(rad) | (int)(c & 0x80000000u), __double2loint(rad));
-    const double2 cs = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(f64tab().tr) + ((c >> 8) & 0xff0));
-    const double dl = __hiloint2double((int)and_or<0x00000FFFu>(c, C.one_hi), (int)d) - (1.0 + 0x1p-9);
-    const double D = dl * dl;
-    const double sd = fma(fma(D, C.ts[2], C.ts[1]), D, C.ts[0]) * dl;          // sin(pi d)
-    const double cm = fma(D, C.tc[1], C.tc[0]) * D;                             // cos(pi d) - 1
-    z0 = rad * fma(-cs.y, sd, fma(cs.x, cm, cs.x));
-    z1 = rad * fma(cs.x, sd, fma(cs.y, cm, cs.y));
-}
-
-__device__ __forceinline__ double neg2_log_u(const LevelConsts& C, double u) {
-#if MLMCB_F64BM_TABLES
-    return neg2_log_tab(C, u);
-#else
-    return neg2_log(C, u);
-#endif
-}
-
-// One Philox block (a,b,c,d) -> two N(0,1): radius from u52(a,b), angle pi*h with h = u52-like
-// from (c,d) shifted to [-1/2,1/2), half-plane from the top bit of c.
-__device__ __forceinline__ void bm_pair_f64(const LevelConsts& C, uint32_t a, uint32_t b, uint32_t c, uint32_t d, double& z0, double& z1) {
-#if MLMCB_F64BM_TABLES
-    bm_pair_f64_tab(C, a, b, c, d, z0, z1);
-#elif MLMCB_F64BM_LIBDEVICE
-    double rad = sqrt(-2.0 * log(u53(a, b)));
-    double sn, cs;
-    sincospi(2.0 * u53(c, d), &sn, &cs);
-    z0 = rad * cs;
-    z1 = rad * sn;
-#else
-    double rad = sqrt_pos(neg2_log(C, u52(a, b)));
-    rad = __hiloint2double(__double2hiint(rad) | (int)(c & 0x80000000u), __double2loint(rad));
-    const double h = __hiloint2double((int)((c & 0x000FFFFFu) | 0x3FF00000u), (int)d) - 1.5;
-    double q, cs;
-    sincos_half(C, h, q, cs);
-    z0 = rad * cs;
-    z1 = (rad * h) * q;
-#endif
-}
-
 template <typename R> __device__ __forceinline__ R fma_(R a, R b, R c);
 template <> __device__ __forceinline__ double fma_<double>(double a, double b, double c) { return fma(a, b, c); }
 template <> __device__ __forceinline__ float fma_<float>(float a, float b, float c) { return fmaf(a, b, c); }
@@ -429,9 +368,14 @@ template <> __device__ __forceinline__ double min_<double>(double a, double b) {
 template <> __device__ __forceinline__ float min_<float>(float a, float b) { return fminf(a, b); }
 
 // Four grid-step normals for (path, block b) = steps 4b+1 .. 4b+4.
+// fp32 sampler: draw block b is Philox block b (four words, four normals).  fp64 sampler: a pair takes three
+// words, so steps 8o+1 .. 8o+8 (an "octet") take Philox blocks 3o, 3o+1, 3o+2:
+//   pair 0 (x,y,z of 3o) | pair 1 (w of 3o; x,y of 3o+1) | pair 2 (z,w of 3o+1; x of 3o+2) | pair 3 (y,z,w of 3o+2)
+// load4(b) serves half an octet (o = b/2: two Philox calls), load8(o) a whole one (three calls).
 template <typename R, int SAMP>
 struct PhiloxSource {
-    static constexpr int kUnroll = SAMP == SAMP_F32BM ? MLMCB_UNROLL : 1;   // blocks in flight per thread
+    static constexpr int kUnroll = SAMP == SAMP_F32BM ? MLMCB_UNROLL : MLMCB_UNROLL_F64;   // draw blocks in flight per thread
+    static constexpr bool kOctets = SAMP == SAMP_F64BM;
     const LevelConsts& C;
     ull pid;
     __device__ __forceinline__ void load4(uint32_t b, R z[4]) const { load4_stream(STREAM_GRID, b, z); }
@@ -441,12 +385,27 @@ struct PhiloxSource {
             bm_quad_f32(C, philox_at(C, pid, kind, b), f);
             z[0] = (R)f[0]; z[1] = (R)f[1]; z[2] = (R)f[2]; z[3] = (R)f[3];
         } else {
-            U4 r = philox_at(C, pid, kind, 2 * b), s = philox_at(C, pid, kind, 2 * b + 1);
+            const uint32_t o3 = 3u * (b >> 1) + (b & 1u);
+            const U4 r = philox_at(C, pid, kind, o3), s = philox_at(C, pid, kind, o3 + 1u);
             double d0, d1, d2, d3;
-            bm_pair_f64(C, r.x, r.y, r.z, r.w, d0, d1);
-            bm_pair_f64(C, s.x, s.y, s.z, s.w, d2, d3);
+            if (b & 1u) {
+                bm_pair_f64<false>(C, r.z, r.w, s.x, d0, d1);
+                bm_pair_f64<false>(C, s.y, s.z, s.w, d2, d3);
+            } else {
+                bm_pair_f64<false>(C, r.x, r.y, r.z, d0, d1);
+                bm_pair_f64<false>(C, r.w, s.x, s.y, d2, d3);
+            }
             z[0] = (R)d0; z[1] = (R)d1; z[2] = (R)d2; z[3] = (R)d3;
         }
+    }
+    // the octet o as Euler-Maruyama step factors t_i = a0 + b0*z_i (fp64 sampler, fp64 paths)
+    __device__ __forceinline__ void load8_affine(uint32_t o, double t[8], double a0, double b0) const {
+        const U4 r = philox_at(C, pid, STREAM_GRID, 3u * o), s = philox_at(C, pid, STREAM_GRID, 3u * o + 1u),
+                 u = philox_at(C, pid, STREAM_GRID, 3u * o + 2u);
+        bm_pair_f64<true>(C, r.x, r.y, r.z, t[0], t[1], a0, b0);
+        bm_pair_f64<true>(C, r.w, s.x, s.y, t[2], t[3], a0, b0);
+        bm_pair_f64<true>(C, s.z, s.w, u.x, t[4], t[5], a0, b0);
+        bm_pair_f64<true>(C, u.y, u.z, u.w, t[6], t[7], a0, b0);
     }
 };
 
@@ -454,6 +413,7 @@ struct PhiloxSource {
 template <typename R>
 struct PackedSource {
     static constexpr int kUnroll = 1;
+    static constexpr bool kOctets = false;
     R z[4];
     int base;
     __device__ __forceinline__ void load4(uint32_t, R out[4]) const {   // two steps per path: base is 0 or 2
@@ -466,6 +426,7 @@ struct PackedSource {
 // Replayed normals, step-major Z[step*n + path] (MLMC_RSCAM.py:343 call order).
 struct ReplaySource {
     static constexpr int kUnroll = 1;
+    static constexpr bool kOctets = false;
     const double* Z;
     ull n, i, nsteps;
     __device__ __forceinline__ void load4(uint32_t b, double z[4]) const {
@@ -610,6 +571,43 @@ struct StepCoef {
 template <typename R, int FN, int MT, int SCH, typename Source>
 __device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source& src,
                                               double& vf, double& vc, double& gf, double& gc) {
+    if constexpr (Source::kOctets && sizeof(R) == 8 && SCH == SCH_EM && (MT == 2 || MT == 4)) {
+        // fp64 sampler, Euler-Maruyama, M = 2 or 4: the draws arrive eight steps at a time (three Philox blocks) and
+        // already as step factors t_i = a + b z_i, so a fine step is ONE fma and - because the coarse drift is M times
+        // the fine one - the coarse factor a_c + b*sum(z) is just the sum of its fine factors.
+        if ((C.nsteps & 7) == 0) {
+            double Xf = C.X0, Xc = C.X0;
+            double Ff = FN == FN_MIN ? C.X0 : 0.0, Fc = Ff;
+            const uint32_t noct = (uint32_t)(C.nsteps >> 3);
+#pragma unroll Source::kUnroll
+            for (uint32_t o = 0; o < noct; ++o) {
+                double t[8];
+                src.load8_affine(o, t, C.a_f, C.b_f);
+#pragma unroll
+                for (int g = 0; g < 8; g += MT) {
+                    const double tc = MT == 4 ? (t[g] + t[g + 1]) + (t[g + 2] + t[g + 3]) : t[g] + t[g + 1];
+#pragma unroll
+                    for (int k = 0; k < MT; ++k) {
+                        Xf = fma(Xf, t[g + k], Xf);
+                        if (FN == FN_AVG) Ff += Xf;
+                        if (FN == FN_MIN) Ff = min_<double>(Ff, Xf);
+                    }
+                    Xc = fma(Xc, tc, Xc);
+                    if (FN == FN_AVG) Fc += Xc;
+                    if (FN == FN_MIN) Fc = min_<double>(Fc, Xc);
+                }
+            }
+            if (FN == FN_AVG) {
+                const double h0 = 0.5 * C.X0;
+                vf = C.avg_wf * (Ff + fma(-0.5, Xf, h0));
+                vc = C.avg_wc * (Fc + fma(-0.5, Xc, h0));
+                gf = gc = 0.0;
+            } else {
+                vf = Xf; vc = Xc; gf = Ff; gc = Fc;
+            }
+            return;
+        }
+    }
     const StepCoef<R, SCH> co(C);
     R Xf = (R)C.X0, Xc = (R)C.X0, sz = (R)0;
     R Ff = FN == FN_MIN ? (R)C.X0 : (R)0, Fc = Ff;
@@ -1018,10 +1016,11 @@ __device__ __forceinline__ void jump_draws(const LevelConsts& C, ull pid, uint32
         bm_pair_f32(C.poly_q4, C.poly_c4, r.z, r.w, a, b);
         zq = (R)a; zw = (R)b;
     } else {
+        // two Philox blocks per record: 52 bits for the gap, three words for the pair of normals
         U4 r = philox_at(C, pid, STREAM_JUMP, 2 * jk), s = philox_at(C, pid, STREAM_JUMP, 2 * jk + 1);
-        gap = neg2_log_u(C, u52(r.x, r.y)) * (0.5 * C.inv_lam);        // Exp(lam) inter-arrival time :454/:474
+        gap = neg2_log_u(C, u52(C, r.x, r.y)) * (0.5 * C.inv_lam);     // Exp(lam) inter-arrival time :454/:474
         double a, b;
-        bm_pair_f64(C, s.x, s.y, s.z, s.w, a, b);
+        bm_pair_f64<false>(C, s.x, s.y, s.z, a, b);
         zq = (R)a; zw = (R)b;
     }
 }

@@ -266,11 +266,12 @@ def test_milstein_level_moments(cuda_lib, c_oracle, cname):
 
 
 def test_f64bm_stream_matches_float64_recomputation(cuda_lib):
-    """The canonical sampler's normals recomputed on the host from the same Philox4x32-10 words
-    (counter layout of mlmcb_kernels.cuh: c0 = stream, c1 = call index, c2,c3 = path id | level<<16)
-    with numpy float64 log/sqrt/sin/cos: the hand-scheduled device math agrees to < 1e-14."""
+    """The fp64 sampler's normals recomputed on the host from the same Philox4x32-10 words (counter layout of
+    mlmcb_kernels.cuh: c0 = stream, c1 = Philox block index, c2,c3 = path id | level<<16; steps 8o+1..8o+8 take
+    blocks 3o..3o+2, three words per pair) with numpy float64 log/sqrt/sin/cos: the table-driven device math
+    agrees to < 1e-14."""
     import torch
-    seed, level, n_paths, n_steps, off = 987654321012345, 5, 64, 8, 7_000_000_123
+    seed, level, n_paths, n_steps, off = 987654321012345, 5, 64, 16, 7_000_000_123
     out = torch.empty(n_steps * n_paths, dtype=torch.float64, device="cuda")
     _lib.check(cuda_lib.mlmcb_sampler_probe(_lib.SAMPLER_F64BM, seed, level, off, n_paths, n_steps, 0, 0, out.data_ptr()))
     torch.cuda.synchronize()
@@ -279,14 +280,18 @@ def test_f64bm_stream_matches_float64_recomputation(cuda_lib):
     worst = 0.0
     for p in range(n_paths):
         pid = off + p
-        for call in range(n_steps // 2):
-            a, b, c, d = _lib.philox4x32_10((0, call, pid & 0xFFFFFFFF, ((pid >> 32) & 0xFFFF) | (level << 16)), key)
-            u = (((a & 0xFFFFF) << 32 | b) + 0.5) * 2.0 ** -52          # u52: 52 random bits + half-ulp offset
-            h = (((c & 0xFFFFF) << 32 | d)) * 2.0 ** -52 - 0.5
-            rad = np.sqrt(-2.0 * np.log(u)) * (-1.0 if c >> 31 else 1.0)
-            want = (rad * np.cos(np.pi * h), rad * np.sin(np.pi * h))
-            got = (z[2 * call, p], z[2 * call + 1, p])
-            worst = max(worst, abs(got[0] - want[0]), abs(got[1] - want[1]))
+        for o in range(n_steps // 8):
+            w = []
+            for blk in range(3):
+                w += _lib.philox4x32_10((0, 3 * o + blk, pid & 0xFFFFFFFF, ((pid >> 32) & 0xFFFF) | (level << 16)), key)
+            for q in range(4):
+                a, b, c = w[3 * q:3 * q + 3]
+                u = (((a & 0xFFFFF) << 32 | b) + 0.5) * 2.0 ** -52          # 52 random bits + half-ulp offset
+                h = (((a >> 23) & 0xFF) + c * 2.0 ** -32) / 256.0 - 0.5      # 8 + 32 angle bits
+                rad = np.sqrt(-2.0 * np.log(u)) * (-1.0 if a >> 31 else 1.0)
+                want = (rad * np.cos(np.pi * h), rad * np.sin(np.pi * h))
+                got = (z[8 * o + 2 * q, p], z[8 * o + 2 * q + 1, p])
+                worst = max(worst, abs(got[0] - want[0]), abs(got[1] - want[1]))
     assert worst < 1e-14, worst
 
 
