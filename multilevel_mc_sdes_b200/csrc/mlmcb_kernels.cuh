@@ -256,27 +256,33 @@ struct F64TabSrc { double2 lg[128]; double2 tr[256]; };
 static __device__ const F64TabSrc g_f64tab = {
 #include "mlmcb_f64tab.inc"
 };
-// In shared memory the 4 KB table comes first and the block is 4 KB-aligned: both tables then sit on a multiple of
-// their own size, and "base + masked byte offset" is "base | masked offset" - folded into the LOP3 that masks.
+// In shared memory the 4 KB table comes first and starts on a 4 KB boundary of the shared WINDOW: both tables then
+// sit on a multiple of their own size, and "base + masked byte offset" is "base | masked offset" - folded into the
+// LOP3 that masks.  The boundary is found at run time inside a buffer 4 KB larger than the tables (the first user
+// variable of a block sits 1 KB into the window on this architecture, so `__align__` alone does not give it).
 struct F64Tab { double2 tr[256]; double2 lg[128]; };
-__device__ __forceinline__ F64Tab& f64tab() {
-    __shared__ __align__(4096) F64Tab t;
-    return t;
+__device__ __forceinline__ uint32_t f64tab_tr() {
+    __shared__ __align__(16) unsigned char buf[sizeof(F64Tab) + 4096];
+    return ((uint32_t)__cvta_generic_to_shared(buf) + 4095u) & ~4095u;
 }
-__device__ __forceinline__ uint32_t f64tab_tr() { return (uint32_t)__cvta_generic_to_shared(f64tab().tr); }
-__device__ __forceinline__ uint32_t f64tab_lg() { return (uint32_t)__cvta_generic_to_shared(f64tab().lg); }
+__device__ __forceinline__ uint32_t f64tab_lg() { return f64tab_tr() + (uint32_t)sizeof(F64Tab::tr); }
+// volatile: the statement has no declared memory operand, and only `volatile` keeps the compiler from moving it
+// above the barrier that ends the table copy (an unordered asm was hoisted there and read garbage)
 __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
     double2 v;
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
+}
+__device__ __forceinline__ void sts_f64x2(uint32_t addr, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" : : "r"(addr), "d"(v.x), "d"(v.y) : "memory");
 }
 // every thread of the block, before the first fp64 draw
 template <int SAMP>
 __device__ __forceinline__ void sampler_init() {
     if (SAMP == SAMP_F64BM) {
-        F64Tab& t = f64tab();
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) t.tr[i] = g_f64tab.tr[i];
-        for (int i = threadIdx.x; i < 128; i += blockDim.x) t.lg[i] = g_f64tab.lg[i];
+        const uint32_t tr = f64tab_tr(), lg = f64tab_lg();
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) sts_f64x2(tr + 16u * i, g_f64tab.tr[i]);
+        for (int i = threadIdx.x; i < 128; i += blockDim.x) sts_f64x2(lg + 16u * i, g_f64tab.lg[i]);
         __syncthreads();
     }
 }
