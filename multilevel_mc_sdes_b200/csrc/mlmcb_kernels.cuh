@@ -45,11 +45,11 @@
 #define MLMCB_UNROLL_MJD 2
 #endif
 #ifndef MLMCB_MINBLOCKS_F64
-#define MLMCB_MINBLOCKS_F64 4       // fp64-sampler GBM kernels: eight step factors and three Philox blocks in flight want ~126
-                                    // registers; 4 to 6 blocks per SM time the same (profiles/r02_f64bm_variants.txt)
+#define MLMCB_MINBLOCKS_F64 2       // fp64-sampler GBM kernels: four octets in flight (236 registers) at two blocks per SM beat
+                                    // every higher-occupancy build (profiles/r02_f64bm_variants.txt: 66.4 vs 75.0 cycles per step)
 #endif
 #ifndef MLMCB_UNROLL_F64
-#define MLMCB_UNROLL_F64 1          // fp64 sampler: draw blocks (two Philox calls, four normals) in flight per thread
+#define MLMCB_UNROLL_F64 4          // fp64 sampler: octets (three Philox calls, eight step factors) in flight per thread
 #endif
 #ifndef MLMCB_MINBLOCKS_F64_MJD
 #define MLMCB_MINBLOCKS_F64_MJD 4   // Merton kernels with the fp64 sampler: <= 128 registers
@@ -1853,7 +1853,7 @@ struct SweepConsts {
 static_assert(sizeof(SweepConsts) <= 32764, "kernel parameters are limited to 32764 bytes");
 
 template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH>
-__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? (MODEL == 0 ? MLMCB_MINBLOCKS_F64 - 1 : MLMCB_MINBLOCKS_F64_MJD)
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? (MODEL == 0 ? MLMCB_MINBLOCKS_F64 : MLMCB_MINBLOCKS_F64_MJD)
                                                                 : (MODEL == 0 ? MLMCB_MINBLOCKS - 2 : MLMCB_MINBLOCKS_FLAT - 1))
 sweep_kernel(const __grid_constant__ SweepConsts S, double* partials, unsigned* ticket, double* out) {
     sampler_init<SAMP>();
