@@ -465,7 +465,7 @@ int sweep_fused(const mlmcb_params* p, int model, int payoff, int M, int n_level
     std::vector<int> order;
     for (int i = 0; i < n_levels; ++i) if (n_paths[i]) order.push_back(i);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return levels[a] > levels[b]; });
-    double cost[kSweepMax], total = 0.0;
+    double cost[kSweepMax], total = 0.0, total_long = 0.0;
     ull cap[kSweepMax];
     for (int j = 0; j < live; ++j) {
         const int i = order[j];
@@ -482,9 +482,14 @@ int sweep_fused(const mlmcb_params* p, int model, int payoff, int M, int n_level
         }
         cost[j] = (double)n_paths[i] * path_cost(model, f64, C->nsteps, model == MLMCB_MERTON ? p->lam * p->T : 0.0);
         total += cost[j];
+        if (C->nsteps >= 64) total_long += cost[j];
         const ull threads = (n_paths[i] + per_thread - 1) / per_thread + (per_thread > 1 ? 1 : 0);
         cap[j] = (threads + kThreads - 1) / kThreads;                   // more blocks than this would idle
     }
+    // A sweep that is mostly long paths and long enough for launch latency not to matter (a fixed-level sweep of
+    // Giles_plot, :1775-1777) is better served by each level's own kernel: the long-path build keeps four octets in
+    // flight, the sweep kernel is built for the short levels where mlmc puts its samples.
+    if (f64 && model == MLMCB_GBM && total_long > 0.5 * total && total / 32.0 > 5e-3 * 148 * 4 * 1.9e9) return 0;
     int grid0 = 0, resident = 0;
     if (int rc = geometry(k, device, ~0ull >> 16, &grid0, &resident)) return rc;
     const double budget = (double)(resident * 4 < kSweepRows - kSweepMax ? resident * 4 : kSweepRows - kSweepMax);   // four waves

@@ -48,6 +48,11 @@
 #define MLMCB_MINBLOCKS_F64 2       // fp64-sampler GBM kernels: four octets in flight (236 registers) at two blocks per SM beat
                                     // every higher-occupancy build (profiles/r02_f64bm_variants.txt: 66.4 vs 75.0 cycles per step)
 #endif
+#ifndef MLMCB_MINBLOCKS_F64_SHORT
+#define MLMCB_MINBLOCKS_F64_SHORT 5 // fp64-sampler GBM packed / four-step kernels and the sweep kernel (where those levels hold nearly
+                                    // all samples): one octet in flight, <= 96 registers.  (Measured: as a standalone kernel for 8..32
+                                    // steps this build is 4-18 % SLOWER than the four-octet one, so level calls never use it.)
+#endif
 #ifndef MLMCB_UNROLL_F64
 #define MLMCB_UNROLL_F64 4          // fp64 sampler: octets (three Philox calls, eight step factors) in flight per thread
 #endif
@@ -574,7 +579,7 @@ struct StepCoef {
 // Returns the path outputs the reference path function returns: terminal values (FN_FINAL),
 // averages (FN_AVG) or terminal values + minima (FN_MIN).
 // ------------------------------------------------------------------------------------------
-template <typename R, int FN, int MT, int SCH, typename Source>
+template <typename R, int FN, int MT, int SCH, typename Source, int UNROLL = Source::kUnroll>
 __device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source& src,
                                               double& vf, double& vc, double& gf, double& gc) {
     if constexpr (Source::kOctets && sizeof(R) == 8 && SCH == SCH_EM && (MT == 2 || MT == 4)) {
@@ -585,7 +590,7 @@ __device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source
             double Xf = C.X0, Xc = C.X0;
             double Ff = FN == FN_MIN ? C.X0 : 0.0, Fc = Ff;
             const uint32_t noct = (uint32_t)(C.nsteps >> 3);
-#pragma unroll Source::kUnroll
+#pragma unroll UNROLL
             for (uint32_t o = 0; o < noct; ++o) {
                 double t[8];
                 src.load8_affine(o, t, C.a_f, C.b_f);
@@ -645,7 +650,7 @@ __device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source
     }
 
     const uint32_t nblk = (uint32_t)(C.nsteps >> 2);
-#pragma unroll Source::kUnroll
+#pragma unroll UNROLL
     for (uint32_t b = 0; b < nblk; ++b) {
         R z[4];
         src.load4(b, z);
@@ -1791,7 +1796,7 @@ __device__ __forceinline__ void gbm_packed_body(const LevelConsts& C, unsigned b
 }
 
 template <typename R, int FN, int SAMP, int SCH, int NS>
-__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64 : MLMCB_MINBLOCKS)
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64_SHORT : MLMCB_MINBLOCKS)
 gbm_packed_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
                   double* out7, double* Pf_out, double* Pc_out) {
     sampler_init<SAMP>();
@@ -1802,7 +1807,8 @@ gbm_packed_kernel(const __grid_constant__ LevelConsts C, double* partials, unsig
 }
 
 
-template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH>
+// SHORT (fp64-sampler GBM only): the sweep kernel's build - one draw block in flight, fewer registers
+template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH, bool SHORT = false>
 __device__ __forceinline__ void level_body(const LevelConsts& C, unsigned bid, unsigned nblk, Sums7& acc,
                                            double* Pf_out, double* Pc_out) {
     const ull stride = (ull)nblk * blockDim.x;
@@ -1812,7 +1818,7 @@ __device__ __forceinline__ void level_body(const LevelConsts& C, unsigned bid, u
         double vf, vc, gf, gc;
         if (MODEL == 0) {
             PhiloxSource<R, SAMP> src{C, pid};
-            gbm_path_fast<R, FN, MT, SCH>(C, src, vf, vc, gf, gc);
+            gbm_path_fast<R, FN, MT, SCH, PhiloxSource<R, SAMP>, SHORT ? 1 : PhiloxSource<R, SAMP>::kUnroll>(C, src, vf, vc, gf, gc);
         } else {
             mjd_path_philox<R, FN, MT, SAMP, SCH>(C, pid, rec, vf, vc, gf, gc);
         }
@@ -1820,15 +1826,15 @@ __device__ __forceinline__ void level_body(const LevelConsts& C, unsigned bid, u
     }
 }
 
-template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH>
-__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? (MODEL == 0 ? MLMCB_MINBLOCKS_F64 : MLMCB_MINBLOCKS_F64_MJD)
+template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH, bool SHORT = false>
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? (MODEL == 0 ? (SHORT ? MLMCB_MINBLOCKS_F64_SHORT : MLMCB_MINBLOCKS_F64) : MLMCB_MINBLOCKS_F64_MJD)
                                                                 : (MODEL == 0 ? MLMCB_MINBLOCKS : MLMCB_MINBLOCKS_MJD))
 level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
              double* out7, double* Pf_out, double* Pc_out) {
     sampler_init<SAMP>();
     Sums7 acc;
     acc.clear();
-    level_body<R, MODEL, FN, MT, SAMP, SCH>(C, blockIdx.x, gridDim.x, acc, Pf_out, Pc_out);
+    level_body<R, MODEL, FN, MT, SAMP, SCH, SHORT>(C, blockIdx.x, gridDim.x, acc, Pf_out, Pc_out);
     grid_finish(acc, partials, ticket, out7);
 }
 
@@ -1853,7 +1859,7 @@ struct SweepConsts {
 static_assert(sizeof(SweepConsts) <= 32764, "kernel parameters are limited to 32764 bytes");
 
 template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH>
-__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? (MODEL == 0 ? MLMCB_MINBLOCKS_F64 : MLMCB_MINBLOCKS_F64_MJD)
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? (MODEL == 0 ? MLMCB_MINBLOCKS_F64_SHORT : MLMCB_MINBLOCKS_F64_MJD)
                                                                 : (MODEL == 0 ? MLMCB_MINBLOCKS - 2 : MLMCB_MINBLOCKS_FLAT - 1))
 sweep_kernel(const __grid_constant__ SweepConsts S, double* partials, unsigned* ticket, double* out) {
     sampler_init<SAMP>();
@@ -1867,7 +1873,7 @@ sweep_kernel(const __grid_constant__ SweepConsts S, double* partials, unsigned* 
         const int kind = S.kind[k];
         if (kind == SK_PACKED) gbm_packed_body<R, FN, SAMP, SCH, 0>(C, bid, nblk, acc, nullptr, nullptr);
         else if (MT != 0 && kind == SK_FOUR) gbm_packed_body<R, FN, SAMP, SCH, MT == 4 ? 4 : -4>(C, bid, nblk, acc, nullptr, nullptr);
-        else level_body<R, 0, FN, MT, SAMP, SCH>(C, bid, nblk, acc, nullptr, nullptr);
+        else level_body<R, 0, FN, MT, SAMP, SCH, true>(C, bid, nblk, acc, nullptr, nullptr);
     } else {
         if (S.kind[k] == SK_MJD_FLAT) mjd_flat_body<R, FN, MT, SAMP, SCH>(C, bid, nblk, acc, nullptr, nullptr);
         else level_body<R, 1, FN, MT, SAMP, SCH>(C, bid, nblk, acc, nullptr, nullptr);
