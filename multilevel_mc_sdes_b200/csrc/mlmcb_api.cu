@@ -187,7 +187,11 @@ LevelKernel pick_kernel(int model, int payoff, int M, int flags, ull nsteps) {
         if (packed) return f64 ? pick_gbm_packed_s<1>(fn, flags, packed) : pick_gbm_packed_s<0>(fn, flags, packed);
         return f64 ? pick_gbm_s<1>(fn, mt, flags) : pick_gbm_s<0>(fn, mt, flags);
     }
-    if (nsteps < flat_below()) return f64 ? pick_merton_flat_s<1>(fn, mt, flags) : pick_merton_flat_s<0>(fn, mt, flags);
+    if (nsteps < flat_below()) {
+        static const char* force = getenv("MLMCB_MJD_WALK");             // "batch" | "event": tuning and the walk-agreement test
+        const bool batch = force ? (force[0] == 'b' && nsteps > 1) : mjd_use_batch(f64 ? SAMP_F64BM : SAMP_F32BM, nsteps);
+        return f64 ? pick_merton_flat_s<1>(fn, mt, flags, batch) : pick_merton_flat_s<0>(fn, mt, flags, batch);
+    }
     return f64 ? pick_merton_uniform_s<1>(fn, mt, flags) : pick_merton_uniform_s<0>(fn, mt, flags);
 }
 

@@ -1,7 +1,7 @@
 // libmlmcb - the level kernels of ONE family and ONE sampler (see mlmcb_pick.cuh, mlmcb_kernels.cuh):
 //   MLMCB_TU_FAMILY 0  GBM: level_kernel<R, 0, ...>, gbm_packed_kernel, level_anti_kernel
 //                   1  Merton, block-uniform walk: level_kernel<R, 1, ...>
-//                   2  Merton, event-driven walk:  mjd_flat_kernel
+//                   2  Merton, short paths: mjd_flat_kernel (event-driven walk, l = 0 loop), mjd_batch_kernel (batch walk)
 //                   3  GBM, one launch per sweep:  sweep_kernel<double, 0, ...>
 //                   4  Merton, one launch per sweep: sweep_kernel<double, 1, ...>
 //   MLMCB_TU_SAMP   0  f32bm, 1 f64bm
@@ -39,6 +39,10 @@ struct MertonFlat {
     template <typename R, int FN, int MT, int SAMP, int SCH>
     static LevelKernel get() { return mjd_flat_kernel<R, FN, MT, SAMP, SCH>; }
 };
+struct MertonBatch {
+    template <typename R, int FN, int MT, int SAMP, int SCH>
+    static LevelKernel get() { return mjd_batch_kernel<R, FN, MT, SAMP, SCH>; }
+};
 #endif
 }  // namespace
 
@@ -54,7 +58,9 @@ template <> LevelKernel pick_gbm_anti_s<S>(int fn, int mt, int flags) { return p
 #elif MLMCB_TU_FAMILY == 1
 template <> LevelKernel pick_merton_uniform_s<S>(int fn, int mt, int flags) { return pick_family<MertonUniform, S>(fn, mt, flags); }
 #elif MLMCB_TU_FAMILY == 2
-template <> LevelKernel pick_merton_flat_s<S>(int fn, int mt, int flags) { return pick_family<MertonFlat, S>(fn, mt, flags); }
+template <> LevelKernel pick_merton_flat_s<S>(int fn, int mt, int flags, bool batch) {
+    return batch ? pick_family<MertonBatch, S>(fn, mt, flags) : pick_family<MertonFlat, S>(fn, mt, flags);
+}
 #elif MLMCB_TU_FAMILY == 3
 template <> SweepKernel pick_gbm_sweep_s<S>(int fn, int mt, int flags) { return pick_sweep<0, S>(fn, mt, flags); }
 #else

@@ -1014,6 +1014,35 @@ struct JD {
 
 // Jump-stream draws for jump number jk of a path: inter-arrival time, jump-size normal and the
 // Brownian normal of the adaptive step that ends at that jump.
+// (the two halves separately: the batch walk draws the arrival times of a whole warp first and the normals only
+// for arrivals that fall inside the path; same words, same values)
+template <int SAMP>
+__device__ __forceinline__ double jump_gap(const LevelConsts& C, ull pid, uint32_t jk) {
+    if (SAMP == SAMP_F32BM) {
+        const U4 r = philox_at(C, pid, STREAM_JUMP, jk);
+        const float u = fminf(fmaf(__uint2float_rn(r.x), 0x1p-32f, 0x1p-33f), 0x1.fffffep-1f);
+        return (double)(lg2_approx(u) * -0.693147180559945309f) * C.inv_lam;
+    } else {
+        const U4 r = philox_at(C, pid, STREAM_JUMP, 2 * jk);
+        return neg2_log_u(C, u52(C, r.x, r.y)) * (0.5 * C.inv_lam);
+    }
+}
+template <typename R, int SAMP>
+__device__ __forceinline__ void jump_normals(const LevelConsts& C, ull pid, uint32_t jk, R& zq, R& zw) {
+    if (SAMP == SAMP_F32BM) {
+        const U4 r = philox_at(C, pid, STREAM_JUMP, jk);
+        float a, b;
+        bm_pair_f32(C.poly_q4, C.poly_c4, r.z, r.w, a, b);
+        zq = (R)a; zw = (R)b;
+    } else {
+        const U4 s = philox_at(C, pid, STREAM_JUMP, 2 * jk + 1);
+        double a, b;
+        bm_pair_f64<false>(C, s.x, s.y, s.z, a, b);
+        zq = (R)a; zw = (R)b;
+    }
+}
+// Jump-stream draws for jump number jk of a path: inter-arrival time, jump-size normal and the
+// Brownian normal of the adaptive step that ends at that jump.
 template <typename R, int SAMP>
 __device__ __forceinline__ void jump_draws(const LevelConsts& C, ull pid, uint32_t jk, double& gap, R& zq, R& zw) {
     if (SAMP == SAMP_F32BM) {
@@ -1027,13 +1056,24 @@ __device__ __forceinline__ void jump_draws(const LevelConsts& C, ull pid, uint32
         bm_pair_f32(C.poly_q4, C.poly_c4, r.z, r.w, a, b);
         zq = (R)a; zw = (R)b;
     } else {
-        // two Philox blocks per record: 52 bits for the gap, three words for the pair of normals
-        U4 r = philox_at(C, pid, STREAM_JUMP, 2 * jk), s = philox_at(C, pid, STREAM_JUMP, 2 * jk + 1);
-        gap = neg2_log_u(C, u52(C, r.x, r.y)) * (0.5 * C.inv_lam);     // Exp(lam) inter-arrival time :454/:474
-        double a, b;
-        bm_pair_f64<false>(C, s.x, s.y, s.z, a, b);
-        zq = (R)a; zw = (R)b;
+        gap = jump_gap<SAMP>(C, pid, jk);
+        jump_normals<R, SAMP>(C, pid, jk, zq, zw);
     }
+}
+
+// the fine step (1-based, integer-valued double) an arrival time falls into: first j with t < j*dt (:457);
+// nsteps+1 for an arrival at or after the end of the path
+__device__ __forceinline__ double jump_step_of(const LevelConsts& C, double t) {
+    const double nd = (double)C.nsteps;
+    double j = nd + 1.0;
+    if (t < nd * C.dt) {
+        j = fmin(floor(t * C.inv_blk_dt * 4.0) + 1.0, nd);
+#pragma unroll 1
+        while (j > 1.0 && t < (j - 1.0) * C.dt) j -= 1.0;
+#pragma unroll 1
+        while (!(t < j * C.dt)) j += 1.0;
+    }
+    return j;
 }
 
 // Merton coupled path, Philox mode.  A 4-step block with no jump inside is exactly a GBM block
@@ -1055,11 +1095,31 @@ __device__ __forceinline__ void jump_draws(const LevelConsts& C, ull pid, uint32
 constexpr int kJumpRecs = MLMCB_JUMP_RECS;          // power of two
 enum { REC_D1 = 0, REC_DW1, REC_DJ, REC_D2, REC_SQ2, REC_STEP, REC_FIELDS };
 
-template <typename R, int FN, int SAMP, int SCH>
+// Where a walker keeps its records.  RingSlots: a ring of kJumpRecs per thread (one column of the block's store),
+// refilled in place.  BatchSlots: the compact per-warp store of the batch walk - records 0..n-1 of this path were
+// produced by the whole warp before the walk (slots base..base+n-1), anything beyond is produced in place into one
+// spare slot (base+n), one at a time.
+struct RingSlots {
+    double* rec;        // rec[(REC_FIELDS*slot + field)*kThreads]
+    __device__ __forceinline__ double& at(uint32_t k, int field) const {
+        return rec[(REC_FIELDS * (k & (kJumpRecs - 1)) + field) * kThreads];
+    }
+};
+constexpr int kBatchKmax = 8;           // records per path produced in the batch phase
+constexpr int kBatchSlots = 128;        // record slots per warp, one spare per lane included
+struct BatchSlots {
+    double* rec;        // rec[field*kBatchSlots + slot], already offset to this lane's first slot
+    uint32_t n;         // records produced in the batch phase
+    __device__ __forceinline__ double& at(uint32_t k, int field) const {
+        return rec[field * kBatchSlots + (k < n ? k : n)];
+    }
+};
+
+template <typename R, int FN, int SAMP, int SCH, typename Slots = RingSlots>
 struct MjdWalker {
     const LevelConsts& C;
     ull pid;
-    double* rec;        // this thread's column of the block's record store: rec[(REC_FIELDS*slot + field)*kThreads]
+    Slots sl;
     JD<R, FN, AR_FAST, SCH> st;
     uint32_t jk;        // index of the next jump of this path
     uint32_t jp;        // records produced so far
@@ -1067,26 +1127,16 @@ struct MjdWalker {
     double tlast;       // time and step of the newest record produced
     double jlast;
     int cm;
+    bool more;          // further records may follow the newest one (always true for the ring store)
 
-    __device__ __forceinline__ double& slot(uint32_t k, int field) const {
-        return rec[(REC_FIELDS * (k & (kJumpRecs - 1)) + field) * kThreads];
-    }
+    __device__ __forceinline__ double& slot(uint32_t k, int field) const { return sl.at(k, field); }
     // the next record from the jump stream
     __device__ __forceinline__ void produce() {
         double gap;
         R zq, zw;
         jump_draws<R, SAMP>(C, pid, jp, gap, zq, zw);
         const double t = tlast + gap;                                    // :454 / :474
-        const double nd = (double)C.nsteps;
-        double j = nd + 1.0;
-        if (t < nd * C.dt) {                                             // first j with t < j*dt  (:457)
-            j = floor(t * C.inv_blk_dt * 4.0) + 1.0;
-            j = fmin(j, nd);
-#pragma unroll 1
-            while (j > 1.0 && t < (j - 1.0) * C.dt) j -= 1.0;
-#pragma unroll 1
-            while (!(t < j * C.dt)) j += 1.0;
-        }
+        const double j = jump_step_of(C, t);
         const double d1 = t - (j == jlast ? tlast : (j - 1.0) * C.dt);   // :458
         const double d2 = j * C.dt - t;                                  // :477, if no further jump in step j
         slot(jp, REC_D1) = d1;
@@ -1102,6 +1152,7 @@ struct MjdWalker {
         st.init(C);
         jk = jp = 0; cm = 0;
         tlast = 0.0; jlast = 0.0;
+        more = true;
         const double nd = (double)C.nsteps;
 #pragma unroll 1
         while (jp < (uint32_t)kJumpRecs) {
@@ -1110,19 +1161,28 @@ struct MjdWalker {
         }
         jnext = slot(0, REC_STEP);
     }
-    // fine step j, which holds the next jump: all its jumps, then the rest of the step  (:457-482)
-    __device__ __forceinline__ void jump_step(double j, R z) {
-        double d2, sq2;
-        do {
-            st.jump_pre(C, slot(jk, REC_D1), (R)slot(jk, REC_DW1), (R)slot(jk, REC_DJ));
-            d2 = slot(jk, REC_D2); sq2 = slot(jk, REC_SQ2);
-            ++jk;
-            if (jk == jp) produce();                                     // record jk-1 was the newest one
-            jnext = slot(jk, REC_STEP);
-        } while (jnext == j);
-        st.grid_pre(C, d2, z * (R)sq2);
+    // batch store: records 0..n-1 are in place; t_last / j_last are the arrival time and step of record n-1
+    __device__ __forceinline__ void start_batch(uint32_t n, bool more_, double t_last, double j_last) {
+        st.init(C);
+        jk = 0; jp = n; cm = 0;
+        tlast = t_last; jlast = j_last;
+        more = more_;
+        if (n == 0 && more) produce();                                   // (only when the batch phase was cut short)
+        jnext = jk < jp ? slot(0, REC_STEP) : (double)C.nsteps + 1.0;
     }
-    __device__ __forceinline__ void whole_step(R z) { st.grid_pre(C, C.dt, z * (R)C.sqrt_dt); }
+    // fine step j (:457-482): its jumps, if it has any - only the lanes that do run that loop - then ONE step to the
+    // grid time for every lane, over the whole fine step or over what is left of it after the last jump
+    __device__ __forceinline__ void fine_step(double j, R z) {
+        double h = C.dt, sq = C.sqrt_dt;
+        while (jnext == j) {
+            st.jump_pre(C, slot(jk, REC_D1), (R)slot(jk, REC_DW1), (R)slot(jk, REC_DJ));
+            h = slot(jk, REC_D2); sq = slot(jk, REC_SQ2);
+            ++jk;
+            if (jk == jp && more) produce();                             // record jk-1 was the newest one
+            jnext = jk < jp ? slot(jk, REC_STEP) : (double)C.nsteps + 1.0;
+        }
+        st.grid_pre(C, h, z * (R)sq);
+    }
 
     // steps j0+1 .. j0+cnt  (:455-487), any M
     template <int MT>
@@ -1130,9 +1190,7 @@ struct MjdWalker {
 #pragma unroll 1
         for (int k = 0; k < cnt; ++k) {
             const R zk = (k & 2) ? ((k & 1) ? z3 : z2) : ((k & 1) ? z1 : z0);
-            const double j = j0 + (double)(k + 1);                       // :456
-            if (jnext == j) jump_step(j, zk);
-            else whole_step(zk);
+            fine_step(j0 + (double)(k + 1), zk);                         // :456
             if (MT == 2) { if (k & 1) st.coarse(C, 0.0); }
             else if (MT == 4) { if (k == 3) st.coarse(C, 0.0); }
             else if (++cm == C.M) { cm = 0; st.coarse(C, 0.0); }         // :483
@@ -1143,9 +1201,7 @@ struct MjdWalker {
     __device__ __forceinline__ void jump_block4(double j0, const R z[4]) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const double j = j0 + (double)(k + 1);
-            if (jnext == j) jump_step(j, z[k]);
-            else whole_step(z[k]);
+            fine_step(j0 + (double)(k + 1), z[k]);
             if (MT == 2 ? (k & 1) : k == 3) st.coarse(C, 0.0);
         }
     }
@@ -1205,12 +1261,23 @@ __device__ __forceinline__ void mjd_fast_block(const LevelConsts& C, const StepC
     }
 }
 
+template <typename R, int FN, int MT, int SAMP, int SCH, typename Walker>
+__device__ __forceinline__ void mjd_walk(const LevelConsts& C, ull pid, Walker& w,
+                                         double& vf, double& vc, double& gf, double& gc);
+
 template <typename R, int FN, int MT, int SAMP, int SCH>
 __device__ __forceinline__ void mjd_path_philox(const LevelConsts& C, ull pid, double* rec,
                                                 double& vf, double& vc, double& gf, double& gc) {
-    PhiloxSource<R, SAMP> src{C, pid};
-    MjdWalker<R, FN, SAMP, SCH> w{C, pid, rec};
+    MjdWalker<R, FN, SAMP, SCH> w{C, pid, RingSlots{rec}};
     w.start();
+    mjd_walk<R, FN, MT, SAMP, SCH>(C, pid, w, vf, vc, gf, gc);
+}
+
+// the block-uniform walk of one path whose walker has its first records in place
+template <typename R, int FN, int MT, int SAMP, int SCH, typename Walker>
+__device__ __forceinline__ void mjd_walk(const LevelConsts& C, ull pid, Walker& w,
+                                         double& vf, double& vc, double& gf, double& gc) {
+    PhiloxSource<R, SAMP> src{C, pid};
     const StepCoef<R, SCH> co(C);
     const uint32_t nfull = (uint32_t)(C.nsteps >> 2);
     // jb = first block that may hold this path's next jump.  The block loop stays uniform across
@@ -1353,6 +1420,18 @@ struct MjdFlat {
     }
 };
 
+__device__ __forceinline__ unsigned char* mjd_shared_bytes();
+#ifndef MLMCB_MJD_BATCH_FROM
+#define MLMCB_MJD_BATCH_FROM 8      // fp64 sampler: levels from this many fine steps take the batch walk, shorter ones the event-driven
+#endif                              // walk (profiles/r02_merton_levels.txt); the fp32 sampler's cheap records favour the event-driven walk
+// which of the two short-path walks a level takes (host and device agree through this one function)
+__host__ __device__ __forceinline__ bool mjd_use_batch(int samp, ull nsteps) {
+    return samp == SAMP_F64BM && nsteps >= (ull)MLMCB_MJD_BATCH_FROM;
+}
+template <typename R, int FN, int MT, int SAMP, int SCH>
+__device__ __forceinline__ void mjd_batch_body(const LevelConsts& C, unsigned bid, unsigned nblk, Sums7& acc,
+                                               double* Pf_out, double* Pc_out);
+
 // Body of the event-driven Merton kernel for block `bid` of the `nblk` blocks that share this level's paths
 // (a whole grid for a level call, a slice of the grid inside a sweep).
 template <typename R, int FN, int MT, int SAMP, int SCH>
@@ -1427,6 +1506,120 @@ __device__ __forceinline__ void mjd_flat_body(const LevelConsts& C, unsigned bid
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Merton, batch walk (levels of 2 .. MLMCB_MJD_FLAT_BELOW-1 fine steps - where mlmc puts its Merton samples).
+// A warp takes 32 paths at a time (lane = path) and goes through three phases, each uniform in code:
+//   arrivals  every lane draws inter-arrival times until its next arrival falls outside the path (or kBatchKmax are
+//             drawn): Philox + log only, the arrival times parked in shared memory.  Rounds = the largest count in the
+//             warp plus one; the cheap part of a record is all that runs at partial occupancy.
+//   records   the arrivals of the WHOLE warp (lam*T*32 of them on average) are dealt out one per lane - a prefix sum
+//             gives every lane its slots, a work list maps slot -> (owner lane, k) - and the expensive part of a record
+//             (second Philox block, Box-Muller pair, exp of the jump size, two square roots, step search) is computed
+//             with nearly all lanes busy, whoever owns the path, and stored in slot order.
+//   walk      the block-uniform walk of the long-path kernel (mjd_walk): all lanes at the same 4-step block, grid
+//             normals drawn with all lanes active, jump-free blocks through the GBM-like block code, blocks that hold
+//             a jump through the jump-adapted steps, reading the records a lane owns from its slots.
+// A path with more than kBatchKmax jumps, or a warp whose arrivals do not fit kBatchSlots, produces the excess
+// records in place inside the walk (one spare slot per lane), exactly as the ring store does.  Same draws, same
+// arithmetic and the same fast-block / jump-block rule as the other walks: per-path payoffs are bit-identical.
+// ------------------------------------------------------------------------------------------
+struct BatchStore {
+    double t[kBatchKmax][32];                   // arrival times, t[k][lane]
+    double rec[REC_FIELDS * kBatchSlots];       // records, rec[field*kBatchSlots + slot]
+    unsigned short work[kBatchSlots];           // work list of the record phase: owner lane | k << 5
+};
+
+constexpr size_t kMjdSharedBytes = sizeof(BatchStore) * (kThreads / 32) > sizeof(double) * kJumpRecs * REC_FIELDS * kThreads
+                                       ? sizeof(BatchStore) * (kThreads / 32) : sizeof(double) * kJumpRecs * REC_FIELDS * kThreads;
+__device__ __forceinline__ unsigned char* mjd_shared_bytes() {
+    __shared__ __align__(16) unsigned char bytes[kMjdSharedBytes];
+    return bytes;
+}
+
+template <typename R, int FN, int MT, int SAMP, int SCH>
+__device__ __forceinline__ void mjd_batch_body(const LevelConsts& C, unsigned bid, unsigned nblk, Sums7& acc,
+                                               double* Pf_out, double* Pc_out) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    BatchStore& bs = reinterpret_cast<BatchStore*>(mjd_shared_bytes())[warp];
+    const unsigned FULL = 0xffffffffu;
+    const double tend = (double)C.nsteps * C.dt;
+    const ull nbatch = (C.n_paths + 31) >> 5;
+    for (ull batch = (ull)bid * wpb + warp; batch < nbatch; batch += (ull)nblk * wpb) {
+        const ull i = (batch << 5) + lane;
+        const bool valid = i < C.n_paths;
+        const ull pid = C.path_offset + i;
+        // ---- arrivals ----
+        double t = 0.0;
+        uint32_t n = 0;
+        bool more = valid;                      // the next arrival may still fall inside the path
+        while (__any_sync(FULL, more && n < (uint32_t)kBatchKmax)) {
+            if (more && n < (uint32_t)kBatchKmax) {
+                t += jump_gap<SAMP>(C, pid, n);                          // :454 / :474
+                if (t < tend) { bs.t[n][lane] = t; ++n; }
+                else more = false;
+            }
+        }
+        // ---- slots: n records + one spare per lane; if the warp's arrivals do not fit, one record per lane ----
+        uint32_t total = __reduce_add_sync(FULL, n + 1u);
+        if (total > (uint32_t)kBatchSlots) {
+            if (n > 1u) { n = 1u; more = true; }
+            total = __reduce_add_sync(FULL, n + 1u);
+        }
+        uint32_t base = n + 1u, wbase = n;      // inclusive scans -> exclusive below
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(FULL, base, o), b = __shfl_up_sync(FULL, wbase, o);
+            if (lane >= (unsigned)o) { base += a; wbase += b; }
+        }
+        const uint32_t nwork = __shfl_sync(FULL, wbase, 31);
+        base -= n + 1u; wbase -= n;
+        for (uint32_t k = 0; k < n; ++k) bs.work[wbase + k] = (unsigned short)(lane | (k << 5));
+        __syncwarp();
+        // ---- records: one arrival per lane, whoever owns the path ----
+        for (uint32_t w0 = 0; w0 < nwork; w0 += 32) {
+            const uint32_t wi = w0 + lane;
+            const bool act = wi < nwork;
+            const uint32_t item = act ? bs.work[wi] : 0u, ol = item & 31u, k = item >> 5;
+            const uint32_t obase = __shfl_sync(FULL, base, ol);
+            if (act) {
+                const double tk = bs.t[k][ol], tp = k ? bs.t[k - 1][ol] : 0.0;
+                R zq, zw;
+                jump_normals<R, SAMP>(C, C.path_offset + (batch << 5) + ol, k, zq, zw);
+                const double j = jump_step_of(C, tk), jprev = k ? jump_step_of(C, tp) : 0.0;
+                const double d1 = tk - (j == jprev ? tp : (j - 1.0) * C.dt);             // :458
+                const double d2 = j * C.dt - tk;                                         // :477
+                double* r = bs.rec + obase + k;
+                r[REC_D1 * kBatchSlots] = d1;
+                r[REC_DW1 * kBatchSlots] = (double)(zw * (R)(d1 > 0.0 ? sqrt_pos(d1) : 0.0));       // :460
+                r[REC_DJ * kBatchSlots] = (double)JD<R, FN, AR_FAST, SCH>::jump_size(C, zq);        // :462
+                r[REC_D2 * kBatchSlots] = d2;
+                r[REC_SQ2 * kBatchSlots] = d2 > 0.0 ? sqrt_pos(d2) : 0.0;                           // :479
+                r[REC_STEP * kBatchSlots] = j;
+            }
+        }
+        __syncwarp();
+        // ---- walk ----
+        MjdWalker<R, FN, SAMP, SCH, BatchSlots> w{C, pid, BatchSlots{bs.rec + base, n}};
+        const double t_last = n ? bs.t[n - 1][lane] : 0.0;
+        w.start_batch(n, more, t_last, n ? w.slot(n - 1, REC_STEP) : 0.0);
+        double vf, vc, gf, gc;
+        mjd_walk<R, FN, MT, SAMP, SCH>(C, pid, w, vf, vc, gf, gc);
+        if (valid) emit_t<FN>(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
+        __syncwarp();                           // the store is rewritten by the next batch
+    }
+}
+
+template <typename R, int FN, int MT, int SAMP, int SCH>
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64_MJD : MLMCB_MINBLOCKS_FLAT)
+mjd_batch_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
+                 double* out7, double* Pf_out, double* Pc_out) {
+    sampler_init<SAMP>();
+    Sums7 acc;
+    acc.clear();
+    mjd_batch_body<R, FN, MT, SAMP, SCH>(C, blockIdx.x, gridDim.x, acc, Pf_out, Pc_out);
+    grid_finish(acc, partials, ticket, out7);
 }
 
 template <typename R, int FN, int MT, int SAMP, int SCH>
@@ -1678,17 +1871,15 @@ __device__ __forceinline__ void emit(const LevelConsts& C, ull i, double vf, dou
     }
 }
 
-// the block's jump-record store (Merton kernels only)
+// the block's jump-record store (Merton kernels only): the ring store of the long-path walk and the batch store of
+// the short-path walk live in the same shared bytes - a block serves one level, so it only ever uses one of them
 template <int MODEL>
 struct JumpRecStore {
     __device__ __forceinline__ static double* column() { return nullptr; }
 };
 template <>
 struct JumpRecStore<1> {
-    __device__ __forceinline__ static double* column() {
-        __shared__ double store[kJumpRecs * REC_FIELDS * kThreads];
-        return store + threadIdx.x;
-    }
+    __device__ __forceinline__ static double* column() { return reinterpret_cast<double*>(mjd_shared_bytes()) + threadIdx.x; }
 };
 
 // GBM paths of one or two fine steps (l = 0; M = 2, l = 1), a kernel of their own so that the long-path
@@ -1875,7 +2066,10 @@ sweep_kernel(const __grid_constant__ SweepConsts S, double* partials, unsigned* 
         else if (MT != 0 && kind == SK_FOUR) gbm_packed_body<R, FN, SAMP, SCH, MT == 4 ? 4 : -4>(C, bid, nblk, acc, nullptr, nullptr);
         else level_body<R, 0, FN, MT, SAMP, SCH, true>(C, bid, nblk, acc, nullptr, nullptr);
     } else {
-        if (S.kind[k] == SK_MJD_FLAT) mjd_flat_body<R, FN, MT, SAMP, SCH>(C, bid, nblk, acc, nullptr, nullptr);
+        if (S.kind[k] == SK_MJD_FLAT) {
+            if (mjd_use_batch(SAMP, C.nsteps)) mjd_batch_body<R, FN, MT, SAMP, SCH>(C, bid, nblk, acc, nullptr, nullptr);
+            else mjd_flat_body<R, FN, MT, SAMP, SCH>(C, bid, nblk, acc, nullptr, nullptr);
+        }
         else level_body<R, 1, FN, MT, SAMP, SCH>(C, bid, nblk, acc, nullptr, nullptr);
     }
     __shared__ double sm[(kThreads / 32) * 8];

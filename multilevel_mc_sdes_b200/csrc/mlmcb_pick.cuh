@@ -61,7 +61,7 @@ template <int SAMP> LevelKernel pick_gbm_s(int fn, int mt, int flags);
 template <int SAMP> LevelKernel pick_gbm_packed_s(int fn, int flags, int nsteps);   // paths of 1, 2 or 4 fine steps
 template <int SAMP> LevelKernel pick_gbm_anti_s(int fn, int mt, int flags);         // antithetic triple (Euro/Asian)
 template <int SAMP> LevelKernel pick_merton_uniform_s(int fn, int mt, int flags);
-template <int SAMP> LevelKernel pick_merton_flat_s(int fn, int mt, int flags);
+template <int SAMP> LevelKernel pick_merton_flat_s(int fn, int mt, int flags, bool batch);   // batch: the batch walk
 template <int SAMP> SweepKernel pick_gbm_sweep_s(int fn, int mt, int flags);         // MLMCB_TU_FAMILY 3
 template <int SAMP> SweepKernel pick_merton_sweep_s(int fn, int mt, int flags);      // MLMCB_TU_FAMILY 4
 

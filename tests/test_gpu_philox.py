@@ -577,21 +577,24 @@ def test_philox_mode_equals_replay_of_its_own_draws_merton_random_parameters(cud
 
 
 def test_merton_walks_agree_per_path(cuda_lib, tmp_path):
-    """The block-uniform and the event-driven Merton walks consume the same draws through the same
-    arithmetic: per-path payoffs are identical, whatever the length of the advance phase."""
+    """The block-uniform (ring of records per thread), the event-driven (lane queues) and the batch (records of a
+    whole warp dealt out one per lane) Merton walks consume the same draws through the same arithmetic: per-path
+    payoffs are identical bit for bit, whatever the length of the event-driven walk's advance phase."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for tag, env in (("uniform", {"MLMCB_MJD_FLAT_BELOW": "0"}), ("event", {"MLMCB_MJD_FLAT_BELOW": "1000000"}),
-                     ("event_run1", {"MLMCB_MJD_FLAT_BELOW": "1000000", "MLMCB_MJD_RUN_BLOCKS": "1"}),
-                     ("event_run3", {"MLMCB_MJD_FLAT_BELOW": "1000000", "MLMCB_MJD_RUN_BLOCKS": "3"})):
+    for tag, env in (("uniform", {"MLMCB_MJD_FLAT_BELOW": "0"}),
+                     ("event", {"MLMCB_MJD_FLAT_BELOW": "1000000", "MLMCB_MJD_WALK": "event"}),
+                     ("batch", {"MLMCB_MJD_FLAT_BELOW": "1000000", "MLMCB_MJD_WALK": "batch"}),
+                     ("event_run1", {"MLMCB_MJD_FLAT_BELOW": "1000000", "MLMCB_MJD_WALK": "event", "MLMCB_MJD_RUN_BLOCKS": "1"}),
+                     ("event_run3", {"MLMCB_MJD_FLAT_BELOW": "1000000", "MLMCB_MJD_WALK": "event", "MLMCB_MJD_RUN_BLOCKS": "3"})):
         f = str(tmp_path / f"{tag}.npz")
         subprocess.run([sys.executable, os.path.join(root, "tests", "merton_walks_case.py"), f], check=True, cwd=root,
                        env={**os.environ, **env, "PYTHONPATH": root})
         res[tag] = dict(np.load(f))
-    for tag in ("event", "event_run1", "event_run3"):
+    for tag in ("event", "batch", "event_run1", "event_run3"):
         for k, v in res["uniform"].items():
             assert np.array_equal(v, res[tag][k]), (tag, k, np.abs(v - res[tag][k]).max())
 
