@@ -1938,11 +1938,11 @@ __device__ __forceinline__ void gbm_packed_body(const LevelConsts& C, unsigned b
         const R X0 = (R)C.X0;
         const double h0 = 0.5 * C.X0, vc0 = FN == FN_AVG ? 0.0 : C.X0, gc0 = FN == FN_MIN ? C.X0 : 0.0;
         double s0 = 0.0, s1 = 0.0;
-        for (ull c = first + tid; c <= last; c += stride) {
+        // one group of four ids through the checked path: bounds test per id, optional per-path outputs
+        auto checked_group = [&](ull c) {
             R z[4];
             PhiloxSource<R, SAMP>{C, c}.load4_stream(STREAM_PACK, 0, z);
             const ull p0 = c << 2;
-            const bool inner = p0 >= lo && p0 + 4 <= hi;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const R Xf = fma_<R>(X0, co.t(z[k]), X0);
@@ -1950,20 +1950,42 @@ __device__ __forceinline__ void gbm_packed_body(const LevelConsts& C, unsigned b
                 if (FN == FN_AVG) vf = C.avg_wf * ((double)Xf + fma(-0.5, (double)Xf, h0));      // :369-386
                 if (FN == FN_MIN) gf = (double)min_<R>(X0, Xf);                                    // :420
                 const double Pf = payoff_fine(C, vf, gf);
-                if (inner || (p0 + k >= lo && p0 + k < hi)) {
+                if (p0 + k >= lo && p0 + k < hi) {
                     s0 += Pf;
                     s1 = fma(Pf, Pf, s1);
-                    if (Pf_out || Pc_out || C.raw) {
-                        const ull i = p0 + k - lo;
-                        if (Pf_out) Pf_out[i] = Pf;
-                        if (Pc_out) Pc_out[i] = vc0;                                               // raw coarse output :82
-                        if (C.raw) {
-                            C.raw[i] = vf; C.raw[C.n_paths + i] = gf;
-                            C.raw[2 * C.n_paths + i] = vc0; C.raw[3 * C.n_paths + i] = gc0;
-                        }
+                    const ull i = p0 + k - lo;
+                    if (Pf_out) Pf_out[i] = Pf;
+                    if (Pc_out) Pc_out[i] = vc0;                                                   // raw coarse output :82
+                    if (C.raw) {
+                        C.raw[i] = vf; C.raw[C.n_paths + i] = gf;
+                        C.raw[2 * C.n_paths + i] = vc0; C.raw[3 * C.n_paths + i] = gc0;
                     }
                 }
             }
+        };
+        if (Pf_out || Pc_out || C.raw) {
+            for (ull c = first + tid; c <= last; c += stride) checked_group(c);
+        } else {
+            // Sums only - the loop MLMC spends most of its samples in: the groups that lie wholly inside the request
+            // (in_first <= c < in_end) run without bounds tests or stores; the at most two ragged groups at the ends
+            // of the id range take the checked path on two threads of the grid.
+            const ull in_first = (lo + 3) >> 2, in_end = hi >> 2;
+            for (ull c = in_first + tid; c < in_end; c += stride) {
+                R z[4];
+                PhiloxSource<R, SAMP>{C, c}.load4_stream(STREAM_PACK, 0, z);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const R Xf = fma_<R>(X0, co.t(z[k]), X0);
+                    double vf = (double)Xf, gf = 0.0;
+                    if (FN == FN_AVG) vf = C.avg_wf * ((double)Xf + fma(-0.5, (double)Xf, h0));
+                    if (FN == FN_MIN) gf = (double)min_<R>(X0, Xf);
+                    const double Pf = payoff_fine(C, vf, gf);
+                    s0 += Pf;
+                    s1 = fma(Pf, Pf, s1);
+                }
+            }
+            if (tid == 0 && first < in_first) checked_group(first);
+            if (tid == 1 % stride && last >= in_end && !(first < in_first && last == first)) checked_group(last);
         }
         acc.s[0] = acc.s[2] = s0;
         acc.s[1] = acc.s[3] = s1;
