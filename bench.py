@@ -330,8 +330,9 @@ def run_b200(args):
                                "rates from mlmcb_pipe_probe in this run (MEASURED_PEAKS.json has no issue or FP64 entry)",
                 "pipe_probe": probe, "hbm_gbs_measured_peak": peaks.get("hbm_gbs"), "algorithmic_hbm_bytes_per_launch": 56,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture of this
-                # kernel under profiles/ (kernel image and constants; the kernel reads no data)
-                "traffic": {"f64bm": 79872, "f32bm": 71680}.get(main_s)}
+                # kernel (profiles/r02_ncu_gbm_euro_f64bm.txt, r01_ncu_gbm_euro_f32bm.txt): kernel image, constants and
+                # the sampler tables; the kernel reads no data and its 56-byte result stays in L2
+                "traffic": {"f64bm": 153856, "f32bm": 71680}.get(main_s)}
     try:
         mix = json.load(open(os.path.join(ROOT, "multilevel_mc_sdes_b200", "csrc", "sass_mix.json")))[main_s]
         inst = mix["inst_per_4_steps"] / 4.0

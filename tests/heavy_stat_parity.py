@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One-off heavy statistical parity run (north-star check (b) at small standard errors).
 
-    python tests/heavy_stat_parity.py > gpurun_out/heavy_stat_parity.json
+    python tests/heavy_stat_parity.py [f64bm|f32bm] > gpurun_out/heavy_stat_parity.json
 
 For every product (8 + antithetic + Milstein + American put) at two levels: the CUDA level function
 with N_gpu samples against the pinned C port of the reference (own generator, all host threads) with
@@ -21,6 +21,7 @@ import multilevel_mc_sdes_b200 as mm  # noqa: E402
 from oracle import c_oracle, np_oracle as O  # noqa: E402
 
 N_CPU, N_GPU = 40_000_000, 4_000_000_000
+SAMPLER = sys.argv[1] if len(sys.argv) > 1 else "f64bm"
 threads = os.cpu_count() or 1
 cases = []
 for cname, model, pay in (("Euro_GBM", O.GBM, O.EURO), ("Asian_GBM", O.GBM, O.ASIAN), ("Lookback_GBM", O.GBM, O.LOOKBACK),
@@ -34,15 +35,17 @@ for cname, pay in (("Euro_Merton", O.EURO), ("Asian_Merton", O.ASIAN), ("Lookbac
         cases.append((cname, O.MERTON, pay, l, M, "em", False))
 cases += [("Euro_GBM", O.GBM, O.EURO, 3, 4, "milstein", False), ("Asian_Merton", O.MERTON, O.ASIAN, 3, 4, "milstein", False),
           ("Euro_GBM", O.GBM, O.EURO, 3, 4, "em", True), ("Asian_GBM", O.GBM, O.ASIAN, 4, 2, "em", True),
+          ("Asian_GBM", O.GBM, O.ASIAN, 3, 4, "milstein", True),        # Milstein stepper under the antithetic estimator
+          ("Euro_GBM", O.GBM, O.EURO, 1, 4, "em", False), ("Asian_GBM", O.GBM, O.ASIAN, 2, 2, "em", False),   # four-step kernels
           ("Amer_GBM", O.GBM, O.AMERICAN, 4, 2, "em", False), ("Amer_GBM", O.GBM, O.AMERICAN, 6, 2, "em", False)]
-rep = {"N_cpu": N_CPU, "N_gpu": N_GPU, "cpu_threads": threads, "cases": []}
+rep = {"N_cpu": N_CPU, "N_gpu": N_GPU, "cpu_threads": threads, "sampler": SAMPLER, "cases": []}
 for cname, model, pay, l, M, scheme, anti in cases:
     p = O.Params(scheme=scheme)
     t0 = time.perf_counter()
     ref = c_oracle.level_sums_anti(p, pay, l, M, N_CPU, seed=77, nthreads=threads) if anti else \
         c_oracle.level_sums(p, model, pay, l, M, N_CPU, seed=77, nthreads=threads)
     t_cpu = time.perf_counter() - t0
-    opt = getattr(mm, cname)(seed=4321, scheme=scheme, verbose=False)
+    opt = getattr(mm, cname)(seed=4321, scheme=scheme, sampler=SAMPLER, verbose=False)
     t0 = time.perf_counter()
     s = opt.looper(N_GPU, l, M, anti)
     t_gpu = time.perf_counter() - t0

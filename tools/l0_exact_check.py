@@ -36,7 +36,7 @@ for name, kw in (("Euro_GBM", {}), ("Euro_GBM_itm", dict(X0=125, K=105, r=0.02, 
         exact = disc * ((m - o.K) * Phi(d) + s * phi(d))
         second = disc ** 2 * (((m - o.K) ** 2 + s * s) * Phi(d) + (m - o.K) * s * phi(d))
     var = second - exact ** 2
-    for sampler, n in (("f32bm", int(a.samples)), ("f64bm", int(a.samples / 4))):
+    for sampler, n in (("f64bm", int(a.samples)), ("f32bm", int(a.samples))):
         means = []
         for seed in range(a.seeds):
             sums = cls(verbose=False, seed=1000 + seed, sampler=sampler, **kw).looper(n, 0, 2, False)
