@@ -490,10 +490,14 @@ int sweep_fused(const mlmcb_params* p, int model, int payoff, int M, int n_level
         const ull threads = (n_paths[i] + per_thread - 1) / per_thread + (per_thread > 1 ? 1 : 0);
         cap[j] = (threads + kThreads - 1) / kThreads;                   // more blocks than this would idle
     }
-    // A sweep that is mostly long paths and long enough for launch latency not to matter (a fixed-level sweep of
-    // Giles_plot, :1775-1777) is better served by each level's own kernel: the long-path build keeps four octets in
-    // flight, the sweep kernel is built for the short levels where mlmc puts its samples.
-    if (f64 && model == MLMCB_GBM && total_long > 0.5 * total && total / 32.0 > 5e-3 * 148 * 4 * 1.9e9) return 0;
+    // One launch pays where launch latency matters: sweeps of up to a few milliseconds of work (the iterations of a
+    // latency-bound mlmc run).  A long sweep - a fixed-level sweep of Giles_plot (:1775-1777), the iterations of a
+    // tight-eps run - is better served by each level's own kernel, which is built for that level's path length
+    // (four octets in flight for long GBM paths, its own occupancy for each Merton walk) where the sweep kernel is one
+    // build for all.  MLMCB_FUSED_SWEEP_MS moves the threshold (tuning).
+    static const double max_ms = [] { const char* e = getenv("MLMCB_FUSED_SWEEP_MS"); return e ? atof(e) : 3.0; }();
+    (void)total_long;
+    if (total / 32.0 > max_ms * 1e-3 * 148 * 4 * 1.9e9) return 0;
     int grid0 = 0, resident = 0;
     if (int rc = geometry(k, device, ~0ull >> 16, &grid0, &resident)) return rc;
     const double budget = (double)(resident * 4 < kSweepRows - kSweepMax ? resident * 4 : kSweepRows - kSweepMax);   // four waves

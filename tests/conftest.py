@@ -20,7 +20,10 @@ def pytest_sessionstart(session):
     import warnings
     from multilevel_mc_sdes_b200 import build as b
     if not os.path.exists(b.LIB):
-        b.build()
+        try:
+            b.build()
+        except Exception as e:  # noqa: BLE001 - no nvcc here: the tests that need the library fail on their own, the
+            warnings.warn(f"libmlmcb.so is missing and could not be built: {e}")      # oracle / driver-logic tests still run
     elif b.is_stale():
         try:            # file times may not survive a copy of the tree: a present library is still usable
             b.build()

@@ -667,3 +667,26 @@ def test_torch_custom_op(cuda_lib):
     want = mm.Lookback_GBM(seed=3).looper(100_000, 3, 4, False)
     got = torch.ops.mlmcb.level_sums(torch_ops.option_params(opt), opt._model, opt._payoff_kind, 3, 4, 100_000, 3, 0, 0, 0)
     assert got.is_cuda and np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("sampler", ["f64bm", "f32bm"])
+def test_sweep_kernel_equals_single_level_calls(cuda_lib, sampler):
+    """One launch for all levels (sweep_kernel: per-level block ranges, bodies of the packed / four-step / long GBM
+    kernels and of the three Merton walks) against one level-kernel launch per level on the same path ids: equal up
+    to fp64 summation order - every product, both schemes, M = 2, 4 and a generic M, ragged sample counts, an empty
+    request in the middle, and a second sweep on the same object (fresh ids, workspace reuse)."""
+    for cname in sorted(CLASS_CODES):
+        for M, Lmax, scheme in ((2, 8, "em"), (4, 4, "em"), (3, 3, "em"), (4, 3, "milstein")):
+            a = getattr(mm, cname)(seed=12, sampler=sampler, scheme=scheme, verbose=False)
+            b = getattr(mm, cname)(seed=12, sampler=sampler, scheme=scheme, verbose=False)
+            for rep in range(2):
+                reqs = [(1000 + 37 * l + 5000 * (l == 0) + rep, l) for l in range(Lmax + 1)]
+                reqs[2] = (0, 2)                                   # nothing asked of level 2
+                rows = a._sweep(reqs, M)
+                for (n, l), row in zip(reqs, rows):
+                    if n == 0:
+                        assert not row.any()
+                        b._take_ids(l, 0)
+                        continue
+                    want = b.looper(n, l, M, False)
+                    np.testing.assert_allclose(row, want, rtol=2e-12, atol=1e-9, err_msg=f"{cname} M={M} l={l} {scheme}")
