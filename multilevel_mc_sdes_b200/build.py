@@ -10,7 +10,7 @@ LIB = os.path.join(CSRC, "libmlmcb.so")
 # one translation unit per (kernel family, sampler), compiled side by side: (source, object name, extra -D flags)
 UNITS = [("mlmcb_api.cu", "api.o", [])] + [
     ("mlmcb_family.cu", f"family{fam}_s{samp}.o", [f"-DMLMCB_TU_FAMILY={fam}", f"-DMLMCB_TU_SAMP={samp}"])
-    for fam in (0, 1, 2, 3, 4) for samp in (0, 1)]
+    for fam in (0, 1, 2, 3, 4, 5) for samp in (0, 1)]
 SOURCES = ["mlmcb_api.cu", "mlmcb_family.cu"]
 HEADERS = ["mlmcb_kernels.cuh", "mlmcb_pick.cuh", "mlmcb_f64tab.inc", os.path.join("..", "..", "include", "mlmcb.h")]
 

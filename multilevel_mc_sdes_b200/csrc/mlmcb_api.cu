@@ -132,6 +132,7 @@ int make_consts(const mlmcb_params* p, int model, int payoff, int l, int M, ull 
     C->avg_wf = C->dt / C->T; C->avg_wc = C->Mdt / C->T;
     C->poly_q4 = MLMCB_Q4; C->poly_c4 = MLMCB_C4;
     C->inv_blk_dt = 1.0 / (4.0 * C->dt);
+    C->inv_sqrt_dt = 1.0 / C->sqrt_dt;
     C->run_blocks = run_blocks_for(C->nsteps);
     // table-driven fp64 Box-Muller (tools/gen_f64bm_tables.py): G(x) = x + x^2 Q(x); sin(pi d)/d and (cos(pi d) - 1)/d^2 in d^2
     static const double lq[5] = {0x1.0000000000000p-2, 0x1.55555555279e5p-4, 0x1.ffffffffafffbp-6, 0x1.999b07519179fp-7,
@@ -187,8 +188,9 @@ LevelKernel pick_kernel(int model, int payoff, int M, int flags, ull nsteps) {
         if (packed) return f64 ? pick_gbm_packed_s<1>(fn, flags, packed) : pick_gbm_packed_s<0>(fn, flags, packed);
         return f64 ? pick_gbm_s<1>(fn, mt, flags) : pick_gbm_s<0>(fn, mt, flags);
     }
+    static const char* force = getenv("MLMCB_MJD_WALK");                 // "batch" | "event" | "legacy": tuning and the walk-agreement test
+    if (mjd_use_factor(flags, mt, nsteps) && !force) return f64 ? pick_merton_factor_s<1>(fn, mt) : pick_merton_factor_s<0>(fn, mt);
     if (nsteps < flat_below()) {
-        static const char* force = getenv("MLMCB_MJD_WALK");             // "batch" | "event": tuning and the walk-agreement test
         const bool batch = force ? (force[0] == 'b' && nsteps > 1) : mjd_use_batch(f64 ? SAMP_F64BM : SAMP_F32BM, nsteps);
         return f64 ? pick_merton_flat_s<1>(fn, mt, flags, batch) : pick_merton_flat_s<0>(fn, mt, flags, batch);
     }
@@ -482,7 +484,9 @@ int sweep_fused(const mlmcb_params* p, int model, int payoff, int M, int n_level
             else if (C->nsteps == 4 && mt != 0) S.kind[j] = SK_FOUR;
             else S.kind[j] = SK_LONG;
         } else {
-            S.kind[j] = C->nsteps < flat_below() ? SK_MJD_FLAT : SK_MJD_UNIFORM;
+            static const bool legacy = getenv("MLMCB_MJD_WALK") != nullptr;
+            S.kind[j] = (mjd_use_factor(flags, mt, C->nsteps) && !legacy) ? SK_MJD_FACTOR
+                        : C->nsteps < flat_below() ? SK_MJD_FLAT : SK_MJD_UNIFORM;
         }
         cost[j] = (double)n_paths[i] * path_cost(model, f64, C->nsteps, model == MLMCB_MERTON ? p->lam * p->T : 0.0);
         total += cost[j];

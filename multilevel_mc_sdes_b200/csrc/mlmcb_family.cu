@@ -4,12 +4,13 @@
 //                   2  Merton, short paths: mjd_flat_kernel (event-driven walk, l = 0 loop), mjd_batch_kernel (batch walk)
 //                   3  GBM, one launch per sweep:  sweep_kernel<double, 0, ...>
 //                   4  Merton, one launch per sweep: sweep_kernel<double, 1, ...>
+//                   5  Merton, factor walk: mjd_factor_kernel (Euler-Maruyama, fp64 paths, M = 2 | 4, 2 .. 2^30 fine steps)
 //   MLMCB_TU_SAMP   0  f32bm, 1 f64bm
 #define MLMCB_TEMPLATES_ONLY
 #include "mlmcb_pick.cuh"
 
 #if !defined(MLMCB_TU_FAMILY) || !defined(MLMCB_TU_SAMP)
-#error "compile with -DMLMCB_TU_FAMILY=0..4 -DMLMCB_TU_SAMP=0|1 (multilevel_mc_sdes_b200/build.py does)"
+#error "compile with -DMLMCB_TU_FAMILY=0..5 -DMLMCB_TU_SAMP=0|1 (multilevel_mc_sdes_b200/build.py does)"
 #endif
 
 namespace mlmcb {
@@ -60,6 +61,11 @@ template <> LevelKernel pick_merton_uniform_s<S>(int fn, int mt, int flags) { re
 #elif MLMCB_TU_FAMILY == 2
 template <> LevelKernel pick_merton_flat_s<S>(int fn, int mt, int flags, bool batch) {
     return batch ? pick_family<MertonBatch, S>(fn, mt, flags) : pick_family<MertonFlat, S>(fn, mt, flags);
+}
+#elif MLMCB_TU_FAMILY == 5
+template <> LevelKernel pick_merton_factor_s<S>(int fn, int mt) {
+    if (mt == 2) return fn == FN_AVG ? mjd_factor_kernel<FN_AVG, 2, S> : fn == FN_MIN ? mjd_factor_kernel<FN_MIN, 2, S> : mjd_factor_kernel<FN_FINAL, 2, S>;
+    return fn == FN_AVG ? mjd_factor_kernel<FN_AVG, 4, S> : fn == FN_MIN ? mjd_factor_kernel<FN_MIN, 4, S> : mjd_factor_kernel<FN_FINAL, 4, S>;
 }
 #elif MLMCB_TU_FAMILY == 3
 template <> SweepKernel pick_gbm_sweep_s<S>(int fn, int mt, int flags) { return pick_sweep<0, S>(fn, mt, flags); }

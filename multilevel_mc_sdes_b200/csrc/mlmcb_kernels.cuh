@@ -59,6 +59,9 @@
 #ifndef MLMCB_MINBLOCKS_F64_MJD
 #define MLMCB_MINBLOCKS_F64_MJD 4   // Merton kernels with the fp64 sampler: <= 128 registers
 #endif
+#ifndef MLMCB_UNROLL_FW
+#define MLMCB_UNROLL_FW 1           // Merton factor walk: jump-free octets in flight per thread (2 measured equal at 128 registers)
+#endif
 #ifndef MLMCB_PHILOX_ROUNDS
 #define MLMCB_PHILOX_ROUNDS 10      // experiments only; the shipped library is Philox4x32-10
 #endif
@@ -80,6 +83,7 @@ enum { PAY_EURO = 0, PAY_ASIAN = 1, PAY_LOOKBACK = 2, PAY_DIGITAL = 3, PAY_AMERI
 #endif
 constexpr int kThreads = MLMCB_THREADS;
 constexpr int kUnrollMjd = MLMCB_UNROLL_MJD;
+constexpr int kUnrollFw = MLMCB_UNROLL_FW;
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 
@@ -99,6 +103,7 @@ struct LevelConsts {
     // Merton
     double lam, inv_lam, jm, js;
     double inv_blk_dt;              // 1/(4*dt): jump time -> block index
+    double inv_sqrt_dt;             // factor walk: rho = sqrt(d2) / sqrt(dt)
     uint32_t run_blocks;            // event-driven Merton walk: iterations of the advance phase between event phases
     double* raw;                    // optional [rows][n_paths] path-function outputs (Option.path), else NULL
     double r, boundary_c, amer_cneg;  // American put: rate, boundary constant, -2/(sig^2 dt); discounting inside the path, exercise boundary constant
@@ -145,7 +150,7 @@ __device__ __forceinline__ U4 philox10(const LevelConsts& C, uint32_t c0, uint32
 // everything else fixed along a path, both multiplies of round 1 and one multiply each of rounds
 // 2 and 3 are loop-invariant and hoisted by the compiler: 16 instead of 20 IMAD.WIDE per block
 // for the same Philox4x32-10 output.
-enum { STREAM_GRID = 0, STREAM_JUMP = 1, STREAM_PACK = 2 };
+enum { STREAM_GRID = 0, STREAM_JUMP = 1, STREAM_PACK = 2, STREAM_GAP = 3 };
 
 __device__ __forceinline__ U4 philox_at(const LevelConsts& C, ull pid, uint32_t kind, uint32_t blk) {
     return philox10(C, kind, blk, (uint32_t)pid, ((uint32_t)(pid >> 32) & 0xFFFFu) | C.ctr3_tag);
@@ -1016,6 +1021,10 @@ struct JD {
 // Brownian normal of the adaptive step that ends at that jump.
 // (the two halves separately: the batch walk draws the arrival times of a whole warp first and the normals only
 // for arrivals that fall inside the path; same words, same values)
+// fp64 sampler: Exp(lam) from 52 random bits  (:1294)
+__device__ __forceinline__ double gap_f64(const LevelConsts& C, uint32_t hi, uint32_t lo) {
+    return neg2_log_u(C, u52(C, hi, lo)) * (0.5 * C.inv_lam);
+}
 template <int SAMP>
 __device__ __forceinline__ double jump_gap(const LevelConsts& C, ull pid, uint32_t jk) {
     if (SAMP == SAMP_F32BM) {
@@ -1023,8 +1032,9 @@ __device__ __forceinline__ double jump_gap(const LevelConsts& C, ull pid, uint32
         const float u = fminf(fmaf(__uint2float_rn(r.x), 0x1p-32f, 0x1p-33f), 0x1.fffffep-1f);
         return (double)(lg2_approx(u) * -0.693147180559945309f) * C.inv_lam;
     } else {
-        const U4 r = philox_at(C, pid, STREAM_JUMP, 2 * jk);
-        return neg2_log_u(C, u52(C, r.x, r.y)) * (0.5 * C.inv_lam);
+        // two inter-arrival times per block of the gap stream: (x, y) for even jk, (z, w) for odd jk
+        const U4 r = philox_at(C, pid, STREAM_GAP, jk >> 1);
+        return gap_f64(C, (jk & 1u) ? r.z : r.x, (jk & 1u) ? r.w : r.y);
     }
 }
 template <typename R, int SAMP>
@@ -1035,7 +1045,7 @@ __device__ __forceinline__ void jump_normals(const LevelConsts& C, ull pid, uint
         bm_pair_f32(C.poly_q4, C.poly_c4, r.z, r.w, a, b);
         zq = (R)a; zw = (R)b;
     } else {
-        const U4 s = philox_at(C, pid, STREAM_JUMP, 2 * jk + 1);
+        const U4 s = philox_at(C, pid, STREAM_JUMP, jk);
         double a, b;
         bm_pair_f64<false>(C, s.x, s.y, s.z, a, b);
         zq = (R)a; zw = (R)b;
@@ -1531,8 +1541,10 @@ struct BatchStore {
     unsigned short work[kBatchSlots];           // work list of the record phase: owner lane | k << 5
 };
 
-constexpr size_t kMjdSharedBytes = sizeof(BatchStore) * (kThreads / 32) > sizeof(double) * kJumpRecs * REC_FIELDS * kThreads
-                                       ? sizeof(BatchStore) * (kThreads / 32) : sizeof(double) * kJumpRecs * REC_FIELDS * kThreads;
+constexpr size_t kFwStoreBytes = 8 * 32 * 8 + 6 * 128 * 8 + 128 * 4 + 128 * 2;    // sizeof(FwStore<FN_AVG>), the factor walk's store (below)
+constexpr size_t kMjdSharedWarp = sizeof(BatchStore) > kFwStoreBytes ? sizeof(BatchStore) : kFwStoreBytes;
+constexpr size_t kMjdSharedBytes = kMjdSharedWarp * (kThreads / 32) > sizeof(double) * kJumpRecs * REC_FIELDS * kThreads
+                                       ? kMjdSharedWarp * (kThreads / 32) : sizeof(double) * kJumpRecs * REC_FIELDS * kThreads;
 __device__ __forceinline__ unsigned char* mjd_shared_bytes() {
     __shared__ __align__(16) unsigned char bytes[kMjdSharedBytes];
     return bytes;
@@ -1630,6 +1642,373 @@ mjd_flat_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigne
     Sums7 acc;
     acc.clear();
     mjd_flat_body<R, FN, MT, SAMP, SCH>(C, blockIdx.x, gridDim.x, acc, Pf_out, Pc_out);
+    grid_finish(acc, partials, ticket, out7);
+}
+
+// ------------------------------------------------------------------------------------------
+// Merton, factor walk (Euler-Maruyama, fp64 paths, M = 2 or 4, every level of 2 .. 2^30 fine steps).
+//
+// An Euler-Maruyama step of the Merton SDE multiplies the state by a factor that does not depend on the state:
+//   grid step          S <- S (1 + t),            t  = mu h + sig sqrt(h) z
+//   step to a jump     S <- S (1 + t1) J,         t1 = mu d1 + sig sqrt(d1) zw,   J = exp(jm + js zq) = 1 + dJ   (:462-465)
+// and the coarse increment over any stretch of fine sub-steps is the SUM of their t's (both are linear in (h, dW)),
+// so the coarse path needs one accumulator: S_c <- S_c (1 + sum t) at every coarse grid time and at every jump.
+// Everything about a jump is therefore known before the walk starts.  The closing step of a fine step that holds a
+// jump - from the jump to the grid time, d2 long, driven by the grid normal z_j of that step - is affine in the factor
+// the sampler delivers for the whole step: with t = a + b z_j,
+//   t' = mu d2 + sig sqrt(d2) z_j = kappa + rho t,   rho = sqrt(d2/dt),  kappa = mu d2 - rho a.
+// A record is (t1, J, rho, kappa, step) [+ d1, d2 for the trapezoid of the Asian payoff]; it is produced with all lanes
+// busy (arrivals of the whole warp dealt out one per lane, as in the batch walk) and APPLYING it is four multiply-adds.
+// The walk itself is uniform across the warp: every lane is at the same fine step; octets (eight steps, three Philox
+// blocks) in which no lane has a jump run the GBM octet code, the others run step by step - "lanes with a jump in this
+// step apply it, then every lane closes the step with t' = fma(rho, t, kappa)" (rho = 1, kappa = 0 without a jump).
+// No lane ever waits for another lane's jump arithmetic: what is left of the divergence is four FMAs per jump.
+//
+// Rounds.  Records are produced for up to kFwKmax arrivals per path and round into kFwSlots slots per warp (prefix
+// sum, n + 1 slots per lane: the last one is a sentinel).  A path with more arrivals, or a warp whose arrivals do not
+// fit (then 3 per lane), is walked as far as the records of EVERY lane are complete - all steps below the step of the
+// last record of a lane that may have more - the jumps already known for the next step are applied, and the next
+// round starts from each lane's last applied record (records produced but not applied are produced again: the draws
+// are a pure function of (path, k)).  Any lam*T terminates: the lane that limits the walk applies all of its records.
+// Same draws and the same per-path control flow as the other walks (:449-491); values differ from theirs by rounding
+// only (products of factors instead of increments: ~1e-15 relative).
+// ------------------------------------------------------------------------------------------
+constexpr int kFwKmax = 8;              // arrivals per path and round
+constexpr int kFwSlots = 128;           // record slots per warp, sentinels included (32 * (3 + 1) always fits)
+enum { FW_T1 = 0, FW_J, FW_RHO, FW_KAPPA, FW_D1, FW_D2 };
+template <int FN>
+struct FwStore {
+    static constexpr int kFields = FN == FN_AVG ? 6 : 4;
+    double t[kFwKmax][32];              // arrival times of this round, t[k][lane]
+    double rec[kFields][kFwSlots];
+    int step[kFwSlots];                 // fine step (1-based) the record falls into; sentinel: INT_MAX
+    unsigned short work[kFwSlots];      // work list of the record phase: owner lane | k << 5
+};
+static_assert(sizeof(FwStore<FN_AVG>) <= kFwStoreBytes, "kFwStoreBytes");
+constexpr ull kFwMaxSteps = 1ull << 30; // step numbers are 32-bit here; longer paths take the block-uniform walk
+// which levels take the factor walk (host and device agree through this one function); flag bits as in mlmcb.h:
+// 0x10 = MLMCB_FP32_PATHS, 0x40 = MLMCB_MILSTEIN
+__host__ __device__ __forceinline__ bool mjd_use_factor(int flags, int mt, ull nsteps) {
+    return !(flags & (0x10 | 0x40)) && mt != 0 && nsteps >= 2 && nsteps <= kFwMaxSteps;
+}
+
+// step factors t_i = a + b z_i of octet o (steps 8o+1 .. 8o+8), or of its first NP pairs
+template <int SAMP>
+struct FactorSource {
+    const LevelConsts& C;
+    ull pid;
+    __device__ __forceinline__ void load8(uint32_t o, double t[8]) const {
+        if (SAMP == SAMP_F64BM) {
+            PhiloxSource<double, SAMP>{C, pid}.load8_affine(o, t, C.a_f, C.b_f);
+        } else {
+            float f[4], g[4];
+            bm_quad_f32(C, philox_at(C, pid, STREAM_GRID, 2u * o), f);
+            bm_quad_f32(C, philox_at(C, pid, STREAM_GRID, 2u * o + 1u), g);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { t[k] = fma(C.b_f, (double)f[k], C.a_f); t[4 + k] = fma(C.b_f, (double)g[k], C.a_f); }
+        }
+    }
+    // paths of 2 or 4 fine steps: the first one or two pairs of octet 0
+    __device__ __forceinline__ void load_head(int npairs, double t[8]) const {
+        if (SAMP == SAMP_F64BM) {
+            const U4 r = philox_at(C, pid, STREAM_GRID, 0u);
+            bm_pair_f64<true>(C, r.x, r.y, r.z, t[0], t[1], C.a_f, C.b_f);
+            if (npairs > 1) {
+                const U4 s = philox_at(C, pid, STREAM_GRID, 1u);
+                bm_pair_f64<true>(C, r.w, s.x, s.y, t[2], t[3], C.a_f, C.b_f);
+            }
+        } else {
+            float f[4];
+            bm_quad_f32(C, philox_at(C, pid, STREAM_GRID, 0u), f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] = fma(C.b_f, (double)f[k], C.a_f);
+        }
+    }
+};
+
+template <int FN, int MT, int SAMP>
+struct FactorWalk {
+    const LevelConsts& C;
+    FwStore<FN>& bs;
+    double Sf, Sc, Gf, Gc;      // G: trapezoid integral (FN_AVG) / running minimum (FN_MIN)
+    double tsum;                // sum of the fine t's since the last coarse step = the coarse t
+    double dtc, h;              // FN_AVG: time since the last coarse step; length of the closing step of the current fine step
+    double rho, kappa;          // closing step of the current fine step: t' = fma(rho, t, kappa)
+    uint32_t jk;                // slot of this lane's next record
+    int jnext;                  // its fine step
+
+    __device__ __forceinline__ void init() {
+        Sf = Sc = C.X0;
+        Gf = Gc = FN == FN_MIN ? C.X0 : 0.0;
+        tsum = 0.0; dtc = 0.0; h = C.dt; rho = 1.0; kappa = 0.0;
+    }
+    // the jumps of fine step j known so far (:457-474), lanes that have one only
+    __device__ __forceinline__ void jumps(int j) {
+        while (__any_sync(0xffffffffu, jnext == j)) {
+            if (jnext == j) {
+                const double t1 = bs.rec[FW_T1][jk], J = bs.rec[FW_J][jk];
+                rho = bs.rec[FW_RHO][jk]; kappa = bs.rec[FW_KAPPA][jk];
+                tsum += t1;
+                if (FN == FN_AVG) {                                      // :532-540
+                    const double d1 = bs.rec[FN == FN_AVG ? FW_D1 : 0][jk];
+                    h = bs.rec[FN == FN_AVG ? FW_D2 : 0][jk];
+                    dtc += d1;
+                    const double uf = fma(Sf, t1, Sf), uc = fma(Sc, tsum, Sc);
+                    Gf = fma(0.5 * d1, Sf + uf, Gf);
+                    Gc = fma(0.5 * dtc, Sc + uc, Gc);
+                    Sf = uf * J; Sc = uc * J;
+                    dtc = 0.0;
+                } else {                                                 // :465-468, :621-622
+                    Sf = fma(Sf, t1, Sf) * J;
+                    Sc = fma(Sc, tsum, Sc) * J;
+                    if (FN == FN_MIN) { Gf = min_<double>(Gf, Sf); Gc = min_<double>(Gc, Sc); }
+                }
+                tsum = 0.0;
+                ++jk;
+                jnext = bs.step[jk];
+            }
+        }
+    }
+    // fine step j: its jumps, then the step to the grid time (:477-487); t = a + b z_j
+    template <bool COARSE_END>
+    __device__ __forceinline__ void step(int j, double t) {
+        jumps(j);
+        const double tt = fma(rho, t, kappa);
+        if (FN == FN_AVG) {                                              // :554-556
+            const double uf = fma(Sf, tt, Sf);
+            Gf = fma(0.5 * h, Sf + uf, Gf);
+            Sf = uf;
+            dtc += h;
+            h = C.dt;
+        } else {
+            Sf = fma(Sf, tt, Sf);                                        // :481
+            if (FN == FN_MIN) Gf = min_<double>(Gf, Sf);                 // :637
+        }
+        tsum += tt;
+        rho = 1.0; kappa = 0.0;
+        if (COARSE_END) {                                                // :483-487
+            if (FN == FN_AVG) {
+                const double uc = fma(Sc, tsum, Sc);
+                Gc = fma(0.5 * dtc, Sc + uc, Gc);
+                Sc = uc;
+                dtc = 0.0;
+            } else {
+                Sc = fma(Sc, tsum, Sc);
+                if (FN == FN_MIN) Gc = min_<double>(Gc, Sc);
+            }
+            tsum = 0.0;
+        }
+    }
+    // an octet in which no lane has a jump (tsum = 0, dtc = 0 on entry and on exit).  The arithmetic is that of step()
+    // without a jump, operation for operation - sequential sums for the coarse factor and the coarse step length, the
+    // trapezoid step by step - so that a path's value does not depend on what the other lanes of its warp do.
+    __device__ __forceinline__ void free_octet(const double t[8]) {
+        const double hdt = 0.5 * C.dt;
+        const double mdt = MT == 4 ? ((C.dt + C.dt) + C.dt) + C.dt : C.dt + C.dt;
+#pragma unroll
+        for (int g = 0; g < 8; g += MT) {
+            const double tc = MT == 4 ? ((t[g] + t[g + 1]) + t[g + 2]) + t[g + 3] : t[g] + t[g + 1];
+#pragma unroll
+            for (int k = 0; k < MT; ++k) {
+                if (FN == FN_AVG) {
+                    const double uf = fma(Sf, t[g + k], Sf);
+                    Gf = fma(hdt, Sf + uf, Gf);
+                    Sf = uf;
+                } else {
+                    Sf = fma(Sf, t[g + k], Sf);
+                    if (FN == FN_MIN) Gf = min_<double>(Gf, Sf);
+                }
+            }
+            if (FN == FN_AVG) {
+                const double uc = fma(Sc, tc, Sc);
+                Gc = fma(0.5 * mdt, Sc + uc, Gc);
+                Sc = uc;
+            } else {
+                Sc = fma(Sc, tc, Sc);
+                if (FN == FN_MIN) Gc = min_<double>(Gc, Sc);
+            }
+        }
+    }
+    __device__ __forceinline__ void outputs(double& vf, double& vc, double& gf, double& gc) const {
+        if (FN == FN_AVG) { vf = Gf / C.T; vc = Gc / C.T; gf = gc = 0.0; }       // :571
+        else { vf = Sf; vc = Sc; gf = Gf; gc = Gc; }
+    }
+};
+
+template <int FN, int MT, int SAMP>
+__device__ __forceinline__ void mjd_factor_body(const LevelConsts& C, unsigned bid, unsigned nblk, Sums7& acc,
+                                                double* Pf_out, double* Pc_out) {
+    static_assert(MT == 2 || MT == 4, "the factor walk is built for M = 2 and M = 4");
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    FwStore<FN>& bs = reinterpret_cast<FwStore<FN>*>(mjd_shared_bytes())[warp];
+    const unsigned FULL = 0xffffffffu;
+    const int nsteps = (int)C.nsteps;
+    const double tend = (double)C.nsteps * C.dt;
+    const ull nbatch = (C.n_paths + 31) >> 5;
+    for (ull batch = (ull)bid * wpb + warp; batch < nbatch; batch += (ull)nblk * wpb) {
+        const ull i = (batch << 5) + lane;
+        const bool valid = i < C.n_paths;
+        const ull pid0 = C.path_offset + (batch << 5), pid = pid0 + lane;
+        FactorWalk<FN, MT, SAMP> w{C, bs};
+        w.init();
+        const FactorSource<SAMP> src{C, pid};
+        uint32_t k_done = 0;            // records applied in earlier rounds
+        double t_done = 0.0;            // arrival time and fine step of the last of them
+        int j_done = 0;
+        bool more = valid;              // the next arrival may still fall inside the path
+        int j_cur = 1;                  // the fine step to close next (the same in every lane)
+        bool mid = false;               // jumps of step j_cur were applied before its records were complete (end of a round)
+        for (;;) {
+            // ---- arrivals: inter-arrival times until the path ends or kFwKmax are drawn (:454, :474) ----
+            double t = t_done;
+            uint32_t n = 0;
+            while (__any_sync(FULL, more && n < (uint32_t)kFwKmax)) {
+                if (more && n < (uint32_t)kFwKmax) {
+                    if (SAMP == SAMP_F64BM) {                            // one block of the gap stream holds two
+                        const uint32_t idx = k_done + n;
+                        const U4 r = philox_at(C, pid, STREAM_GAP, idx >> 1);
+                        if (!(idx & 1u)) {
+                            t += gap_f64(C, r.x, r.y);
+                            if (t < tend) { bs.t[n][lane] = t; ++n; }
+                            else more = false;
+                        }
+                        if (more && n < (uint32_t)kFwKmax) {
+                            t += gap_f64(C, r.z, r.w);
+                            if (t < tend) { bs.t[n][lane] = t; ++n; }
+                            else more = false;
+                        }
+                    } else {
+                        t += jump_gap<SAMP>(C, pid, k_done + n);
+                        if (t < tend) { bs.t[n][lane] = t; ++n; }
+                        else more = false;
+                    }
+                }
+            }
+            // ---- slots: n records and a sentinel per lane; three records per lane always fit ----
+            if (__reduce_add_sync(FULL, n + 1u) > (uint32_t)kFwSlots && n > 3u) { n = 3u; more = true; }
+            uint32_t base = n + 1u, wbase = n;  // inclusive scans -> exclusive below
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t a = __shfl_up_sync(FULL, base, o), b = __shfl_up_sync(FULL, wbase, o);
+                if (lane >= (unsigned)o) { base += a; wbase += b; }
+            }
+            const uint32_t nwork = __shfl_sync(FULL, wbase, 31);
+            base -= n + 1u; wbase -= n;
+            for (uint32_t k = 0; k < n; ++k) bs.work[wbase + k] = (unsigned short)(lane | (k << 5));
+            bs.step[base + n] = 0x7fffffff;
+            __syncwarp();
+            // ---- records: one arrival per lane, whoever owns the path ----
+            for (uint32_t w0 = 0; w0 < nwork; w0 += 32) {
+                const uint32_t wi = w0 + lane;
+                const bool act = wi < nwork;
+                const uint32_t item = act ? bs.work[wi] : 0u, ol = item & 31u, k = item >> 5;
+                const uint32_t obase = __shfl_sync(FULL, base, ol), okd = __shfl_sync(FULL, k_done, ol);
+                const double otd = __shfl_sync(FULL, t_done, ol);
+                const int ojd = __shfl_sync(FULL, j_done, ol);
+                const uint32_t s = obase + k;
+                double tk = 0.0;
+                int j = 0;
+                if (act) {
+                    tk = bs.t[k][ol];
+                    j = (int)jump_step_of(C, tk);
+                    bs.step[s] = j;
+                }
+                __syncwarp();                   // the step of the previous arrival of the same path: slot s - 1
+                if (act) {
+                    const double tp = k ? bs.t[k - 1][ol] : otd;
+                    const int jprev = k ? bs.step[s - 1] : ojd;
+                    double zq, zw;
+                    jump_normals<double, SAMP>(C, pid0 + ol, okd + k, zq, zw);
+                    const double d1 = tk - (j == jprev ? tp : (double)(j - 1) * C.dt);      // :458
+                    const double d2 = (double)j * C.dt - tk;                                // :477
+                    const double dW1 = zw * (d1 > 0.0 ? sqrt_pos(d1) : 0.0);                // :460
+                    const double r = (d2 > 0.0 ? sqrt_pos(d2) : 0.0) * C.inv_sqrt_dt;       // :479
+                    bs.rec[FW_T1][s] = fma(C.sig, dW1, C.mu * d1);
+                    bs.rec[FW_J][s] = exp_bounded(C, fma(C.js, zq, C.jm));                  // :462
+                    bs.rec[FW_RHO][s] = r;
+                    bs.rec[FW_KAPPA][s] = fma(-r, C.a_f, C.mu * d2);
+                    if (FN == FN_AVG) { bs.rec[FN == FN_AVG ? FW_D1 : 0][s] = d1; bs.rec[FN == FN_AVG ? FW_D2 : 0][s] = d2; }
+                }
+            }
+            __syncwarp();
+            w.jk = base;
+            w.jnext = bs.step[base];
+            // steps 1 .. hz can be closed: every lane's records for them are complete
+            const int hz = (int)__reduce_min_sync(FULL, (unsigned)(more && n ? bs.step[base + n - 1] - 1 : nsteps));
+            // ---- walk ----
+            while (j_cur <= hz) {
+                const uint32_t o = (uint32_t)(j_cur - 1) >> 3;
+                if (nsteps >= 8 && ((j_cur - 1) & 7) == 0 && !mid) {
+                    // whole octets ahead in which no lane has a jump, as far as they may be closed
+                    const int lim = w.jnext <= hz ? w.jnext - 1 : hz;                       // steps 1 .. lim are jump-free in this lane
+                    const uint32_t stop = __reduce_min_sync(FULL, (unsigned)lim >> 3);      // octets [o, stop)
+                    if (stop > o) {
+#pragma unroll kUnrollFw
+                        for (uint32_t q = o; q < stop; ++q) {
+                            double tq[8];
+                            src.load8(q, tq);
+                            w.free_octet(tq);
+                        }
+                        j_cur = (int)(stop << 3) + 1;
+                        continue;
+                    }
+                }
+                double tq[8];
+                if (nsteps >= 8) {
+                    src.load8(o, tq);
+                } else {
+                    src.load_head(nsteps >> 1, tq);
+                    if (hz == nsteps && j_cur == 1) {                   // the whole path in one go (2 or 4 steps)
+                        if (MT == 2) {
+                            w.template step<false>(1, tq[0]);
+                            w.template step<true>(2, tq[1]);
+                            if (nsteps == 4) { w.template step<false>(3, tq[2]); w.template step<true>(4, tq[3]); }
+                        } else {
+                            w.template step<false>(1, tq[0]);
+                            w.template step<false>(2, tq[1]);
+                            w.template step<false>(3, tq[2]);
+                            w.template step<true>(4, tq[3]);
+                        }
+                        j_cur = nsteps + 1;
+                        break;
+                    }
+                }
+                const int j0 = (int)(o << 3);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int j = j0 + k + 1;
+                    if (j >= j_cur && j <= hz) {
+                        if ((k % MT) == MT - 1) w.template step<true>(j, tq[k]);
+                        else w.template step<false>(j, tq[k]);
+                    }
+                }
+                j_cur = j0 + 8 < hz ? j0 + 9 : hz + 1;
+                mid = false;
+            }
+            if (j_cur > nsteps) break;
+            // ---- the walk waits for records: apply what is known of step j_cur, restart from the last applied record ----
+            w.jumps(j_cur);
+            mid = true;
+            const uint32_t c = w.jk - base;
+            if (c) { t_done = bs.t[c - 1][lane]; j_done = bs.step[base + c - 1]; k_done += c; }
+            if (c < n) more = true;
+            __syncwarp();
+        }
+        double vf, vc, gf, gc;
+        w.outputs(vf, vc, gf, gc);
+        if (valid) emit_t<FN, false>(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
+        __syncwarp();                           // the store is rewritten by the next batch
+    }
+}
+
+template <int FN, int MT, int SAMP>
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? MLMCB_MINBLOCKS_F64_MJD : MLMCB_MINBLOCKS_FLAT)
+mjd_factor_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
+                  double* out7, double* Pf_out, double* Pc_out) {
+    sampler_init<SAMP>();
+    Sums7 acc;
+    acc.clear();
+    mjd_factor_body<FN, MT, SAMP>(C, blockIdx.x, gridDim.x, acc, Pf_out, Pc_out);
     grid_finish(acc, partials, ticket, out7);
 }
 
@@ -2062,7 +2441,7 @@ level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* 
 // constants sit in the kernel's parameter block (indexed by a block-uniform level number).
 // ------------------------------------------------------------------------------------------
 constexpr int kSweepMax = 20;
-enum { SK_PACKED = 0, SK_FOUR = 1, SK_LONG = 2, SK_MJD_FLAT = 3, SK_MJD_UNIFORM = 4 };
+enum { SK_PACKED = 0, SK_FOUR = 1, SK_LONG = 2, SK_MJD_FLAT = 3, SK_MJD_UNIFORM = 4, SK_MJD_FACTOR = 5 };
 struct SweepConsts {
     int n_levels, n_rows;
     unsigned first[kSweepMax + 1];      // blocks [first[k], first[k+1]) simulate entry k
@@ -2088,7 +2467,9 @@ sweep_kernel(const __grid_constant__ SweepConsts S, double* partials, unsigned* 
         else if (MT != 0 && kind == SK_FOUR) gbm_packed_body<R, FN, SAMP, SCH, MT == 4 ? 4 : -4>(C, bid, nblk, acc, nullptr, nullptr);
         else level_body<R, 0, FN, MT, SAMP, SCH, true>(C, bid, nblk, acc, nullptr, nullptr);
     } else {
-        if (S.kind[k] == SK_MJD_FLAT) {
+        if (S.kind[k] == SK_MJD_FACTOR) {
+            if constexpr (sizeof(R) == 8 && SCH == SCH_EM && MT != 0) mjd_factor_body<FN, MT, SAMP>(C, bid, nblk, acc, nullptr, nullptr);
+        } else if (S.kind[k] == SK_MJD_FLAT) {
             if (mjd_use_batch(SAMP, C.nsteps)) mjd_batch_body<R, FN, MT, SAMP, SCH>(C, bid, nblk, acc, nullptr, nullptr);
             else mjd_flat_body<R, FN, MT, SAMP, SCH>(C, bid, nblk, acc, nullptr, nullptr);
         }

@@ -1,7 +1,7 @@
 // libmlmcb - selecting one instantiation of a level-kernel family from run-time codes.
 // A family x sampler pair is one translation unit: mlmcb_family.cu compiled with
-// -DMLMCB_TU_FAMILY={0 GBM, 1 Merton block-uniform, 2 Merton event-driven, 3 GBM sweep, 4 Merton sweep} -DMLMCB_TU_SAMP={0 f32bm, 1 f64bm}
-// (build.py), so nvcc compiles the ten of them side by side; replay, American and probe kernels stay in
+// -DMLMCB_TU_FAMILY={0 GBM, 1 Merton block-uniform, 2 Merton event-driven, 3 GBM sweep, 4 Merton sweep, 5 Merton factor walk}
+// -DMLMCB_TU_SAMP={0 f32bm, 1 f64bm} (build.py), so nvcc compiles the twelve of them side by side; replay, American and probe kernels stay in
 // mlmcb_api.cu.
 #pragma once
 #include "../../include/mlmcb.h"
@@ -62,6 +62,7 @@ template <int SAMP> LevelKernel pick_gbm_packed_s(int fn, int flags, int nsteps)
 template <int SAMP> LevelKernel pick_gbm_anti_s(int fn, int mt, int flags);         // antithetic triple (Euro/Asian)
 template <int SAMP> LevelKernel pick_merton_uniform_s(int fn, int mt, int flags);
 template <int SAMP> LevelKernel pick_merton_flat_s(int fn, int mt, int flags, bool batch);   // batch: the batch walk
+template <int SAMP> LevelKernel pick_merton_factor_s(int fn, int mt);                        // MLMCB_TU_FAMILY 5: factor walk (EM, fp64 paths, mt 2 | 4)
 template <int SAMP> SweepKernel pick_gbm_sweep_s(int fn, int mt, int flags);         // MLMCB_TU_FAMILY 3
 template <int SAMP> SweepKernel pick_merton_sweep_s(int fn, int mt, int flags);      // MLMCB_TU_FAMILY 4
 

@@ -579,13 +579,17 @@ def test_philox_mode_equals_replay_of_its_own_draws_merton_random_parameters(cud
 def test_merton_walks_agree_per_path(cuda_lib, tmp_path):
     """The block-uniform (ring of records per thread), the event-driven (lane queues) and the batch (records of a
     whole warp dealt out one per lane) Merton walks consume the same draws through the same arithmetic: per-path
-    payoffs are identical bit for bit, whatever the length of the event-driven walk's advance phase."""
+    payoffs are identical bit for bit, whatever the length of the event-driven walk's advance phase.  The factor
+    walk (the default for Euler-Maruyama, M = 2 | 4) consumes the same draws with the jump arithmetic in factor
+    form: the same payoffs to rounding (1e-12 relative), including the cases that need several record rounds
+    (lam*T = 12 and 40)."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for tag, env in (("uniform", {"MLMCB_MJD_FLAT_BELOW": "0"}),
+    for tag, env in (("factor", {}),
+                     ("uniform", {"MLMCB_MJD_FLAT_BELOW": "0", "MLMCB_MJD_WALK": "uniform"}),
                      ("event", {"MLMCB_MJD_FLAT_BELOW": "1000000", "MLMCB_MJD_WALK": "event"}),
                      ("batch", {"MLMCB_MJD_FLAT_BELOW": "1000000", "MLMCB_MJD_WALK": "batch"}),
                      ("event_run1", {"MLMCB_MJD_FLAT_BELOW": "1000000", "MLMCB_MJD_WALK": "event", "MLMCB_MJD_RUN_BLOCKS": "1"}),
@@ -597,6 +601,11 @@ def test_merton_walks_agree_per_path(cuda_lib, tmp_path):
     for tag in ("event", "batch", "event_run1", "event_run3"):
         for k, v in res["uniform"].items():
             assert np.array_equal(v, res[tag][k]), (tag, k, np.abs(v - res[tag][k]).max())
+    differ = 0
+    for k, v in res["uniform"].items():
+        np.testing.assert_allclose(res["factor"][k], v, rtol=1e-12, atol=1e-10, err_msg=k)
+        differ += int(not np.array_equal(res["factor"][k], v))
+    assert differ > 0       # the factor walk did run (its rounding is its own)
 
 
 def test_merton_without_jumps_is_gbm(cuda_lib):

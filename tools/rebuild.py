@@ -1,0 +1,12 @@
+#!/usr/bin/env python
+"""Rebuild only some translation units of libmlmcb.so (kernel work): python tools/rebuild.py family5_s1.o family4_s1.o ..."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from multilevel_mc_sdes_b200 import build as b  # noqa: E402
+
+t0 = time.time()
+b.compile_lib(b.LIB, only=sys.argv[1:] or None, verbose="-v" in sys.argv)
+print(f"rebuilt {sys.argv[1:] or 'all'} in {time.time() - t0:.0f} s")
