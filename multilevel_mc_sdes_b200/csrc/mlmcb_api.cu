@@ -434,7 +434,7 @@ int host_side(int dev, HostSide** out) {
 // Relative cost of one path in SMSP cycles per warp (profiles/r0*_gbm_levels.txt, r0*_merton_levels.txt): only the
 // proportions matter - they decide how many blocks of the launch each level gets; the block scheduler evens
 // out what the model gets wrong because the grid is several waves deep.
-double path_cost(int model, bool f64, ull nsteps, double lamT) {
+double path_cost(int model, bool f64, ull nsteps, double lamT, bool factor) {
     const double step = f64 ? 80.0 : 38.0, n = (double)nsteps;
     if (model == MLMCB_GBM) {
         if (nsteps == 1) return f64 ? 260.0 : 130.0;
@@ -443,6 +443,8 @@ double path_cost(int model, bool f64, ull nsteps, double lamT) {
     }
     const double event = (f64 ? 1600.0 : 800.0) * (lamT + 1.0);
     if (nsteps == 1) return event;
+    // factor walk: arrivals + records per path, then steps whose extra cost falls with the share of jump-free octets
+    if (factor) return (f64 ? 1000.0 : 850.0) * (lamT + 1.0) + step * n * (1.04 + 0.7 * lamT * exp(-n / 100.0));
     if (nsteps < flat_below()) return 1.3 * event + 2.5 * step * n;
     return 6.0 * event + 1.05 * step * n;
 }
@@ -488,7 +490,8 @@ int sweep_fused(const mlmcb_params* p, int model, int payoff, int M, int n_level
             S.kind[j] = (mjd_use_factor(flags, mt, C->nsteps) && !legacy) ? SK_MJD_FACTOR
                         : C->nsteps < flat_below() ? SK_MJD_FLAT : SK_MJD_UNIFORM;
         }
-        cost[j] = (double)n_paths[i] * path_cost(model, f64, C->nsteps, model == MLMCB_MERTON ? p->lam * p->T : 0.0);
+        cost[j] = (double)n_paths[i] * path_cost(model, f64, C->nsteps, model == MLMCB_MERTON ? p->lam * p->T : 0.0,
+                                                 S.kind[j] == SK_MJD_FACTOR);
         total += cost[j];
         if (C->nsteps >= 64) total_long += cost[j];
         const ull threads = (n_paths[i] + per_thread - 1) / per_thread + (per_thread > 1 ? 1 : 0);

@@ -62,6 +62,9 @@
 #ifndef MLMCB_UNROLL_FW
 #define MLMCB_UNROLL_FW 1           // Merton factor walk: jump-free octets in flight per thread (2 measured equal at 128 registers)
 #endif
+#ifndef MLMCB_FW_SLOTS
+#define MLMCB_FW_SLOTS 128          // Merton factor walk: record slots per warp
+#endif
 #ifndef MLMCB_PHILOX_ROUNDS
 #define MLMCB_PHILOX_ROUNDS 10      // experiments only; the shipped library is Philox4x32-10
 #endif
@@ -1541,7 +1544,7 @@ struct BatchStore {
     unsigned short work[kBatchSlots];           // work list of the record phase: owner lane | k << 5
 };
 
-constexpr size_t kFwStoreBytes = 8 * 32 * 8 + 6 * 128 * 8 + 128 * 4 + 128 * 2;    // sizeof(FwStore<FN_AVG>), the factor walk's store (below)
+constexpr size_t kFwStoreBytes = 8 * 32 * 8 + 6 * MLMCB_FW_SLOTS * 8 + MLMCB_FW_SLOTS * 4 + MLMCB_FW_SLOTS * 2;    // sizeof(FwStore<FN_AVG>), the factor walk's store (below)
 constexpr size_t kMjdSharedWarp = sizeof(BatchStore) > kFwStoreBytes ? sizeof(BatchStore) : kFwStoreBytes;
 constexpr size_t kMjdSharedBytes = kMjdSharedWarp * (kThreads / 32) > sizeof(double) * kJumpRecs * REC_FIELDS * kThreads
                                        ? kMjdSharedWarp * (kThreads / 32) : sizeof(double) * kJumpRecs * REC_FIELDS * kThreads;
@@ -1674,7 +1677,8 @@ mjd_flat_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigne
 // only (products of factors instead of increments: ~1e-15 relative).
 // ------------------------------------------------------------------------------------------
 constexpr int kFwKmax = 8;              // arrivals per path and round
-constexpr int kFwSlots = 128;           // record slots per warp, sentinels included (32 * (3 + 1) always fits)
+constexpr int kFwSlots = MLMCB_FW_SLOTS; // record slots per warp, sentinels included
+constexpr uint32_t kFwCap = kFwSlots / 32 - 1;   // records per lane and round that always fit (with the sentinels)
 enum { FW_T1 = 0, FW_J, FW_RHO, FW_KAPPA, FW_D1, FW_D2 };
 template <int FN>
 struct FwStore {
@@ -1885,7 +1889,7 @@ __device__ __forceinline__ void mjd_factor_body(const LevelConsts& C, unsigned b
                 }
             }
             // ---- slots: n records and a sentinel per lane; three records per lane always fit ----
-            if (__reduce_add_sync(FULL, n + 1u) > (uint32_t)kFwSlots && n > 3u) { n = 3u; more = true; }
+            if (__reduce_add_sync(FULL, n + 1u) > (uint32_t)kFwSlots && n > kFwCap) { n = kFwCap; more = true; }
             uint32_t base = n + 1u, wbase = n;  // inclusive scans -> exclusive below
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
