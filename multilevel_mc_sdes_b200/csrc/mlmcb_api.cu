@@ -135,8 +135,7 @@ int make_consts(const mlmcb_params* p, int model, int payoff, int l, int M, ull 
     C->inv_sqrt_dt = 1.0 / C->sqrt_dt;
     C->run_blocks = run_blocks_for(C->nsteps);
     // table-driven fp64 Box-Muller (tools/gen_f64bm_tables.py): G(x) = x + x^2 Q(x); sin(pi d)/d and (cos(pi d) - 1)/d^2 in d^2
-    static const double lq[5] = {0x1.0000000000000p-2, 0x1.55555555279e5p-4, 0x1.ffffffffafffbp-6, 0x1.999b07519179fp-7,
-                                 0x1.5556955655562p-8};
+    static const double lq[5] = {0x1.fffffffffeaabp-3, 0x1.555555555430cp-4, 0x1.00002aaab1aabp-5, 0x1.9999e2be38548p-7, 0.0};
     static const double ts[3] = {0x1.921fb54442d18p+1, -0x1.4abbce625a8c0p+2, 0x1.466ba9b398947p+1};
     static const double tc[2] = {-0x1.3bd3cc9be3b30p+2, 0x1.03c1db247a00ep+2};
     memcpy(C->lq, lq, sizeof lq); memcpy(C->ts, ts, sizeof ts); memcpy(C->tc, tc, sizeof tc);

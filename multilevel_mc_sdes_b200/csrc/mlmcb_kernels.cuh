@@ -238,13 +238,13 @@ __device__ __forceinline__ void bm_quad_f32(const LevelConsts& C, U4 w, float z[
 //           d = c*2^-40 - 2^-9 (32 bits), and bit 31 of a picks the half-plane (sign of r): 41 angle bits
 //   (z0, z1) = (r cos theta, r sin theta)
 // so three Philox4x32-10 blocks give four pairs = eight normals.  All arithmetic is fp64, about 1 ulp:
-//   -2 ln u = k(-2 ln2) + B_i + G(x),  u = 2^k m,  x = fma(m, A_i, 2) = -2(m/c_i - 1), G(x) = x + x^2 Q(x), |x| <= 2^-7,
-//             128-entry table (A_i, B_i); the interval that holds m = 1 is centred on it (c = 1, A = -2, B = 0), so
+//   -2 ln u = k(-2 ln2) + B_i + G(x),  u = 2^k m,  x = fma(m, A_i, 2) = -2(m/c_i - 1), G(x) = x + x^2 Q(x), |x| <= 2^-8,
+//             256-entry table (A_i, B_i), Q of degree 3; the interval that holds m = 1 is centred on it (c = 1, A = -2, B = 0), so
 //             x is exact there and u -> 1 keeps full relative accuracy;
-//   sqrt      reciprocal-root seed (MUFU.RSQ64H) and two residual corrections;
+//   sqrt      reciprocal-root seed (MUFU.RSQ64H) and one third-order correction;
 //   sin/cos   256-entry table (cos, sin)(pi h_j), the remainder pi*d by three-/two-term polynomials, one rotation.
-// 30 FP64-pipe instructions per pair (the round-1 table-free form - fdlibm log, degree-8 sin/cos - took 53).  The two
-// tables (6 KB) are copied to shared memory by every kernel that draws fp64 normals.  tools/gen_f64bm_tables.py
+// 28 FP64-pipe instructions per pair (the round-1 table-free form - fdlibm log, degree-8 sin/cos - took 53).  The two
+// tables (8 KB) are copied to shared memory by every kernel that draws fp64 normals.  tools/gen_f64bm_tables.py
 // generates tables and coefficients and checks the pair against 60-digit values (worst |z - exact| 1.3e-15 at
 // |z| = 8.6); tests/test_gpu_philox.py recomputes the device stream from the Philox words in numpy float64.
 
@@ -265,15 +265,15 @@ __device__ __forceinline__ double rsqrt64_seed(double x) {
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));      // MUFU.RSQ64H, ~2^-22
     return y;
 }
-struct F64TabSrc { double2 lg[128]; double2 tr[256]; };
+struct F64TabSrc { double2 lg[256]; double2 tr[256]; };
 static __device__ const F64TabSrc g_f64tab = {
 #include "mlmcb_f64tab.inc"
 };
-// In shared memory the 4 KB table comes first and starts on a 4 KB boundary of the shared WINDOW: both tables then
-// sit on a multiple of their own size, and "base + masked byte offset" is "base | masked offset" - folded into the
+// In shared memory the two 4 KB tables start on a 4 KB boundary of the shared WINDOW: each then
+// sits on a multiple of its own size, and "base + masked byte offset" is "base | masked offset" - folded into the
 // LOP3 that masks.  The boundary is found at run time inside a buffer 4 KB larger than the tables (the first user
 // variable of a block sits 1 KB into the window on this architecture, so `__align__` alone does not give it).
-struct F64Tab { double2 tr[256]; double2 lg[128]; };
+struct F64Tab { double2 tr[256]; double2 lg[256]; };
 __device__ __forceinline__ uint32_t f64tab_tr() {
     __shared__ __align__(16) unsigned char buf[sizeof(F64Tab) + 4096];
     return ((uint32_t)__cvta_generic_to_shared(buf) + 4095u) & ~4095u;
@@ -295,7 +295,7 @@ __device__ __forceinline__ void sampler_init() {
     if (SAMP == SAMP_F64BM) {
         const uint32_t tr = f64tab_tr(), lg = f64tab_lg();
         for (int i = threadIdx.x; i < 256; i += blockDim.x) sts_f64x2(tr + 16u * i, g_f64tab.tr[i]);
-        for (int i = threadIdx.x; i < 128; i += blockDim.x) sts_f64x2(lg + 16u * i, g_f64tab.lg[i]);
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) sts_f64x2(lg + 16u * i, g_f64tab.lg[i]);
         __syncthreads();
     }
 }
@@ -306,29 +306,28 @@ __device__ __forceinline__ double u52(const LevelConsts& C, uint32_t hi, uint32_
 // -2 ln u for a normal double u in (0,1)
 __device__ __forceinline__ double neg2_log_u(const LevelConsts& C, double u) {
     const int ix = __double2hiint(u);
-    const int tmp = ix - 0x3fe6b000;
+    const int tmp = ix - 0x3fe6b800;
     const int k = tmp >> 20;
     int mh;                                                                              // ix - (k << 20) as ONE IMAD
     asm("mad.lo.s32 %0, %1, -1048576, %2;" : "=r"(mh) : "r"(k), "r"(ix));
-    const double m = __hiloint2double(mh, __double2loint(u));                            // [0.70898, 1.41797)
-    const double2 e = lds_f64x2(and_or<0x7f0u>((uint32_t)tmp >> 9, f64tab_lg()));                    // lg[(tmp >> 13) & 127]
+    const double m = __hiloint2double(mh, __double2loint(u));                            // [0.70947, 1.41895)
+    const double2 e = lds_f64x2(and_or<0xff0u>((uint32_t)tmp >> 8, f64tab_lg()));                    // lg[(tmp >> 12) & 255]
     const double x = fma(m, e.x, 2.0);
     const double x2 = x * x;
-    double q = fma(x, C.lq[4], C.lq[3]);
-    q = fma(q, x, C.lq[2]);
+    double q = fma(x, C.lq[3], C.lq[2]);
     q = fma(q, x, C.lq[1]);
     q = fma(q, x, C.lq[0]);
     const double t = fma((double)k, C.neg2ln2, e.y);
     return t + fma(x2, q, x);
 }
-// sqrt(s), s > 0 normal: reciprocal-root seed y (2^-22), then two residual corrections g += (s - g*g)*(y/2); the
-// half-seed's own error only scales the correction, so the second pass lands at e*e1 ~ 2^-62 before the final rounding.
+// sqrt(s), s > 0 normal: reciprocal-root seed y (2^-22), g = s y, e = 1 - g y (exact to its own rounding), and
+// sqrt(s) = g (1 - e)^(-1/2) = g (1 + e/2 + 3 e^2/8) with a truncation of 5 e^3/16 < 2^-64: five instructions
+// (two residual corrections took six), < 1 ulp.
 __device__ __forceinline__ double sqrt_pos(double s) {
     const double y = rsqrt64_seed(s);
-    double g = s * y;
-    const double hy = 0.5 * y;
-    g = fma(fma(-g, g, s), hy, g);
-    return fma(fma(-g, g, s), hy, g);
+    const double g = s * y;
+    const double e = fma(-g, y, 1.0);
+    return fma(g * e, fma(0.375, e, 0.5), g);
 }
 // AFFINE = false: (z0, z1);  AFFINE = true: (a0 + b0*z0, a0 + b0*z1) - the Euler-Maruyama step factor, one multiply
 // per pair instead of one FMA per normal

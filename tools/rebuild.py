@@ -8,5 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from multilevel_mc_sdes_b200 import build as b  # noqa: E402
 
 t0 = time.time()
-b.compile_lib(b.LIB, only=sys.argv[1:] or None, verbose="-v" in sys.argv)
+only = [a for a in sys.argv[1:] if a != "-v"]
+b.compile_lib(b.LIB, only=only or None, verbose="-v" in sys.argv)
+b.write_sass_mix()
 print(f"rebuilt {sys.argv[1:] or 'all'} in {time.time() - t0:.0f} s")
