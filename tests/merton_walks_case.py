@@ -10,11 +10,12 @@ import multilevel_mc_sdes_b200 as mm
 out = {}
 for cname in ("Euro_Merton", "Asian_Merton", "Lookback_Merton", "Digital_Merton"):
     for l, M, kw in ((1, 2, {}), (2, 2, {}), (3, 2, {}), (2, 4, {}), (2, 3, {}), (6, 2, {"lam": 5.0}), (3, 4, {"scheme": "milstein"}),
-                     (3, 2, {"lam": 40.0}), (8, 2, {"lam": 12.0})):        # many more jumps than records kept ahead
+                     (3, 2, {"lam": 40.0}), (8, 2, {"lam": 12.0}),         # many more jumps than records kept ahead
+                     (2, 2, {"lam": 300.0, "jumpstd": 0.02, "jumpmean": -0.0002})):   # dozens of record rounds inside one fine step
         for sampler in ("f64bm", "f32bm"):
             opt = getattr(mm, cname)(seed=23, sampler=sampler, **kw)
             opt._next_path[l] = 77
-            Pf, Pc = opt.payoff(4099, l, M)
+            Pf, Pc = opt.payoff(4099 if kw.get("lam", 1.0) < 100 else 515, l, M)
             key = f"{cname}_{l}_{M}_{sorted(kw.items())}_{sampler}"
             out[key + "_f"] = Pf
             out[key + "_c"] = Pc
