@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-level cost table of one product: ms per 2^22 samples and SMSP cycles per warp-path for l = 0..Lmax.
+"""Per-level cost table of one product: ms per launch and SMSP cycles per warp-path for l = 0..Lmax.
 
     python tools/level_times.py --cls Digital_Merton --M 2 --Lmax 8 [--flags 0]
 """
@@ -18,15 +18,15 @@ ap.add_argument("--cls", default="Digital_Merton")
 ap.add_argument("--M", type=int, default=2)
 ap.add_argument("--Lmax", type=int, default=8)
 ap.add_argument("--flags", type=int, default=0)
-ap.add_argument("--n", type=float, default=float(1 << 24))
+ap.add_argument("--n", type=float, default=0.0, help="samples per launch; default: 2^32 / steps clamped to [2^24, 2^30]")
 a = ap.parse_args()
 lib = _lib.load()
 opt = getattr(mm, a.cls)()
 p = opt._params()
 out = torch.zeros(7, dtype=torch.float64, device="cuda")
-n = int(a.n)
 st = torch.cuda.current_stream().cuda_stream
 for l in range(a.Lmax + 1):
+    n = int(a.n) if a.n else max(1 << 24, min(1 << 30, (1 << 32) // a.M ** l))
     best = 1e9
     for r in range(4):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
