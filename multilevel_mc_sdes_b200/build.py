@@ -91,7 +91,7 @@ def write_sass_mix():
         unroll64 = int(re.search(r"#define MLMCB_UNROLL_F64 (\d+)", hdr).group(1))
         # fp32 sampler: four steps per draw block; fp64 sampler: eight (an octet of three Philox blocks)
         out = {k: sass_mix.hot_loop_mix(LIB, pat, 4 * unroll if k == "f32bm" else 8 * unroll64) for k, pat in
-               (("f32bm", "level_kernel<double, 0, 0, 4, 0, 0, false>"), ("f64bm", "level_kernel<double, 0, 0, 4, 1, 0, false>"))}
+               (("f32bm", "level_kernel<double, 0, 0, 4, 0, 0, 0>"), ("f64bm", "level_kernel<double, 0, 0, 4, 1, 0, 2>"))}
         json.dump(out, open(os.path.join(CSRC, "sass_mix.json"), "w"), indent=1)
     except Exception as e:  # cuobjdump missing: not fatal
         sys.stderr.write(f"sass_mix skipped: {e}\n")

@@ -185,6 +185,9 @@ LevelKernel pick_kernel(int model, int payoff, int M, int flags, ull nsteps) {
         // the coarsest levels have kernels of their own: 1 or 2 fine steps, and 4 (M = 4, l = 1 / M = 2, l = 2)
         const int packed = nsteps <= 2 ? 1 : (nsteps == 4 && M == 4) ? 4 : (nsteps == 4 && M == 2) ? -4 : 0;
         if (packed) return f64 ? pick_gbm_packed_s<1>(fn, flags, packed) : pick_gbm_packed_s<0>(fn, flags, packed);
+        // long paths with the default sampler: the software-pipelined build of the same loop
+        if (f64 && mt != 0 && !(flags & (MLMCB_MILSTEIN | MLMCB_FP32_PATHS)) && nsteps >= (ull)MLMCB_PIPE_FROM && (nsteps & 7) == 0)
+            return pick_gbm_long_s<1>(fn, mt);
         return f64 ? pick_gbm_s<1>(fn, mt, flags) : pick_gbm_s<0>(fn, mt, flags);
     }
     static const char* force = getenv("MLMCB_MJD_WALK");                 // "batch" | "event" | "legacy": tuning and the walk-agreement test

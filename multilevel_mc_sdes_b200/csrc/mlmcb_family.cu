@@ -26,6 +26,13 @@ struct GbmPacked {      // one, two or four fine steps per path: the coarseness 
     template <typename R, int FN, int MT, int SAMP, int SCH>
     static LevelKernel get() { return gbm_packed_kernel<R, FN, SAMP, SCH, NS>; }
 };
+struct GbmLong {        // fp64 sampler, Euler-Maruyama, fp64 paths, M = 2 | 4: software-pipelined octets
+    template <typename R, int FN, int MT, int SAMP, int SCH>
+    static LevelKernel get() {
+        if constexpr (SAMP == SAMP_F64BM && sizeof(R) == 8 && SCH == SCH_EM && MT != 0) return level_kernel<R, 0, FN, MT, SAMP, SCH, 2>;
+        else return nullptr;
+    }
+};
 struct GbmAnti {
     template <typename R, int FN, int MT, int SAMP, int SCH>
     static LevelKernel get() { return FN == FN_MIN ? nullptr : level_anti_kernel<R, FN == FN_MIN ? FN_FINAL : FN, MT, SAMP, SCH>; }
@@ -55,6 +62,7 @@ template <> LevelKernel pick_gbm_packed_s<S>(int fn, int flags, int nsteps) {
     if (nsteps == -4) return pick_family<GbmPacked<-4>, S>(fn, 2, flags);
     return pick_family<GbmPacked<0>, S>(fn, 0, flags);
 }
+template <> LevelKernel pick_gbm_long_s<S>(int fn, int mt) { return pick_family<GbmLong, S>(fn, mt, 0); }
 template <> LevelKernel pick_gbm_anti_s<S>(int fn, int mt, int flags) { return pick_family<GbmAnti, S>(fn, mt, flags); }
 #elif MLMCB_TU_FAMILY == 1
 template <> LevelKernel pick_merton_uniform_s<S>(int fn, int mt, int flags) { return pick_family<MertonUniform, S>(fn, mt, flags); }

@@ -65,6 +65,12 @@
 #ifndef MLMCB_FW_SLOTS
 #define MLMCB_FW_SLOTS 128          // Merton factor walk: record slots per warp
 #endif
+#ifndef MLMCB_PIPE_G
+#define MLMCB_PIPE_G 2             // octets per stage of the software-pipelined fp64 GBM loop (the long-path kernel)
+#endif
+#ifndef MLMCB_PIPE_FROM
+#define MLMCB_PIPE_FROM 1024       // fine steps from which GBM levels take the long-path kernel (64 steps: 20 % slower, 256: equal, 1024+: 2-3 % faster)
+#endif
 #ifndef MLMCB_PHILOX_ROUNDS
 #define MLMCB_PHILOX_ROUNDS 10      // experiments only; the shipped library is Philox4x32-10
 #endif
@@ -418,12 +424,22 @@ struct PhiloxSource {
     }
     // the octet o as Euler-Maruyama step factors t_i = a0 + b0*z_i (fp64 sampler, fp64 paths)
     __device__ __forceinline__ void load8_affine(uint32_t o, double t[8], double a0, double b0) const {
-        const U4 r = philox_at(C, pid, STREAM_GRID, 3u * o), s = philox_at(C, pid, STREAM_GRID, 3u * o + 1u),
-                 u = philox_at(C, pid, STREAM_GRID, 3u * o + 2u);
-        bm_pair_f64<true>(C, r.x, r.y, r.z, t[0], t[1], a0, b0);
-        bm_pair_f64<true>(C, r.w, s.x, s.y, t[2], t[3], a0, b0);
-        bm_pair_f64<true>(C, s.z, s.w, u.x, t[4], t[5], a0, b0);
-        bm_pair_f64<true>(C, u.y, u.z, u.w, t[6], t[7], a0, b0);
+        U4 w[3];
+        words8(o, w);
+        affine8(w, t, a0, b0);
+    }
+    // the same in two halves - the integer half (three Philox blocks) and the FP64 half (four pairs) - so that a
+    // loop can draw the words of its NEXT octets next to the floating-point work of the current ones
+    __device__ __forceinline__ void words8(uint32_t o, U4 w[3]) const {
+        w[0] = philox_at(C, pid, STREAM_GRID, 3u * o);
+        w[1] = philox_at(C, pid, STREAM_GRID, 3u * o + 1u);
+        w[2] = philox_at(C, pid, STREAM_GRID, 3u * o + 2u);
+    }
+    __device__ __forceinline__ void affine8(const U4 w[3], double t[8], double a0, double b0) const {
+        bm_pair_f64<true>(C, w[0].x, w[0].y, w[0].z, t[0], t[1], a0, b0);
+        bm_pair_f64<true>(C, w[0].w, w[1].x, w[1].y, t[2], t[3], a0, b0);
+        bm_pair_f64<true>(C, w[1].z, w[1].w, w[2].x, t[4], t[5], a0, b0);
+        bm_pair_f64<true>(C, w[2].y, w[2].z, w[2].w, t[6], t[7], a0, b0);
     }
 };
 
@@ -586,7 +602,7 @@ struct StepCoef {
 // Returns the path outputs the reference path function returns: terminal values (FN_FINAL),
 // averages (FN_AVG) or terminal values + minima (FN_MIN).
 // ------------------------------------------------------------------------------------------
-template <typename R, int FN, int MT, int SCH, typename Source, int UNROLL = Source::kUnroll>
+template <typename R, int FN, int MT, int SCH, typename Source, int UNROLL = Source::kUnroll, bool PIPE = false>
 __device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source& src,
                                               double& vf, double& vc, double& gf, double& gc) {
     if constexpr (Source::kOctets && sizeof(R) == 8 && SCH == SCH_EM && (MT == 2 || MT == 4)) {
@@ -597,8 +613,58 @@ __device__ __forceinline__ void gbm_path_fast(const LevelConsts& C, const Source
             double Xf = C.X0, Xc = C.X0;
             double Ff = FN == FN_MIN ? C.X0 : 0.0, Fc = Ff;
             const uint32_t noct = (uint32_t)(C.nsteps >> 3);
+            // PIPE (the long-path build: its own kernel, so that the plain loop's register allocation does not move):
+            // software pipeline - the Philox words of the next group of octets are drawn (integer pipes) in the same
+            // loop body as the Box-Muller pairs and steps of the current group (FP64 pipe); ptxas otherwise runs all
+            // twelve Philox blocks of an iteration first and the FP64 work after them, and IMAD.WIDE + LOP3 pairs cost
+            // 3.2 cycles where DFMA + LOP3 cost 2.4 (bench.py pipe_probe)
+            constexpr int G = MLMCB_PIPE_G;
+            uint32_t o0 = 0;            // octets done by the pipelined loop; what is left takes the plain one
+            if constexpr (PIPE) {
+              if (noct >= 2 * G) {
+                const uint32_t npipe = noct - noct % (2 * G);
+                U4 wa[G][3], wb[G][3];
+#pragma unroll
+                for (int q = 0; q < G; ++q) src.words8(q, wa[q]);
+                auto consume = [&](const U4 (&w)[G][3]) {
+#pragma unroll
+                    for (int q = 0; q < G; ++q) {
+                        double t[8];
+                        src.affine8(w[q], t, C.a_f, C.b_f);
+#pragma unroll
+                        for (int g = 0; g < 8; g += MT) {
+                            const double tc = MT == 4 ? (t[g] + t[g + 1]) + (t[g + 2] + t[g + 3]) : t[g] + t[g + 1];
+#pragma unroll
+                            for (int k = 0; k < MT; ++k) {
+                                Xf = fma(Xf, t[g + k], Xf);
+                                if (FN == FN_AVG) Ff += Xf;
+                                if (FN == FN_MIN) Ff = min_<double>(Ff, Xf);
+                            }
+                            Xc = fma(Xc, tc, Xc);
+                            if (FN == FN_AVG) Fc += Xc;
+                            if (FN == FN_MIN) Fc = min_<double>(Fc, Xc);
+                        }
+                    }
+                };
+                uint32_t o = 0;
+#pragma unroll 1
+                for (; o + 2 * G < npipe; o += 2 * G) {
+#pragma unroll
+                    for (int q = 0; q < G; ++q) src.words8(o + G + q, wb[q]);
+                    consume(wa);
+#pragma unroll
+                    for (int q = 0; q < G; ++q) src.words8(o + 2 * G + q, wa[q]);
+                    consume(wb);
+                }
+#pragma unroll
+                for (int q = 0; q < G; ++q) src.words8(o + G + q, wb[q]);                // the last pass draws nothing past the end
+                consume(wa);
+                consume(wb);
+                o0 = npipe;
+              }
+            }
 #pragma unroll UNROLL
-            for (uint32_t o = 0; o < noct; ++o) {
+            for (uint32_t o = o0; o < noct; ++o) {
                 double t[8];
                 src.load8_affine(o, t, C.a_f, C.b_f);
 #pragma unroll
@@ -2402,8 +2468,9 @@ gbm_packed_kernel(const __grid_constant__ LevelConsts C, double* partials, unsig
 }
 
 
-// SHORT (fp64-sampler GBM only): the sweep kernel's build - one draw block in flight, fewer registers
-template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH, bool SHORT = false>
+// VAR (fp64-sampler GBM only): 1 = the sweep kernel's build - one draw block in flight, fewer registers;
+// 2 = the long-path build - software-pipelined octets (gbm_path_fast PIPE)
+template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH, int VAR = 0>
 __device__ __forceinline__ void level_body(const LevelConsts& C, unsigned bid, unsigned nblk, Sums7& acc,
                                            double* Pf_out, double* Pc_out) {
     const ull stride = (ull)nblk * blockDim.x;
@@ -2413,7 +2480,7 @@ __device__ __forceinline__ void level_body(const LevelConsts& C, unsigned bid, u
         double vf, vc, gf, gc;
         if (MODEL == 0) {
             PhiloxSource<R, SAMP> src{C, pid};
-            gbm_path_fast<R, FN, MT, SCH, PhiloxSource<R, SAMP>, SHORT ? 1 : PhiloxSource<R, SAMP>::kUnroll>(C, src, vf, vc, gf, gc);
+            gbm_path_fast<R, FN, MT, SCH, PhiloxSource<R, SAMP>, VAR == 1 ? 1 : PhiloxSource<R, SAMP>::kUnroll, VAR == 2>(C, src, vf, vc, gf, gc);
         } else {
             mjd_path_philox<R, FN, MT, SAMP, SCH>(C, pid, rec, vf, vc, gf, gc);
         }
@@ -2421,15 +2488,15 @@ __device__ __forceinline__ void level_body(const LevelConsts& C, unsigned bid, u
     }
 }
 
-template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH, bool SHORT = false>
-__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? (MODEL == 0 ? (SHORT ? MLMCB_MINBLOCKS_F64_SHORT : MLMCB_MINBLOCKS_F64) : MLMCB_MINBLOCKS_F64_MJD)
+template <typename R, int MODEL, int FN, int MT, int SAMP, int SCH, int VAR = 0>
+__global__ void __launch_bounds__(kThreads, (SAMP != SAMP_F32BM) ? (MODEL == 0 ? (VAR == 1 ? MLMCB_MINBLOCKS_F64_SHORT : MLMCB_MINBLOCKS_F64) : MLMCB_MINBLOCKS_F64_MJD)
                                                                 : (MODEL == 0 ? MLMCB_MINBLOCKS : MLMCB_MINBLOCKS_MJD))
 level_kernel(const __grid_constant__ LevelConsts C, double* partials, unsigned* ticket,
              double* out7, double* Pf_out, double* Pc_out) {
     sampler_init<SAMP>();
     Sums7 acc;
     acc.clear();
-    level_body<R, MODEL, FN, MT, SAMP, SCH, SHORT>(C, blockIdx.x, gridDim.x, acc, Pf_out, Pc_out);
+    level_body<R, MODEL, FN, MT, SAMP, SCH, VAR>(C, blockIdx.x, gridDim.x, acc, Pf_out, Pc_out);
     grid_finish(acc, partials, ticket, out7);
 }
 
@@ -2468,7 +2535,7 @@ sweep_kernel(const __grid_constant__ SweepConsts S, double* partials, unsigned* 
         const int kind = S.kind[k];
         if (kind == SK_PACKED) gbm_packed_body<R, FN, SAMP, SCH, 0>(C, bid, nblk, acc, nullptr, nullptr);
         else if (MT != 0 && kind == SK_FOUR) gbm_packed_body<R, FN, SAMP, SCH, MT == 4 ? 4 : -4>(C, bid, nblk, acc, nullptr, nullptr);
-        else level_body<R, 0, FN, MT, SAMP, SCH, true>(C, bid, nblk, acc, nullptr, nullptr);
+        else level_body<R, 0, FN, MT, SAMP, SCH, 1>(C, bid, nblk, acc, nullptr, nullptr);
     } else {
         if (S.kind[k] == SK_MJD_FACTOR) {
             if constexpr (sizeof(R) == 8 && SCH == SCH_EM && MT != 0) mjd_factor_body<FN, MT, SAMP>(C, bid, nblk, acc, nullptr, nullptr);

@@ -60,6 +60,7 @@ SweepKernel pick_sweep(int fn, int mt, int flags) {
 template <int SAMP> LevelKernel pick_gbm_s(int fn, int mt, int flags);
 template <int SAMP> LevelKernel pick_gbm_packed_s(int fn, int flags, int nsteps);   // paths of 1, 2 or 4 fine steps
 template <int SAMP> LevelKernel pick_gbm_anti_s(int fn, int mt, int flags);         // antithetic triple (Euro/Asian)
+template <int SAMP> LevelKernel pick_gbm_long_s(int fn, int mt);                    // long paths, fp64 sampler (nullptr otherwise)
 template <int SAMP> LevelKernel pick_merton_uniform_s(int fn, int mt, int flags);
 template <int SAMP> LevelKernel pick_merton_flat_s(int fn, int mt, int flags, bool batch);   // batch: the batch walk
 template <int SAMP> LevelKernel pick_merton_factor_s(int fn, int mt);                        // MLMCB_TU_FAMILY 5: factor walk (EM, fp64 paths, mt 2 | 4)
