@@ -916,6 +916,54 @@ __global__ void __launch_bounds__(256) pipe_probe_kernel(float seed, unsigned* s
     if (acc == 0x12345u) sink[0] = acc;
 }
 
+// The headline loop's instruction mix per fine step (16 FP64, 6 IMAD.WIDE, ~15 INT32) issued two ways, on independent
+// chains so that only the pipes and the issue port limit it:
+//   MODE 0  every warp issues the whole mix, finely interleaved (what a perfect single-stream schedule could reach);
+//   MODE 1  warp-specialised: of every three warps two issue the FP64 part (+ 8 INT32) and one issues the Philox part
+//           (12 IMAD.WIDE + 14 INT32 = the draws of both) - the scheduler interleaves them at issue time.
+// One block per SM; MODE 0: 8 warps (two per SMSP), MODE 1: 12 warps (two FP64 + one Philox warp per SMSP).
+template <int MODE>
+__global__ void __launch_bounds__(384) mix_probe_kernel(float seed, unsigned* sink, int iters) {
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, warp = threadIdx.x >> 5;
+    double d[16];
+    unsigned u[16];
+    unsigned long long w[12];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { d[c] = 1.0 + 1e-9 * (tid + c); u[c] = tid * 2654435761u + c; }
+#pragma unroll
+    for (int c = 0; c < 12; ++c) w[c] = u[c];
+    const double da = 1.0000000001, db = 1e-12;
+    const bool philox_warp = MODE == 1 && warp >= 8;
+    for (int it = 0; it < iters; ++it) {
+        if (MODE == 0) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                d[c] = fma(d[c], da, db);
+                if (c < 15) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[c]) : "r"(tid), "r"(0x9E3779B9u + it));
+                if (c < 6) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"((unsigned)w[c]), "r"(0xD2511F53u));
+            }
+        } else if (!philox_warp) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                d[c] = fma(d[c], da, db);
+                if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[c]) : "r"(tid), "r"(0x9E3779B9u + it));
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 14; ++c) {
+                if (c < 12) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"((unsigned)w[c]), "r"(0xD2511F53u));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[c]) : "r"(tid), "r"(0x9E3779B9u + it));
+            }
+        }
+    }
+    unsigned acc = 0;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc ^= (unsigned)d[c] ^ u[c];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) acc ^= (unsigned)w[c];
+    if (acc == 0x12345u) sink[0] = acc;
+}
+
 typedef void (*ProbeKernel)(float, unsigned*);
 ProbeKernel probe_of(int which) {
     switch (which) {
@@ -939,6 +987,35 @@ ProbeKernel probe_of(int which) {
 }
 
 }  // namespace
+
+// milliseconds of `iters` passes of the mix probe on every SM (one block each)
+extern "C" int mlmcb_mix_probe(int mode, int device, int iters, float* ms_out) {
+    DeviceGuard g(device);
+    if (!g.ok) return fail(MLMCB_ECUDA, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    DeviceInfo* d;
+    if (int rc = device_info(device, &d)) return rc;
+    unsigned* sink = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float ms = 0;
+    cudaError_t e = cudaMalloc((void**)&sink, 4);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    for (int rep = 0; rep < 2 && e == cudaSuccess; ++rep) {
+        if (rep) e = cudaEventRecord(e0);
+        if (mode == 0) mix_probe_kernel<0><<<d->sms, 256>>>(1e-7f, sink, iters);
+        else mix_probe_kernel<1><<<d->sms, 384>>>(1e-7f, sink, iters);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(e1);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (sink) cudaFree(sink);
+    if (e != cudaSuccess) return fail(MLMCB_ECUDA, "mix probe failed: %s", cudaGetErrorString(e));
+    if (ms_out) *ms_out = ms;
+    return 0;
+}
 
 extern "C" int mlmcb_pipe_probe(int which, int device, double* inst_per_s, float* ms_out) {
     ProbeKernel k = probe_of(which);
