@@ -867,8 +867,10 @@ __global__ void __launch_bounds__(256) pipe_probe_kernel(float seed, unsigned* s
     float f[kProbeChains];
     unsigned u[kProbeChains];
     unsigned long long w[kProbeChains];
+    unsigned f2u[kProbeChains];
 #pragma unroll
     for (int c = 0; c < kProbeChains; ++c) {
+        f2u[c] = tid + 3 * c;
         d[c] = 1.0 + 1e-9 * (tid + c); f[c] = 1.0f + seed * (tid + c); u[c] = tid * 2654435761u + c; w[c] = u[c];
     }
     const double da = 1.0000000001, db = 1e-12;
@@ -906,13 +908,24 @@ __global__ void __launch_bounds__(256) pipe_probe_kernel(float seed, unsigned* s
                 } else if (WHICH == 14) {    // IMAD (32-bit multiply-add, not wide) + DFMA
                     d[c] = fma(d[c], da, db);
                     asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(u[c]) : "r"(0x9E3779B1u), "r"(tid));
+                } else if (WHICH == 15) {    // IMAD.HI (high half of a 32x32 multiply)
+                    asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(u[c]) : "r"(0xD2511F53u), "r"(tid));
+                } else if (WHICH == 16) {    // DFMA + IMAD.HI
+                    d[c] = fma(d[c], da, db);
+                    asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(u[c]) : "r"(0xD2511F53u), "r"(tid));
+                } else if (WHICH == 17) {    // IMAD.HI + LOP3
+                    asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(u[c]) : "r"(0xD2511F53u), "r"(tid));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(f2u[c]) : "r"(tid), "r"(0x9E3779B9u + it));
+                } else if (WHICH == 18) {    // IMAD.HI + IMAD (both halves as two instructions)
+                    asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(f2u[c]) : "r"(u[c]), "r"(0xD2511F53u), "r"(tid));
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(u[c]) : "r"(0xD2511F53u), "r"(f2u[c]));
                 }
             }
         }
     }
     unsigned acc = 0;
 #pragma unroll
-    for (int c = 0; c < kProbeChains; ++c) acc ^= (unsigned)d[c] ^ __float_as_uint(f[c]) ^ u[c] ^ (unsigned)w[c];
+    for (int c = 0; c < kProbeChains; ++c) acc ^= (unsigned)d[c] ^ __float_as_uint(f[c]) ^ u[c] ^ (unsigned)w[c] ^ f2u[c];
     if (acc == 0x12345u) sink[0] = acc;
 }
 
@@ -982,6 +995,10 @@ ProbeKernel probe_of(int which) {
     case 12: return pipe_probe_kernel<12>;
     case 13: return pipe_probe_kernel<13>;
     case 14: return pipe_probe_kernel<14>;
+    case 15: return pipe_probe_kernel<15>;
+    case 16: return pipe_probe_kernel<16>;
+    case 17: return pipe_probe_kernel<17>;
+    case 18: return pipe_probe_kernel<18>;
     default: return nullptr;
     }
 }
@@ -1047,7 +1064,7 @@ extern "C" int mlmcb_pipe_probe(int which, int device, double* inst_per_s, float
     if (sink) cudaFree(sink);
     if (e != cudaSuccess) return fail(MLMCB_ECUDA, "pipe probe failed: %s", cudaGetErrorString(e));
     // F2F probe issues two conversions per chain step, the mixes two instructions
-    const double per_step = (which == 7 || which >= 9) ? 2.0 : 1.0;
+    const double per_step = (which == 7 || (which >= 9 && which != 15)) ? 2.0 : 1.0;
     const double warp_insts = (double)grid * (threads / 32) * kProbeIters * kProbeUnroll * kProbeChains * per_step;
     if (inst_per_s) *inst_per_s = warp_insts / (ms * 1e-3);
     if (ms_out) *ms_out = ms;
