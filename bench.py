@@ -332,7 +332,7 @@ def run_b200(args):
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture of this
                 # kernel (profiles/r02_ncu_gbm_euro_f64bm.txt, r01_ncu_gbm_euro_f32bm.txt): kernel image, constants and
                 # the sampler tables; the kernel reads no data and its 56-byte result stays in L2
-                "traffic": {"f64bm": 123904, "f32bm": 71680}.get(main_s)}
+                "traffic": {"f64bm": 154112, "f32bm": 71680}.get(main_s)}
     try:
         mix = json.load(open(os.path.join(ROOT, "multilevel_mc_sdes_b200", "csrc", "sass_mix.json")))[main_s]
         inst = mix["inst_per_4_steps"] / 4.0
