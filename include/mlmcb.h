@@ -152,8 +152,8 @@ int mlmcb_sampler_probe(int sampler, uint64_t seed, int l, uint64_t path_offset,
 int mlmcb_packed_probe(int sampler, uint64_t seed, int l, int n_steps, uint64_t path_offset, uint64_t n_paths,
                        int device, void* cuda_stream, double* d_out);
 /* The jump-stream records the Philox-mode Merton kernels use: d_out[3][n_records][n_paths] =
- * inter-arrival times (scaled by 1/lam), jump-size normals, Brownian normals of the sub-step ending at
- * each jump.  With mlmcb_sampler_probe this lets a test rebuild the exact draw streams of a Philox-mode
+ * inter-arrival times (scaled by 1/lam; fp64 sampler: two per Philox block of the gap stream), jump-size
+ * normals, Brownian normals of the sub-step ending at each jump (one block of the jump stream per record).  With mlmcb_sampler_probe this lets a test rebuild the exact draw streams of a Philox-mode
  * call and push them through the replay entry point.                                                */
 int mlmcb_jump_probe(int sampler, uint64_t seed, int l, double lam, uint64_t path_offset, uint64_t n_paths,
                      uint64_t n_records, int device, void* cuda_stream, double* d_out);
@@ -165,6 +165,12 @@ void mlmcb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t 
  * 14 DFMA+IMAD (the table behind "an INT32 instruction holds the dispatch port two cycles").
  * Returns warp-level instructions per second per GPU in *inst_per_s and the elapsed ms.      */
 int mlmcb_pipe_probe(int which, int device, double* inst_per_s, float* ms);
+/* 15 IMAD.HI, 16 DFMA+IMAD.HI, 17 IMAD.HI+LOP3, 18 IMAD.HI+IMAD complete the table (tools/pipe_probe.py).
+ * mlmcb_mix_probe: the headline loop's per-step instruction mix (16 FP64, 6 IMAD.WIDE, 15 INT32) on independent
+ * chains, `iters` passes on every SM.  mode 0: every warp issues the whole mix, finely interleaved (two warps per
+ * SMSP); mode 1: warp-specialised (two FP64 warps and one Philox warp per SMSP).  One pass is two warp-steps per SMSP
+ * in both modes; elapsed milliseconds in *ms (tools/mix_probe.py).                               */
+int mlmcb_mix_probe(int mode, int device, int iters, float* ms);
 /* Steps/sec the kernel's launch geometry: threads per block and resident blocks used.       */
 int mlmcb_launch_geometry(int model, int payoff, int M, int flags, int device,
                           int* threads_per_block, int* max_blocks);

@@ -57,6 +57,7 @@ SIGNATURES = {
     "mlmcb_jump_probe": (C.c_int, [C.c_int, _u64, C.c_int, C.c_double, _u64, _u64, _u64, C.c_int, _vp, _vp]),
     "mlmcb_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "mlmcb_pipe_probe": (C.c_int, [C.c_int, C.c_int, _dp, C.POINTER(C.c_float)]),
+    "mlmcb_mix_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "mlmcb_launch_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mlmcb_params_fill_derived": (None, [C.POINTER(Params)]),

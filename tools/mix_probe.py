@@ -9,7 +9,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from multilevel_mc_sdes_b200 import _lib  # noqa: E402
 
 lib = _lib.load()
-lib.mlmcb_mix_probe.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
 iters = 200000
 for mode, name in ((0, "every warp the whole mix (2 warps per SMSP)"), (1, "2 FP64 warps + 1 Philox warp per SMSP")):
     ms = C.c_float()
