@@ -1538,11 +1538,20 @@ __device__ __forceinline__ void mjd_flat_body(const LevelConsts& C, unsigned bid
                 const bool jump = tau < tend;                            // :457
                 const double d = (jump ? tau : tend) - t;                // :458 / :477
                 const R dW = zw * (R)(d > 0.0 ? sqrt_pos(d) : 0.0);      // :460 / :479
+                // the diffusion sub-step is the same whether it ends at a jump or at T; the jump factor is evaluated on
+                // every lane (a lane that closes its path discards it): cheaper than running the two cases one after
+                // the other on half a warp each
+                const R u = st.Sf + st.dx(C, st.Sf, d, dW);              // :465 / :481
+                if (FN == FN_AVG) st.Gf = st.Gf + st.half_area(st.Sf, d) + st.half_area(u, d);   // :532-534 / :554-556
+                const R J = (R)exp_bounded(C, fma(C.js, (double)zq, C.jm));                       // 1 + dJ  :462
+                st.Sf = jump ? u * J : u;
+                if (FN == FN_MIN) st.Gf = min_<R>(st.Gf, st.Sf);         // :621 / :637
                 if (jump) {
-                    st.template jump_pre<false>(C, d, dW, JD<R, FN, AR_FAST, SCH>::jump_size(C, zq));
+                    // the coarse path of a one-step level takes the very increments of the fine one at a jump and does
+                    // not move otherwise: it IS the fine state after the jump (:468, :622)
+                    st.Sc = st.Sf; st.Gc = st.Gf;
                     t = tau; ++k;
                 } else {
-                    st.grid_pre(C, d, dW);
                     double vf, vc, gf, gc;
                     st.outputs(C, vf, vc, gf, gc);
                     emit_t<FN>(C, i, vf, vc, gf, gc, acc, Pf_out, Pc_out);
