@@ -133,6 +133,7 @@ int make_consts(const mlmcb_params* p, int model, int payoff, int l, int M, ull 
     C->poly_q4 = MLMCB_Q4; C->poly_c4 = MLMCB_C4;
     C->inv_blk_dt = 1.0 / (4.0 * C->dt);
     C->inv_sqrt_dt = 1.0 / C->sqrt_dt;
+    C->inv_T = 1.0 / C->T;
     C->run_blocks = run_blocks_for(C->nsteps);
     // table-driven fp64 Box-Muller (tools/gen_f64bm_tables.py): G(x) = x + x^2 Q(x); sin(pi d)/d and (cos(pi d) - 1)/d^2 in d^2
     static const double lq[5] = {0x1.fffffffffeaabp-3, 0x1.555555555430cp-4, 0x1.00002aaab1aabp-5, 0x1.9999e2be38548p-7, 0.0};

@@ -113,6 +113,7 @@ struct LevelConsts {
     double lam, inv_lam, jm, js;
     double inv_blk_dt;              // 1/(4*dt): jump time -> block index
     double inv_sqrt_dt;             // factor walk: rho = sqrt(d2) / sqrt(dt)
+    double inv_T;                   // Merton average: Af/T as a multiplication (production arithmetic)
     uint32_t run_blocks;            // event-driven Merton walk: iterations of the advance phase between event phases
     double* raw;                    // optional [rows][n_paths] path-function outputs (Option.path), else NULL
     double r, boundary_c, amer_cneg;  // American put: rate, boundary constant, -2/(sig^2 dt); discounting inside the path, exercise boundary constant
@@ -1077,7 +1078,7 @@ struct JD {
     __device__ __forceinline__ void outputs(const LevelConsts& C, double& vf, double& vc, double& gf, double& gc) const {
         if (FN == FN_AVG) {
             if (AR == AR_EXACT) { vf = __ddiv_rn((double)Gf, C.T); vc = __ddiv_rn((double)Gc, C.T); }   // :571
-            else { vf = (double)Gf / C.T; vc = (double)Gc / C.T; }
+            else { vf = (double)Gf * C.inv_T; vc = (double)Gc * C.inv_T; }   // production arithmetic: no fp64 division per path
             gf = gc = 0.0;
         } else {
             vf = (double)Sf; vc = (double)Sc; gf = (double)Gf; gc = (double)Gc;
@@ -1908,7 +1909,7 @@ struct FactorWalk {
         }
     }
     __device__ __forceinline__ void outputs(double& vf, double& vc, double& gf, double& gc) const {
-        if (FN == FN_AVG) { vf = Gf / C.T; vc = Gc / C.T; gf = gc = 0.0; }       // :571
+        if (FN == FN_AVG) { vf = Gf * C.inv_T; vc = Gc * C.inv_T; gf = gc = 0.0; }       // :571
         else { vf = Sf; vc = Sc; gf = Gf; gc = Gc; }
     }
 };
