@@ -68,6 +68,9 @@
 #ifndef MLMCB_PIPE_G
 #define MLMCB_PIPE_G 2             // octets per stage of the software-pipelined fp64 GBM loop (the long-path kernel)
 #endif
+#ifndef MLMCB_PIPE_SHORT
+#define MLMCB_PIPE_SHORT 1         // the same pipeline across paths in the four-step kernel (1-3 %)
+#endif
 #ifndef MLMCB_PIPE_FROM
 #define MLMCB_PIPE_FROM 1024       // fine steps from which GBM levels take the long-path kernel (64 steps: 20 % slower, 256: equal, 1024+: 2-3 % faster)
 #endif
@@ -428,6 +431,17 @@ struct PhiloxSource {
         U4 w[3];
         words8(o, w);
         affine8(w, t, a0, b0);
+    }
+    // the first half of octet 0 (a four-step path) in the same two halves: two Philox blocks, two pairs -> four normals
+    __device__ __forceinline__ void words4(U4 w[2], uint32_t kind = STREAM_GRID) const {
+        w[0] = philox_at(C, pid, kind, 0u);
+        w[1] = philox_at(C, pid, kind, 1u);
+    }
+    __device__ __forceinline__ void normals4(const U4 w[2], R z[4]) const {
+        double d0, d1, d2, d3;
+        bm_pair_f64<false>(C, w[0].x, w[0].y, w[0].z, d0, d1);
+        bm_pair_f64<false>(C, w[0].w, w[1].x, w[1].y, d2, d3);
+        z[0] = (R)d0; z[1] = (R)d1; z[2] = (R)d2; z[3] = (R)d3;
     }
     // the same in two halves - the integer half (three Philox blocks) and the FP64 half (four pairs) - so that a
     // loop can draw the words of its NEXT octets next to the floating-point work of the current ones
@@ -2355,9 +2369,19 @@ __device__ __forceinline__ void gbm_packed_body(const LevelConsts& C, unsigned b
         const StepCoef<R, SCH> co(C);
         const R X0 = (R)C.X0;
         const double h0 = 0.5 * C.X0;
+        // fp64 sampler: the words of the thread's NEXT path are drawn in the body that turns the current ones into
+        // normals (integer work next to FP64 work, see gbm_path_fast PIPE)
+        U4 wcur[2] = {}, wnext[2] = {};
+        if (SAMP == SAMP_F64BM && MLMCB_PIPE_SHORT && tid < C.n_paths) PhiloxSource<R, SAMP>{C, C.path_offset + tid}.words4(wcur);
         for (ull i = tid; i < C.n_paths; i += stride) {
             R z[4];
-            PhiloxSource<R, SAMP>{C, C.path_offset + i}.load4(0, z);
+            if (SAMP == SAMP_F64BM && MLMCB_PIPE_SHORT) {
+                PhiloxSource<R, SAMP>{C, C.path_offset + i + stride}.words4(wnext);      // one path past the end on the last pass: unused
+                PhiloxSource<R, SAMP>{C, 0}.normals4(wcur, z);
+                wcur[0] = wnext[0]; wcur[1] = wnext[1];
+            } else {
+                PhiloxSource<R, SAMP>{C, C.path_offset + i}.load4(0, z);
+            }
             R Xf = X0, Xc = X0;
             R Ff = FN == FN_MIN ? X0 : (R)0, Fc = Ff;
 #pragma unroll
@@ -2428,7 +2452,7 @@ __device__ __forceinline__ void gbm_packed_body(const LevelConsts& C, unsigned b
             // (in_first <= c < in_end) run without bounds tests or stores; the at most two ragged groups at the ends
             // of the id range take the checked path on two threads of the grid.
             const ull in_first = (lo + 3) >> 2, in_end = hi >> 2;
-            for (ull c = in_first + tid; c < in_end; c += stride) {
+            for (ull c = in_first + tid; c < in_end; c += stride) {         // (pipelining this loop across groups measured 2-5 % slower)
                 R z[4];
                 PhiloxSource<R, SAMP>{C, c}.load4_stream(STREAM_PACK, 0, z);
 #pragma unroll
