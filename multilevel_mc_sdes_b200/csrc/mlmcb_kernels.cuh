@@ -1835,37 +1835,38 @@ struct FactorWalk {
         Gf = Gc = FN == FN_MIN ? C.X0 : 0.0;
         tsum = 0.0; dtc = 0.0; h = C.dt; rho = 1.0; kappa = 0.0;
     }
-    // the jumps of fine step j known so far (:457-474), lanes that have one only
+    // this lane's next record: the sub-step to the jump and the jump itself, on both paths (:458-474)
+    __device__ __forceinline__ void apply_record() {
+        const double t1 = bs.rec[FW_T1][jk], J = bs.rec[FW_J][jk];
+        rho = bs.rec[FW_RHO][jk]; kappa = bs.rec[FW_KAPPA][jk];
+        tsum += t1;
+        if (FN == FN_AVG) {                                              // :532-540
+            const double d1 = bs.rec[FN == FN_AVG ? FW_D1 : 0][jk];
+            h = bs.rec[FN == FN_AVG ? FW_D2 : 0][jk];
+            dtc += d1;
+            const double uf = fma(Sf, t1, Sf), uc = fma(Sc, tsum, Sc);
+            Gf = fma(0.5 * d1, Sf + uf, Gf);
+            Gc = fma(0.5 * dtc, Sc + uc, Gc);
+            Sf = uf * J; Sc = uc * J;
+            dtc = 0.0;
+        } else {                                                         // :465-468, :621-622
+            Sf = fma(Sf, t1, Sf) * J;
+            Sc = fma(Sc, tsum, Sc) * J;
+            if (FN == FN_MIN) { Gf = min_<double>(Gf, Sf); Gc = min_<double>(Gc, Sc); }
+        }
+        tsum = 0.0;
+        ++jk;
+        jnext = bs.step[jk];
+    }
+    // the jumps of fine step j known so far (:457-474), lanes that have one only; every lane of the warp calls it
     __device__ __forceinline__ void jumps(int j) {
         while (__any_sync(0xffffffffu, jnext == j)) {
-            if (jnext == j) {
-                const double t1 = bs.rec[FW_T1][jk], J = bs.rec[FW_J][jk];
-                rho = bs.rec[FW_RHO][jk]; kappa = bs.rec[FW_KAPPA][jk];
-                tsum += t1;
-                if (FN == FN_AVG) {                                      // :532-540
-                    const double d1 = bs.rec[FN == FN_AVG ? FW_D1 : 0][jk];
-                    h = bs.rec[FN == FN_AVG ? FW_D2 : 0][jk];
-                    dtc += d1;
-                    const double uf = fma(Sf, t1, Sf), uc = fma(Sc, tsum, Sc);
-                    Gf = fma(0.5 * d1, Sf + uf, Gf);
-                    Gc = fma(0.5 * dtc, Sc + uc, Gc);
-                    Sf = uf * J; Sc = uc * J;
-                    dtc = 0.0;
-                } else {                                                 // :465-468, :621-622
-                    Sf = fma(Sf, t1, Sf) * J;
-                    Sc = fma(Sc, tsum, Sc) * J;
-                    if (FN == FN_MIN) { Gf = min_<double>(Gf, Sf); Gc = min_<double>(Gc, Sc); }
-                }
-                tsum = 0.0;
-                ++jk;
-                jnext = bs.step[jk];
-            }
+            if (jnext == j) apply_record();
         }
     }
-    // fine step j: its jumps, then the step to the grid time (:477-487); t = a + b z_j
+    // the step to the grid time that closes fine step j (:477-487); t = a + b z_j
     template <bool COARSE_END>
-    __device__ __forceinline__ void step(int j, double t) {
-        jumps(j);
+    __device__ __forceinline__ void close(double t) {
         const double tt = fma(rho, t, kappa);
         if (FN == FN_AVG) {                                              // :554-556
             const double uf = fma(Sf, tt, Sf);
@@ -1890,6 +1891,55 @@ struct FactorWalk {
                 if (FN == FN_MIN) Gc = min_<double>(Gc, Sc);
             }
             tsum = 0.0;
+        }
+    }
+    // fine step j: its jumps, then the closing step; every lane of the warp calls it
+    template <bool COARSE_END>
+    __device__ __forceinline__ void step(int j, double t) {
+        jumps(j);
+        close<COARSE_END>(t);
+    }
+    // A whole octet that every lane may close and in which SOME lanes have jumps: per coarse interval, the lanes that
+    // have a jump in it walk its MT steps on their own (the very operations of step(), so a path's value does not depend
+    // on which of the two forms ran) and turn their factors of the interval into no-ops; then every lane runs the
+    // jump-free interval.  A lane without jumps never waits for more than the few lanes' MT steps.
+    __device__ __forceinline__ void mixed_octet(int j0, double t[8]) {
+        const double mdt = MT == 4 ? ((C.dt + C.dt) + C.dt) + C.dt : C.dt + C.dt;
+#pragma unroll
+        for (int g = 0; g < 8; g += MT) {
+            double tc = MT == 4 ? ((t[g] + t[g + 1]) + t[g + 2]) + t[g + 3] : t[g] + t[g + 1];
+            double hdt = 0.5 * C.dt, hmdt = 0.5 * mdt;                   // FN_AVG: zero on a lane that walked the interval itself
+            if (__any_sync(0xffffffffu, jnext <= j0 + g + MT)) {
+                if (jnext <= j0 + g + MT) {
+#pragma unroll
+                    for (int k = 0; k < MT; ++k) {
+                        while (jnext == j0 + g + k + 1) apply_record();
+                        if (k == MT - 1) close<true>(t[g + k]);
+                        else close<false>(t[g + k]);
+                        t[g + k] = 0.0;
+                    }
+                    tc = 0.0; hdt = 0.0; hmdt = 0.0;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < MT; ++k) {
+                if (FN == FN_AVG) {
+                    const double uf = fma(Sf, t[g + k], Sf);
+                    Gf = fma(hdt, Sf + uf, Gf);
+                    Sf = uf;
+                } else {
+                    Sf = fma(Sf, t[g + k], Sf);
+                    if (FN == FN_MIN) Gf = min_<double>(Gf, Sf);
+                }
+            }
+            if (FN == FN_AVG) {
+                const double uc = fma(Sc, tc, Sc);
+                Gc = fma(hmdt, Sc + uc, Gc);
+                Sc = uc;
+            } else {
+                Sc = fma(Sc, tc, Sc);
+                if (FN == FN_MIN) Gc = min_<double>(Gc, Sc);
+            }
         }
     }
     // an octet in which no lane has a jump (tsum = 0, dtc = 0 on entry and on exit).  The arithmetic is that of step()
@@ -2049,6 +2099,16 @@ __device__ __forceinline__ void mjd_factor_body(const LevelConsts& C, unsigned b
                 double tq[8];
                 if (nsteps >= 8) {
                     src.load8(o, tq);
+                    // a whole closable octet with jumps in some lanes.  (Final-value products only: with the trapezoid or
+                    // the running minimum in the 128-register budget the extra code costs the short levels 1-2 % and
+                    // gains 3-5 % from 128 steps on - measured, not kept.)
+                    if constexpr (FN == FN_FINAL) {
+                        if (((j_cur - 1) & 7) == 0 && !mid && (int)(o << 3) + 8 <= hz) {
+                            w.mixed_octet((int)(o << 3), tq);
+                            j_cur += 8;
+                            continue;
+                        }
+                    }
                 } else {
                     src.load_head(nsteps >> 1, tq);
                     if (hz == nsteps && j_cur == 1) {                   // the whole path in one go (2 or 4 steps)
