@@ -62,6 +62,9 @@
 #ifndef MLMCB_UNROLL_FW
 #define MLMCB_UNROLL_FW 1           // Merton factor walk: jump-free octets in flight per thread (2 measured equal at 128 registers)
 #endif
+#ifndef MLMCB_FW_MIXED_FROM
+#define MLMCB_FW_MIXED_FROM 32      // Merton factor walk: from this many fine steps mixed octets let the jump lanes walk alone (8, 16 steps: 2 %,
+#endif                              // nearly every lane has a jump in every octet there and all lanes stay busy step by step)
 #ifndef MLMCB_FW_SLOTS
 #define MLMCB_FW_SLOTS 128          // Merton factor walk: record slots per warp
 #endif
@@ -2103,7 +2106,7 @@ __device__ __forceinline__ void mjd_factor_body(const LevelConsts& C, unsigned b
                     // the running minimum in the 128-register budget the extra code costs the short levels 1-2 % and
                     // gains 3-5 % from 128 steps on - measured, not kept.)
                     if constexpr (FN == FN_FINAL) {
-                        if (((j_cur - 1) & 7) == 0 && !mid && (int)(o << 3) + 8 <= hz) {
+                        if (nsteps >= MLMCB_FW_MIXED_FROM && ((j_cur - 1) & 7) == 0 && !mid && (int)(o << 3) + 8 <= hz) {
                             w.mixed_octet((int)(o << 3), tq);
                             j_cur += 8;
                             continue;
