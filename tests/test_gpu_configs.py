@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 import multilevel_mc_sdes_b200 as mm
+from multilevel_mc_sdes_b200 import _lib
 from tests.conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
@@ -123,3 +124,30 @@ def test_config2_asian_mlmc_tight(cuda_lib):
     opt = mm.Asian_GBM(verbose=False, seed=5)
     sums, N = opt.mlmc(1e-3, M=4)
     assert abs(float(np.sum(sums[0] / N)) - 5.7630) < 3e-3
+
+
+def test_pipe_and_mix_probes(cuda_lib):
+    """The probes behind the roofline line (bench.py `roofline.pipe_probe`): every mode runs, the measured
+    issue intervals are the ones the model rests on - IMAD.WIDE and LOP3 as long as DFMA (two SMSP cycles per warp
+    instruction), FFMA half, IMAD.HI twice that, DFMA+LOP3 overlapping and DFMA+IMAD.WIDE additive - and the loop's
+    mix finely interleaved beats the same mix on specialised warps."""
+    import ctypes as C
+
+    def interval(which):        # seconds per warp instruction per GPU: only ratios are used (clock-independent)
+        ips, ms = C.c_double(), C.c_float()
+        _lib.check(cuda_lib.mlmcb_pipe_probe(which, 0, C.byref(ips), C.byref(ms)))
+        return 1.0 / ips.value
+
+    dfma, ffma, wide, lop3, hi = interval(0), interval(2), interval(3), interval(4), interval(15)
+    assert 0.8 < wide / dfma < 1.25 and 0.8 < lop3 / dfma < 1.25 and 0.4 < ffma / dfma < 0.65 and 1.6 < hi / dfma < 2.4
+    pair_lop3, pair_wide = 2 * interval(9), 2 * interval(10)
+    assert pair_lop3 < dfma + 0.6 * lop3          # mostly overlapped
+    assert pair_wide > 0.85 * (dfma + wide)       # additive: IMAD.WIDE shares the FP64 pipe's port
+    with pytest.raises(ValueError):
+        _lib.check(cuda_lib.mlmcb_pipe_probe(99, 0, None, None))
+    t = []
+    for mode in (0, 1):
+        ms = C.c_float()
+        _lib.check(cuda_lib.mlmcb_mix_probe(mode, 0, 20000, C.byref(ms)))
+        t.append(ms.value)
+    assert 0 < t[0] < t[1]
