@@ -258,9 +258,11 @@ def run_b200(args):
     # ---- the second half of BASELINE.json's metric: mlmc(eps) wall time, on all N GPUs ----------------
     mlmc_wall = {}
     for name, ctor, eps, kw in (("asian_gbm_eps1e-4_M4", lambda: mm.Asian_GBM(verbose=False, device=local, distributed=world > 1), 1e-4, dict(M=4)),
-                                ("readme_euro_gbm_eps0.01", lambda: mm.Euro_GBM(verbose=False, device=local, distributed=world > 1, **OPT_KW), 0.01, {})):
+                                ("readme_euro_gbm_eps0.01", lambda: mm.Euro_GBM(verbose=False, device=local, distributed=world > 1, **OPT_KW), 0.01, {}),
+                                # BASELINE config #4 (Merton factor walk + the l = 0 loop): one run, about 5 s on one GPU
+                                ("digital_merton_eps1e-3_M2", lambda: mm.Digital_Merton(beta_0=0.5, verbose=False, device=local, distributed=world > 1), 1e-3, dict(M=2))):
         best = None
-        for rep in range(2):                       # second run: warm library state (pools, pinned buffers, NCCL)
+        for rep in range(1 if name.startswith("digital_merton") else 2):   # second run: warm library state (pools, pinned buffers, NCCL)
             o = ctor()
             barrier()
             t0 = time.perf_counter()
@@ -270,6 +272,7 @@ def run_b200(args):
                 best = {"seconds": dt_m, "price": float(np.sum(sums_m[0] / N_m)), "levels": len(N_m), "samples": float(N_m.sum())}
         mlmc_wall[name] = best
     mlmc_wall["readme_euro_gbm_eps0.01"]["BS"] = 35.17419437739385
+    mlmc_wall["digital_merton_eps1e-3_M2"]["exact"] = 44.77499       # Poisson mixture of Black-Scholes digitals (tests/test_gpu_configs.py)
     mlmc_wall["sampler"] = "f64bm (default)"
 
     # ---- fixed total work split over the GPUs (what can bend as N grows) ------------------------------
