@@ -10,7 +10,7 @@ Files
                       seed; small cases also carry the literal normals Z[step,path] the
                       reference consumed (np.random.randn wrapped while the reference ran)
   payoffs_anti_milstein.npz  anti_payoff with the notebook's Milstein stepper bound over `sde`
-  payoffs_merton_deep.npz    the 4 Merton products at 128 / 256 fine steps (l=7,8 M=2; l=4 M=4)
+  payoffs_merton_deep.npz    the 4 Merton products at 128 / 256 fine steps (l=7,8 M=2; l=4 M=4) and at 512 / 1024 (l=9 M=2; l=5 M=4)
   payoffs_merton.npz  same for the 4 Merton products with the three ragged draw streams
                       (dW normals, jump-size normals, inter-arrival times) in CSR layout
   looper.npz          `opt.looper(Nl,l,M,False,Npl)` 7-vectors for seeds
@@ -317,48 +317,47 @@ def anti_milstein_cases(ref):
 
 
 def merton_deep_cases(ref):
-    """JD_path* (:428-651) at 128 and 256 fine steps - the regime the block-uniform Merton walk serves
-    (l = 7, 8 with M = 2; l = 4 with M = 4).  Same layout as payoffs_merton.npz."""
+    """JD_path* (:428-651) at 128 and 256 fine steps (l = 7, 8 with M = 2; l = 4 with M = 4) and, 8 paths each, at
+    512 and 1024 (l = 9, M = 2; l = 5, M = 4) - the long-path regime.  Same layout as payoffs_merton.npz."""
     out = {}
     idx = 0
-    for cname in MJD_CLASSES:
-        for kw_name, kw in (("default", {}), ("alt", ALT_MJD)):
-            for (l, M) in ((7, 2), (8, 2), (4, 4)):
-                if kw_name == "alt" and l == 8:
-                    continue
-                n = 24
-                seed = 5600 + idx
-                kw2 = dict(kw)
-                if cname == "Lookback_Merton":
-                    kw2.pop("K", None)
-                opt = getattr(ref, cname)(**kw2)
-                np.random.seed(seed)
-                Pf_all, Pc_all, zw, zq, ex = [], [], [], [], []
-                for _ in range(n):
-                    with Tap() as tap:
-                        tap.wrap_jumptime(opt)
-                        Pf, Pc = opt.payoff(1, l, M)
-                        opt.jumptime = np.random.exponential
-                    Pf_all.append(float(Pf[0]))
-                    Pc_all.append(float(np.asarray(Pc).reshape(-1)[0]))
-                    zw.append([float(v) for v in tap.randn_calls])
-                    zq.append(tap.stdn)
-                    ex.append(tap.expo)
+    # the 512- and 1024-step cases were appended later: they come last so that the earlier cases keep their seeds
+    plan = [(cname, kw_name, kw, l, M, 24) for cname in MJD_CLASSES for kw_name, kw in (("default", {}), ("alt", ALT_MJD))
+            for (l, M) in ((7, 2), (8, 2), (4, 4)) if not (kw_name == "alt" and l == 8)]
+    plan += [(cname, "default", {}, l, M, 8) for cname in MJD_CLASSES for (l, M) in ((9, 2), (5, 4))]
+    for cname, kw_name, kw, l, M, n in plan:
+        seed = 5600 + idx
+        kw2 = dict(kw)
+        if cname == "Lookback_Merton":
+            kw2.pop("K", None)
+        opt = getattr(ref, cname)(**kw2)
+        np.random.seed(seed)
+        Pf_all, Pc_all, zw, zq, ex = [], [], [], [], []
+        for _ in range(n):
+            with Tap() as tap:
+                tap.wrap_jumptime(opt)
+                Pf, Pc = opt.payoff(1, l, M)
+                opt.jumptime = np.random.exponential
+            Pf_all.append(float(Pf[0]))
+            Pc_all.append(float(np.asarray(Pc).reshape(-1)[0]))
+            zw.append([float(v) for v in tap.randn_calls])
+            zq.append(tap.stdn)
+            ex.append(tap.expo)
 
-                def csr(rows):
-                    off = np.zeros(len(rows) + 1, dtype=np.int64)
-                    off[1:] = np.cumsum([len(r) for r in rows])
-                    return np.array([v for r in rows for v in r], dtype=np.float64), off
+        def csr(rows):
+            off = np.zeros(len(rows) + 1, dtype=np.int64)
+            off[1:] = np.cumsum([len(r) for r in rows])
+            return np.array([v for r in rows for v in r], dtype=np.float64), off
 
-                key = f"c{idx}"
-                out[key + "_meta"] = np.array([cname, kw_name, str(l), str(M), str(n), str(seed)])
-                out[key + "_Pf"] = np.array(Pf_all)
-                out[key + "_Pc"] = np.array(Pc_all)
-                for nm, rows in (("W", zw), ("Q", zq), ("E", ex)):
-                    flat, off = csr(rows)
-                    out[key + "_z" + nm] = flat
-                    out[key + "_off" + nm] = off
-                idx += 1
+        key = f"c{idx}"
+        out[key + "_meta"] = np.array([cname, kw_name, str(l), str(M), str(n), str(seed)])
+        out[key + "_Pf"] = np.array(Pf_all)
+        out[key + "_Pc"] = np.array(Pc_all)
+        for nm, rows in (("W", zw), ("Q", zq), ("E", ex)):
+            flat, off = csr(rows)
+            out[key + "_z" + nm] = flat
+            out[key + "_off" + nm] = off
+        idx += 1
     out["n_cases"] = np.array(idx)
     return out
 

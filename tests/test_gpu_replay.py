@@ -163,7 +163,8 @@ def test_antithetic_replay_with_milstein_stepper(golden, cuda_lib):
 
 
 def test_merton_replay_deep_levels(golden, cuda_lib):
-    """Reference fixtures at 128 and 256 fine steps (l = 7, 8 at M = 2; l = 4 at M = 4), both policies."""
+    """Reference fixtures at 128 and 256 fine steps (l = 7, 8 at M = 2; l = 4 at M = 4) and at 512 and 1024 (l = 9 at
+    M = 2; l = 5 at M = 4), both policies."""
     n = 0
     for c in merton_cases(golden["payoffs_merton_deep"]):
         p = oracle_params(c["cname"], c["kw_name"])
@@ -175,7 +176,7 @@ def test_merton_replay_deep_levels(golden, cuda_lib):
                 assert np.all(np.abs(Pf - c["Pf"]) <= payoff_tol(p, c["Pf"])), (c["idx"], arith, np.abs(Pf - c["Pf"]).max())
                 assert np.all(np.abs(Pc - c["Pc"]) <= payoff_tol(p, c["Pc"])), (c["idx"], arith, np.abs(Pc - c["Pc"]).max())
         n += 1
-    assert n == 20
+    assert n == 28
 
 
 def test_milstein_replay(golden, cuda_lib):

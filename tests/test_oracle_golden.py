@@ -144,7 +144,8 @@ def test_oracles_antithetic_with_milstein_stepper(golden, c_oracle):
 
 
 def test_oracles_merton_deep_levels(golden, c_oracle):
-    """128 / 256 fine steps (l = 7, 8 at M = 2; l = 4 at M = 4): numpy restatement bit-exact, C port to libm's exp."""
+    """128 / 256 fine steps (l = 7, 8 at M = 2; l = 4 at M = 4) and 512 / 1024 (l = 9 at M = 2; l = 5 at M = 4):
+    numpy restatement bit-exact, C port to libm's exp."""
     n = 0
     for c in merton_cases(golden["payoffs_merton_deep"]):
         model, pay = CLASS_CODES[c["cname"]]
@@ -156,7 +157,7 @@ def test_oracles_merton_deep_levels(golden, c_oracle):
         np.testing.assert_allclose(Pf, c["Pf"], rtol=0, atol=2e-13 * p.X0)
         np.testing.assert_allclose(Pc, c["Pc"], rtol=0, atol=2e-13 * p.X0)
         n += 1
-    assert n == 20
+    assert n == 28
 
 
 def test_oracles_milstein(golden, c_oracle):
