@@ -553,8 +553,9 @@ def test_philox_mode_equals_replay_of_its_own_draws_merton(cuda_lib, lam, sample
     """Exercises the jump-free run length agreement, the jump blocks and the tail of the block-uniform kernel,
     the event-driven kernel and the l = 0 loop against the straightforward replay loop."""
     for cls in (mm.Euro_Merton, mm.Asian_Merton, mm.Lookback_Merton):
-        # 1 step: lane-queue loop; 2, 8, 9, 32, 64: event-driven kernel; 128, 256: block-uniform kernel
-        for l, M in ((0, 2), (1, 2), (3, 2), (3, 4), (2, 3), (5, 2), (7, 2), (4, 4)):
+        # 1 step: lane-queue loop; 9 (M = 3): event-driven walk; everything else: the factor walk - 2 steps in one go, 8 and
+        # 32 step by step, 64 .. 512 with jump-free runs and (final-value products) mixed octets; lam = 6 needs record rounds
+        for l, M in ((0, 2), (1, 2), (3, 2), (3, 4), (2, 3), (5, 2), (7, 2), (4, 4), (9, 2)):
             _merton_own_draws_case(cuda_lib, cls, dict(lam=lam), l, M, sampler=sampler)
 
 
