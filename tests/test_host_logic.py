@@ -234,3 +234,29 @@ def test_flag_combinations_are_checked_before_the_device():
     assert geo(_lib.FP32_PATHS | _lib.MILSTEIN) == _lib.ENOTIMPL               # Milstein: fp64 path arithmetic only
     assert b"Milstein" in lib.mlmcb_last_error()
     assert _lib.SAMPLER_F64BM == 0                                              # flags == 0 is the all-fp64 kernel
+
+
+def test_f64_sampler_tables_match_their_generator():
+    """csrc/mlmcb_f64tab.inc and the polynomial coefficients compiled into mlmcb_api.cu are exactly what
+    tools/gen_f64bm_tables.py produces (60-digit arithmetic, rounded once), and a sample of pairs emulated in
+    float64 / long-double FMA stays within 2e-15 of the 60-digit normals."""
+    pytest.importorskip("mpmath")
+    import re
+    import sys
+    tools = os.path.join(ROOT, "tools")
+    sys.path.insert(0, tools)
+    try:
+        import gen_f64bm_tables as g
+    finally:
+        sys.path.remove(tools)
+    lg, tr = g.log_table(), g.trig_table()
+    lq, ts, tc = g.coefficients()
+    inc = open(os.path.join(ROOT, "multilevel_mc_sdes_b200", "csrc", "mlmcb_f64tab.inc")).read()
+    rows = re.findall(r"\{(-?0x[0-9a-f.]+p[+-]\d+), (-?0x[0-9a-f.]+p[+-]\d+)\}", inc)
+    assert len(rows) == len(lg) + len(tr) == 512
+    want = [(a.hex(), b.hex()) for a, b in lg + tr]
+    assert rows == want
+    api = open(os.path.join(ROOT, "multilevel_mc_sdes_b200", "csrc", "mlmcb_api.cu")).read()
+    for c in lq + ts + tc:
+        assert c.hex() in api, c.hex()
+    assert g.check(lg, tr, lq, ts, tc, n=1500) < 2e-15
