@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import np_oracle as O
-from tests.helpers import amer_cases, case_kwargs
+from tests.helpers import amer_cases, case_kwargs, payoff_tol
 from tests.helpers import (CLASS_CODES, anti_cases, gbm_cases, merton_cases, milstein_gbm_cases,
                            milstein_merton_cases, oracle_params, regen_Z)
 
@@ -204,3 +204,114 @@ def test_oracles_american_put(golden, c_oracle):
     with pytest.raises(ValueError, match="M must be equal to 2"):
         O.level_payoffs(O.Params(), O.GBM, O.AMERICAN, 2, 4, n=4)
     assert "M must be equal to 2" in str(g["bad_M_message"])
+
+
+def _factor_walk(p, functional, l, M, packed):
+    """The kernel's factor form of the jump-adapted scheme (csrc/mlmcb_kernels.cuh: FactorWalk) in plain
+    Python, on the reference's own draws.  A jump is the record (t1, J, rho, kappa[, d1, d2]) computed from the draws
+    alone; the walk multiplies: S_f (1 + t1) J at a jump, S_f (1 + kappa + rho t) to close a step (t = a + b z is the
+    factor the sampler delivers for the whole step), and the coarse path takes the SUM of the fine t's."""
+    N = M ** l
+    T, X0 = p.T, p.X0
+    mu = p.r - p.lam * p.J_bar
+    dt = T / N
+    sqrt_dt = np.sqrt(dt)
+    a, b = mu * dt, p.sig * sqrt_dt
+    n = len(packed["offW"]) - 1
+    out = [np.zeros(n) for _ in range(4)]
+    for i in range(n):
+        zW = packed["zW"][packed["offW"][i]:packed["offW"][i + 1]]
+        zQ = packed["zQ"][packed["offQ"][i]:packed["offQ"][i + 1]]
+        E = packed["E"][packed["offE"][i]:packed["offE"][i + 1]]
+        # ---- records: everything a jump does, before the walk (arrival times, then one record per arrival) ----
+        iw = iq = 0
+        tau = E[0]
+        ie = 1
+        recs = {}                 # step -> list of records
+        grid_z = {}
+        tprev, jprev = 0.0, 0
+        for j in range(1, N + 1):
+            tn = j * T / N                                          # :456
+            while tau < tn:                                         # :457
+                d1 = tau - (tprev if jprev == j else (j - 1) * T / N if j > 1 else 0.0)
+                d2 = tn - tau
+                t1 = mu * d1 + p.sig * (zW[iw] * np.sqrt(d1))
+                J = np.exp(p.jumpmean + p.jumpstd * zQ[iq])
+                rho = np.sqrt(d2) / sqrt_dt
+                recs.setdefault(j, []).append((t1, J, rho, mu * d2 - rho * a, d1, d2))
+                iw += 1
+                iq += 1
+                tprev, jprev = tau, j
+                tau += E[ie]
+                ie += 1
+            grid_z[j] = zW[iw]
+            iw += 1
+        # ---- walk ----
+        Sf = Sc = X0
+        Gf = Gc = X0 if functional == O.LOOKBACK else 0.0
+        tsum = dtc = 0.0
+        for j in range(1, N + 1):
+            rho, kappa, h = 1.0, 0.0, dt
+            for (t1, J, r_, k_, d1, d2) in recs.get(j, ()):
+                tsum += t1
+                if functional == O.ASIAN:
+                    dtc += d1
+                    uf, uc = Sf + Sf * t1, Sc + Sc * tsum
+                    Gf += 0.5 * d1 * (Sf + uf)
+                    Gc += 0.5 * dtc * (Sc + uc)
+                    Sf, Sc, dtc = uf * J, uc * J, 0.0
+                else:
+                    Sf, Sc = (Sf + Sf * t1) * J, (Sc + Sc * tsum) * J
+                    if functional == O.LOOKBACK:
+                        Gf, Gc = min(Gf, Sf), min(Gc, Sc)
+                tsum = 0.0
+                rho, kappa, h = r_, k_, d2
+            tt = kappa + rho * (a + b * grid_z[j])
+            uf = Sf + Sf * tt
+            if functional == O.ASIAN:
+                Gf += 0.5 * h * (Sf + uf)
+                dtc += h
+            Sf = uf
+            if functional == O.LOOKBACK:
+                Gf = min(Gf, Sf)
+            tsum += tt
+            if j % M == 0:
+                uc = Sc + Sc * tsum
+                if functional == O.ASIAN:
+                    Gc += 0.5 * dtc * (Sc + uc)
+                    dtc = 0.0
+                Sc = uc
+                if functional == O.LOOKBACK:
+                    Gc = min(Gc, Sc)
+                tsum = 0.0
+        out[0][i], out[1][i], out[2][i], out[3][i] = Sf, Gf, Sc, Gc
+    if functional == O.ASIAN:
+        return out[1] / T, out[3] / T
+    if functional == O.LOOKBACK:
+        return out[0], out[1], out[2], out[3]
+    return out[0], out[2]
+
+
+def test_factor_form_of_the_jump_adapted_scheme_reproduces_the_reference(golden):
+    """The algebra the Merton factor walk rests on - jumps as state-independent factors, the closing step affine in the
+    whole-step factor, the coarse increment as the sum of the fine ones - against the REFERENCE's per-path payoffs on
+    its own draws (fixtures made by oracle/make_golden.py from /root/reference): 1e-12 like the replay kernels, for the
+    four products at 1 .. 1024 fine steps, M = 2, 3 and 4."""
+    n = 0
+    for name in ("payoffs_merton", "payoffs_merton_deep"):
+        for c in merton_cases(golden[name]):
+            if c["idx"] % 2 and name == "payoffs_merton":
+                continue                                            # every other shallow case keeps the test quick
+            model, pay = CLASS_CODES[c["cname"]]
+            p = oracle_params(c["cname"], c["kw_name"])
+            path_out = _factor_walk(p, O.functional_of(pay), c["l"], c["M"], c["packed"])
+            Pf, Pc = O.apply_payoff(p, pay, c["l"], c["M"], path_out)
+            if c["l"] == 0:
+                Pc = c["Pc"]                                        # l = 0: the raw coarse output is not a payoff (:82)
+            if c["cname"] == "Digital_Merton":
+                assert np.array_equal(Pf, c["Pf"]) and np.array_equal(np.asarray(Pc, dtype=float), c["Pc"]), c["idx"]
+            else:
+                assert np.all(np.abs(Pf - c["Pf"]) <= payoff_tol(p, c["Pf"])), (name, c["idx"], np.abs(Pf - c["Pf"]).max())
+                assert np.all(np.abs(Pc - c["Pc"]) <= payoff_tol(p, c["Pc"])), (name, c["idx"], np.abs(Pc - c["Pc"]).max())
+            n += 1
+    assert n >= 60
